@@ -1,0 +1,408 @@
+// Host-side BC7 support (see bc7_host.h).
+#include "bc7_host.h"
+
+#include <algorithm>
+#include <string.h>
+
+#include "bc7_tables.inc"
+
+namespace cvttb200
+{
+    unsigned bc7_shape_mask(int shape) { return kBC7ShapeMask[shape]; }
+
+    static int popcount16(unsigned m)
+    {
+        int n = 0;
+        for (; m; m &= m - 1)
+            n++;
+        return n;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // plan configuration
+
+    void bc7_plan_default(BC7PlanPOD &plan)
+    {
+        memset(&plan, 0, sizeof(plan));
+        for (int i = 0; i < 243; i++)
+        {
+            plan.rgbShapeList[i] = (uint8_t)i;
+            plan.seedPointsForShapeRGB[i] = 4;
+        }
+        plan.rgbNumShapesToEvaluate = 243;
+        for (int i = 0; i < 129; i++)
+        {
+            plan.rgbaShapeList[i] = (uint8_t)i;
+            plan.seedPointsForShapeRGBA[i] = 4;
+        }
+        plan.rgbaNumShapesToEvaluate = 129;
+        plan.mode0PartitionEnabled = 0xffff;
+        plan.mode1PartitionEnabled = plan.mode2PartitionEnabled = plan.mode3PartitionEnabled = ~(uint64_t)0;
+        plan.mode6Enabled = 1;
+        plan.mode7RGBPartitionEnabled = plan.mode7RGBAPartitionEnabled = ~(uint64_t)0;
+        for (int r = 0; r < 4; r++)
+        {
+            plan.mode4SP[r][0] = plan.mode4SP[r][1] = 4;
+            plan.mode5SP[r] = 4;
+        }
+    }
+
+    namespace
+    {
+        struct ShapeSeeds
+        {
+            BC7PlanPOD &plan;
+            void rgb(int shape, uint8_t sp) { plan.seedPointsForShapeRGB[shape] = std::max(plan.seedPointsForShapeRGB[shape], sp); }
+            void rgba(int shape, uint8_t sp) { plan.seedPointsForShapeRGBA[shape] = std::max(plan.seedPointsForShapeRGBA[shape], sp); }
+        };
+    }
+
+    bool bc7_plan_from_fine_tuning(BC7PlanPOD &plan, const BC7FineTuningPOD &params)
+    {
+        memset(&plan, 0, sizeof(plan));
+        ShapeSeeds seeds = { plan };
+
+        // three-subset modes take their shapes from kBC7Shapes3, two-subset modes from kBC7Shapes2
+        for (int p = 0; p < 16; p++)
+            if (uint8_t sp = params.mode0SP[p])
+            {
+                plan.mode0PartitionEnabled |= (uint16_t)(1u << p);
+                for (int k = 0; k < 3; k++)
+                    seeds.rgb(kBC7Shapes3[p * 3 + k], sp);
+            }
+        for (int p = 0; p < 64; p++)
+        {
+            const uint64_t bit = (uint64_t)1 << p;
+            if (uint8_t sp = params.mode1SP[p])
+            {
+                plan.mode1PartitionEnabled |= bit;
+                seeds.rgb(kBC7Shapes2[p * 2], sp);
+                seeds.rgb(kBC7Shapes2[p * 2 + 1], sp);
+            }
+            if (uint8_t sp = params.mode2SP[p])
+            {
+                plan.mode2PartitionEnabled |= bit;
+                for (int k = 0; k < 3; k++)
+                    seeds.rgb(kBC7Shapes3[p * 3 + k], sp);
+            }
+            if (uint8_t sp = params.mode3SP[p])
+            {
+                plan.mode3PartitionEnabled |= bit;
+                seeds.rgb(kBC7Shapes2[p * 2], sp);
+                seeds.rgb(kBC7Shapes2[p * 2 + 1], sp);
+            }
+            if (uint8_t sp = params.mode7SP[p])
+            {
+                plan.mode7RGBAPartitionEnabled |= bit;
+                seeds.rgba(kBC7Shapes2[p * 2], sp);
+                seeds.rgba(kBC7Shapes2[p * 2 + 1], sp);
+            }
+        }
+        memcpy(plan.mode4SP, params.mode4SP, sizeof(plan.mode4SP));
+        memcpy(plan.mode5SP, params.mode5SP, sizeof(plan.mode5SP));
+        if (params.mode6SP)
+        {
+            plan.mode6Enabled = 1;
+            seeds.rgba(0, params.mode6SP);
+        }
+
+        for (int s = 0; s < 243; s++)
+            if (plan.seedPointsForShapeRGB[s])
+                plan.rgbShapeList[plan.rgbNumShapesToEvaluate++] = (uint8_t)s;
+        for (int s = 0; s < 129; s++)
+            if (plan.seedPointsForShapeRGBA[s])
+                plan.rgbaShapeList[plan.rgbaNumShapesToEvaluate++] = (uint8_t)s;
+
+        plan.mode7RGBPartitionEnabled = plan.mode7RGBAPartitionEnabled & ~plan.mode3PartitionEnabled;
+        return true;
+    }
+
+    void bc7_plan_from_quality(BC7PlanPOD &plan, int quality)
+    {
+        quality = std::min(100, std::max(1, quality));
+
+        BC7FineTuningPOD ft;
+        memset(&ft, 0, sizeof(ft));
+
+        const unsigned short *lists[2] = { kBC7PrioRGB, kBC7PrioRGBA };
+        const int counts[2] = { CVTT_BC7_NUM_PRIO_RGB * quality / 100, CVTT_BC7_NUM_PRIO_RGBA * quality / 100 };
+        for (int li = 0; li < 2; li++)
+            for (int i = 0; i < counts[li]; i++)
+            {
+                // tools/gen_tables.py: (seedPoints - 1) << 9 | mode << 6 | (partition, or rotation | indexSelector << 2)
+                const unsigned code = lists[li][i];
+                const uint8_t sp = (uint8_t)(((code >> 9) & 3) + 1);
+                const int sub = code & 63;
+                switch ((code >> 6) & 7)
+                {
+                case 0: ft.mode0SP[sub] = sp; break;
+                case 1: ft.mode1SP[sub] = sp; break;
+                case 2: ft.mode2SP[sub] = sp; break;
+                case 3: ft.mode3SP[sub] = sp; break;
+                case 4: ft.mode4SP[sub & 3][(sub >> 2) & 1] = sp; break;
+                case 5: ft.mode5SP[sub & 3] = sp; break;
+                case 6: ft.mode6SP = sp; break;
+                case 7: ft.mode7SP[sub] = sp; break;
+                }
+            }
+        bc7_plan_from_fine_tuning(plan, ft);
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // command stream
+
+    namespace
+    {
+        struct Run { int mode, seeds, slot; };
+
+        void emit_shape(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, int shape, const std::vector<Run> &runs)
+        {
+            bool inRGBList = false, inRGBAList = false, anyRGB = false, anyRGBA = false;
+            for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
+                inRGBList |= (plan.rgbShapeList[i] == shape);
+            for (int i = 0; i < plan.rgbaNumShapesToEvaluate; i++)
+                inRGBAList |= (plan.rgbaShapeList[i] == shape);
+            for (size_t r = 0; r < runs.size(); r++)
+                (runs[r].mode < 4 ? anyRGB : anyRGBA) = true;
+
+            // the RGB fit is needed by RGB-mode runs and, through ExpandTo<4>, by RGBA runs of opaque groups
+            const bool listedRGB = inRGBList && (anyRGB || anyRGBA);
+            const unsigned mask = kBC7ShapeMask[shape];
+            cmds.push_back(kCmdShape | ((uint32_t)runs.size() << 8) | ((uint32_t)listedRGB << 16) | ((uint32_t)inRGBAList << 17) | ((uint32_t)anyRGBA << 18));
+            cmds.push_back(mask | ((uint32_t)popcount16(mask) << 16));
+            for (size_t r = 0; r < runs.size(); r++)
+                cmds.push_back((uint32_t)runs[r].mode | ((uint32_t)std::min(runs[r].seeds, 4) << 4) | ((uint32_t)runs[r].slot << 8));
+        }
+
+        void emit_eval(std::vector<uint32_t> &cmds, int mode, int partition, int numSubsets, const int *slots)
+        {
+            cmds.push_back(kCmdEval | ((uint32_t)mode << 8) | ((uint32_t)partition << 16) | ((uint32_t)numSubsets << 24));
+            uint32_t w = 0;
+            for (int s = 0; s < numSubsets; s++)
+                w |= (uint32_t)slots[s] << (8 * s);
+            cmds.push_back(w);
+        }
+    }
+
+    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds)
+    {
+        cmds.clear();
+        const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
+        int maxSlot = 0;
+
+        // Two-subset modes 1, 3, 7, partition-major: every two-subset shape belongs to exactly one partition, so
+        // six recycled slots are enough.  A (mode, partition) whose subsets are not all searched can never win in
+        // the reference (its total is >= FLT_MAX), so it is not emitted at all.  Mode 7 scans all 64 partitions
+        // whatever mode7RGBAPartitionEnabled says (the reference assigns a misspelt variable, BC67.cpp:1593-1596).
+        for (int p = 0; p < 64; p++)
+        {
+            const int shapes[2] = { kBC7Shapes2[p * 2], kBC7Shapes2[p * 2 + 1] };
+            const bool rgbSearched = spRGB[shapes[0]] && spRGB[shapes[1]];
+            const bool m1 = ((plan.mode1PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m3 = ((plan.mode3PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m7 = spRGBA[shapes[0]] && spRGBA[shapes[1]];
+            if (!m1 && !m3 && !m7)
+                continue;
+            for (int s = 0; s < 2; s++)
+            {
+                std::vector<Run> runs;
+                if (m1) runs.push_back(Run{ 1, spRGB[shapes[s]], 0 + s });
+                if (m3) runs.push_back(Run{ 3, spRGB[shapes[s]], 2 + s });
+                if (m7) runs.push_back(Run{ 7, spRGBA[shapes[s]], 4 + s });
+                emit_shape(cmds, plan, shapes[s], runs);
+            }
+            const int s1[2] = { 0, 1 }, s3[2] = { 2, 3 }, s7[2] = { 4, 5 };
+            if (m1) emit_eval(cmds, 1, p, 2, s1);
+            if (m3) emit_eval(cmds, 3, p, 2, s3);
+            if (m7) emit_eval(cmds, 7, p, 2, s7);
+            maxSlot = 6;
+        }
+
+        // Three-subset modes 0 and 2: shapes are shared between partitions, so each needed shape is searched once
+        // and kept in its own slot until the partitions are scanned.
+        {
+            int slotOf[2][243];
+            for (int i = 0; i < 243; i++)
+                slotOf[0][i] = slotOf[1][i] = -1;
+            bool enabled[2][64];
+            for (int p = 0; p < 64; p++)
+            {
+                const bool searched = spRGB[kBC7Shapes3[p * 3]] && spRGB[kBC7Shapes3[p * 3 + 1]] && spRGB[kBC7Shapes3[p * 3 + 2]];
+                enabled[0][p] = p < 16 && ((plan.mode0PartitionEnabled >> p) & 1) && searched;
+                enabled[1][p] = ((plan.mode2PartitionEnabled >> p) & 1) && searched;
+            }
+            int nextSlot = 6;
+            for (int m = 0; m < 2; m++)
+                for (int p = 0; p < 64; p++)
+                    if (enabled[m][p])
+                        for (int k = 0; k < 3; k++)
+                            slotOf[m][kBC7Shapes3[p * 3 + k]] = 0;
+            for (int shape = 0; shape < 243; shape++)
+            {
+                std::vector<Run> runs;
+                if (slotOf[0][shape] == 0)
+                    runs.push_back(Run{ 0, spRGB[shape], slotOf[0][shape] = nextSlot++ });
+                if (slotOf[1][shape] == 0)
+                    runs.push_back(Run{ 2, spRGB[shape], slotOf[1][shape] = nextSlot++ });
+                if (!runs.empty())
+                    emit_shape(cmds, plan, shape, runs);
+            }
+            for (int m = 0; m < 2; m++)
+                for (int p = 0; p < 64; p++)
+                    if (enabled[m][p])
+                    {
+                        const int slots[3] = { slotOf[m][kBC7Shapes3[p * 3]], slotOf[m][kBC7Shapes3[p * 3 + 1]], slotOf[m][kBC7Shapes3[p * 3 + 2]] };
+                        emit_eval(cmds, m ? 2 : 0, p, 3, slots);
+                    }
+            maxSlot = std::max(maxSlot, nextSlot);
+        }
+
+        // Mode 6: the whole block (shape 0)
+        if (plan.mode6Enabled && spRGBA[0])
+        {
+            std::vector<Run> runs(1, Run{ 6, spRGBA[0], 0 });
+            emit_shape(cmds, plan, 0, runs);
+            const int slots[1] = { 0 };
+            emit_eval(cmds, 6, 0, 1, slots);
+            maxSlot = std::max(maxSlot, 1);
+        }
+
+        // Modes 4 and 5 (BC67.cpp:1675-1683, 1735-1742)
+        for (int mode = 4; mode <= 5; mode++)
+            for (int rotation = 0; rotation < 4; rotation++)
+                for (int isel = 0; isel < (mode == 4 ? 2 : 1); isel++)
+                {
+                    const int seeds = std::min<int>(4, mode == 4 ? plan.mode4SP[rotation][isel] : plan.mode5SP[rotation]);
+                    if (seeds > 0)
+                        cmds.push_back(kCmdDual | ((uint32_t)mode << 8) | ((uint32_t)rotation << 16) | ((uint32_t)isel << 20) | ((uint32_t)seeds << 24));
+                }
+
+        cmds.push_back(kCmdEnd);
+        return maxSlot;
+    }
+
+    // ---------------------------------------------------------------------------------------------------
+    // constants
+
+    static QuantConst make_quant(int bits, bool withP, int unqBits)
+    {
+        QuantConst q;
+        memset(&q, 0, sizeof(q));
+        if (withP)
+        {
+            // QuantizeP: N = c * (2^(bits+1) - 1) + addend(p); v = N >> 9; out = 2v + p
+            const int K = (1 << (bits + 1)) - 1;
+            const int addend[2] = { 255, (1 << (8 - bits)) - 1 };
+            q.qMul = (float)K / 512.0f;
+            for (int p = 0; p < 2; p++)
+                q.qAdd[p] = (float)(2 * addend[p] - 511) / 1024.0f;
+            q.pMul = 2.0f;
+            q.pAdd = 1.0f;
+        }
+        else
+        {
+            // Quantize: N = c * (2^bits - 1) + 127 + 2^(7-bits); v = N >> 8
+            const int K = (1 << bits) - 1;
+            const int addend = 127 + (1 << (7 - bits));
+            q.qMul = (float)K / 256.0f;
+            q.qAdd[0] = q.qAdd[1] = (float)(2 * addend - 255) / 512.0f;
+            q.pMul = 1.0f;
+            q.pAdd = 0.0f;
+        }
+        if (unqBits)
+        {
+            // Unquantize: out = v * 2^(8-b) + floor(v / 2^(2b-8))
+            const int s = 2 * unqBits - 8;
+            q.hasUnq = 1;
+            q.uMul = (float)(1 << (8 - unqBits));
+            q.uScale = 1.0f / (float)(1 << s);
+            q.uOff = -(float)((1 << s) - 1) / (float)(1 << (s + 1));
+        }
+        return q;
+    }
+
+    void bc7_fill_params(BC7Params &P, const OptionsPOD &options, const BC7PlanPOD &plan, const float rcpN[17])
+    {
+        memset(&P, 0, sizeof(P));
+
+        // Util::FillWeights, ConvectionKernels_Util.cpp:62-73
+        if (options.flags & kFlag_Uniform)
+            P.w[0] = P.w[1] = P.w[2] = P.w[3] = 1.0f;
+        else
+        {
+            P.w[0] = options.redWeight;
+            P.w[1] = options.greenWeight;
+            P.w[2] = options.blueWeight;
+            P.w[3] = options.alphaWeight;
+        }
+        for (int ch = 0; ch < 4; ch++)
+        {
+            P.wSq[ch] = P.w[ch] * P.w[ch];
+            P.rcpW[ch] = (P.w[ch] != 0.0f) ? 1.0f / P.w[ch] : 1.0f;    // EndpointRefiner.h:52-57
+        }
+        for (int n = 0; n < 17; n++)
+            P.rcpN[n] = rcpN[n];
+
+        for (int bits = 2; bits <= 4; bits++)
+        {
+            IndexConst &ic = P.ic[bits - 2];
+            const int range = 1 << bits;
+            ic.maxValue = (float)(range - 1);
+            ic.wScale = 64.0f / (float)(range - 1);
+            ic.rcpMaxIndex = 1.0f / (float)(range - 1);
+            for (int tweak = 0; tweak < 4; tweak++)
+            {
+                // Util::ComputeTweakFactors, ConvectionKernels_Util.cpp:75-85
+                const int totalUnits = range - 1;
+                const int minOutsideUnits = (tweak >> 1) & 1, maxOutsideUnits = tweak & 1;
+                const int insideUnits = totalUnits - minOutsideUnits - maxOutsideUnits;
+                ic.tweak[tweak][0] = -(float)minOutsideUnits / (float)insideUnits;
+                ic.tweak[tweak][1] = (float)maxOutsideUnits / (float)insideUnits + 1.0f;
+            }
+        }
+
+        // g_modes (BC67.cpp:108-119) and CompressEndpoints0-7 (BC67.cpp:862-938)
+        struct { int bits, withP, unq, parityMax, sharedP, indexBits; } const modes[8] =
+        {
+            { 4, 1, 5, 4, 0, 3 },
+            { 6, 1, 7, 2, 1, 3 },
+            { 5, 0, 5, 1, 0, 2 },
+            { 7, 1, 0, 4, 0, 2 },
+            { 5, 0, 5, 1, 0, 2 },   // mode 4 RGB; index precision is chosen per index selector
+            { 7, 0, 7, 1, 0, 2 },   // mode 5 RGB
+            { 7, 1, 0, 4, 0, 4 },
+            { 5, 1, 6, 4, 0, 2 },
+        };
+        for (int m = 0; m < 8; m++)
+        {
+            P.mc[m].q = make_quant(modes[m].bits, modes[m].withP != 0, modes[m].unq);
+            P.mc[m].parityBitMax = modes[m].parityMax;
+            P.mc[m].sharedP = modes[m].sharedP;
+            P.mc[m].indexBits = modes[m].indexBits;
+        }
+        P.alphaQ4 = make_quant(6, false, 6);
+
+        P.mode7RGBPartitionEnabled = plan.mode7RGBPartitionEnabled;
+        P.flags = options.flags;
+        P.refineRounds = std::max(1, options.refineRoundsBC7);     // BC67.cpp:1046-1047
+    }
+
+    const BC7PackTables &bc7_pack_tables()
+    {
+        static BC7PackTables T;
+        static bool ready = false;
+        if (!ready)
+        {
+            for (int i = 0; i < 64; i++)
+            {
+                T.partitionMask2[i] = kBC7PartitionMask2[i];
+                T.partitionMap3[i] = kBC7PartitionMap3[i];
+                T.fixup2[i] = kBC7Fixup2[i];
+            }
+            for (int i = 0; i < 128; i++)
+                T.fixup3[i] = kBC7Fixup3[i];
+            ready = true;
+        }
+        return T;
+    }
+}

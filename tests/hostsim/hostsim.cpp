@@ -1,0 +1,85 @@
+// TEST INFRASTRUCTURE ONLY.  CPU build of the per-thread device code (convectionkernels_b200/csrc/*_core.cuh)
+// so the kernel logic can be checked against the oracle in the GPU-less dev container.  It emulates the
+// kernel's warp of 32 lanes = 4 reference groups; it is NOT part of the product library and the product never
+// falls back to it.
+#include <vector>
+#include <xmmintrin.h>
+
+#include "../../convectionkernels_b200/csrc/bc7_host.h"
+
+using namespace cvttb200;
+
+extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const BC7PlanPOD *plan, int warpFlagsAllTrue)
+{
+    if (nBlocks % 8)
+        return -1;
+    float rcpN[17];
+    for (int n = 0; n < 17; n++)
+        rcpN[n] = _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
+    std::vector<uint32_t> cmds;
+    int slots = bc7_compile_plan(*plan, cmds);
+    if (slots > kBC7MaxSlots)
+        return -2;
+    BC7Params P;
+    bc7_fill_params(P, *options, *plan, rcpN);
+    P.cmds = cmds.data();
+    const BC7PackTables &T = bc7_pack_tables();
+    const bool fast = (options->flags & kFlag_BC7_FastIndexing) != 0;
+
+    for (size_t warpBase = 0; warpBase < nBlocks; warpBase += 32)
+    {
+        const size_t lanes = std::min<size_t>(32, nBlocks - warpBase);
+        BC7LaneFlags lf[32];
+        int minAlpha[32];
+        for (size_t l = 0; l < lanes; l++)
+        {
+            minAlpha[l] = 255;
+            for (int px = 0; px < 16; px++)
+                minAlpha[l] = std::min<int>(minAlpha[l], blocks[(warpBase + l) * 64 + px * 4 + 3]);
+        }
+        bool wRGB = false, wPCA4 = false, wM7 = false;
+        for (size_t l = 0; l < lanes; l++)
+        {
+            const size_t g = l & ~(size_t)7;
+            bool anyAlpha = false, allowRGB = false;
+            for (size_t k = g; k < g + 8; k++)
+            {
+                anyAlpha |= minAlpha[k] < 255;
+                allowRGB |= minAlpha[k] > 250;
+            }
+            lf[l].anyBlockHasAlpha = anyAlpha;
+            lf[l].allowRGBModes = allowRGB;
+            lf[l].blockHasNonMaxAlpha = minAlpha[l] < 255;
+            wRGB |= allowRGB;
+            wPCA4 |= anyAlpha || !allowRGB;
+            wM7 |= anyAlpha || plan->mode7RGBPartitionEnabled != 0;
+        }
+        for (size_t l = 0; l < lanes; l++)
+        {
+            lf[l].warpAnyRGB = warpFlagsAllTrue ? true : wRGB;
+            lf[l].warpAnyPCA4 = warpFlagsAllTrue ? true : wPCA4;
+            lf[l].warpAnyExpand = true;
+            lf[l].warpAnyMode7 = warpFlagsAllTrue ? true : wM7;
+            F4 pix[16];
+            for (int px = 0; px < 16; px++)
+            {
+                const uint8_t *s = blocks + (warpBase + l) * 64 + px * 4;
+                pix[px].x = as_float(kMagicBits | s[0]);
+                pix[px].y = as_float(kMagicBits | s[1]);
+                pix[px].z = as_float(kMagicBits | s[2]);
+                pix[px].w = as_float(kMagicBits | s[3]);
+            }
+            uint32_t o[4];
+            if (fast)
+                bc7_encode_block<true>(P, T, pix, 1, lf[l], o);
+            else
+                bc7_encode_block<false>(P, T, pix, 1, lf[l], o);
+            memcpy(out + (warpBase + l) * 16, o, 16);
+        }
+    }
+    return 0;
+}
+
+extern "C" void hostsim_plan_from_quality(BC7PlanPOD *plan, int q) { bc7_plan_from_quality(*plan, q); }
+extern "C" void hostsim_plan_default(BC7PlanPOD *plan) { bc7_plan_default(*plan); }
+extern "C" int hostsim_plan_from_finetune(BC7PlanPOD *plan, const BC7FineTuningPOD *ft) { return bc7_plan_from_fine_tuning(*plan, *ft) ? 1 : 0; }
