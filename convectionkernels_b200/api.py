@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference's public interface for the encode hot path (reference ConvectionKernels.h:236-277),
+over the C ABI of libcvtt_b200.so (include/cvtt_b200.h).
+
+Names follow the reference: Options, BC7EncodingPlan, BC7FineTuningParams, Flags, ConfigureBC7EncodingPlanFromQuality,
+EncodeBC7 ... -- except that an Encode* call takes any multiple of NumParallelBlocks (8) blocks instead of exactly 8;
+blocks [8k, 8k+8) are the k-th reference call.
+
+Inputs / outputs may be numpy arrays (host memory) or torch CUDA tensors (device memory, work is enqueued on
+torch's current stream).  There is no CPU fallback: if the CUDA library or a B200 is missing the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+NumParallelBlocks = 8
+
+
+class Flags:
+    """cvtt::Flags, reference ConvectionKernels.h:33-69"""
+    BC7_FastIndexing = 0x008
+    BC7_TrySingleColor = 0x010
+    BC7_RespectPunchThrough = 0x020
+    BC6H_FastIndexing = 0x040
+    S3TC_Exhaustive = 0x080
+    S3TC_Paranoid = 0x100
+    Uniform = 0x200
+    ETC_UseFakeBT709 = 0x400
+    ETC_FakeBT709Accurate = 0x800
+    Fastest = BC6H_FastIndexing | BC7_FastIndexing | S3TC_Paranoid
+    Faster = BC6H_FastIndexing | BC7_FastIndexing | S3TC_Paranoid
+    Fast = BC7_FastIndexing | S3TC_Paranoid
+    Default = BC7_FastIndexing | S3TC_Paranoid
+    Better = S3TC_Paranoid | S3TC_Exhaustive
+    Ultra = BC7_TrySingleColor | S3TC_Paranoid | S3TC_Exhaustive | ETC_FakeBT709Accurate
+
+
+class Options(ctypes.Structure):
+    """cvtt::Options, reference ConvectionKernels.h:73-103"""
+    _fields_ = [("flags", ctypes.c_uint32), ("threshold", ctypes.c_float),
+                ("redWeight", ctypes.c_float), ("greenWeight", ctypes.c_float), ("blueWeight", ctypes.c_float), ("alphaWeight", ctypes.c_float),
+                ("refineRoundsBC7", ctypes.c_int), ("refineRoundsBC6H", ctypes.c_int), ("refineRoundsIIC", ctypes.c_int),
+                ("refineRoundsS3TC", ctypes.c_int), ("seedPoints", ctypes.c_int)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        _lib().cvttb200_options_default(ctypes.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class BC7FineTuningParams(ctypes.Structure):
+    """cvtt::BC7FineTuningParams, reference ConvectionKernels.h:105-140"""
+    _fields_ = [("mode0SP", ctypes.c_uint8 * 16), ("mode1SP", ctypes.c_uint8 * 64), ("mode2SP", ctypes.c_uint8 * 64), ("mode3SP", ctypes.c_uint8 * 64),
+                ("mode4SP", (ctypes.c_uint8 * 2) * 4), ("mode5SP", ctypes.c_uint8 * 4), ("mode6SP", ctypes.c_uint8), ("mode7SP", ctypes.c_uint8 * 64)]
+
+    def __init__(self):
+        super().__init__()
+        _lib().cvttb200_bc7_fine_tuning_default(ctypes.byref(self))
+
+
+class BC7EncodingPlan(ctypes.Structure):
+    """cvtt::BC7EncodingPlan, reference ConvectionKernels.h:142-199"""
+    kNumRGBAShapes = 129
+    kNumRGBShapes = 243
+    _fields_ = [("mode1PartitionEnabled", ctypes.c_uint64), ("mode2PartitionEnabled", ctypes.c_uint64), ("mode3PartitionEnabled", ctypes.c_uint64),
+                ("mode0PartitionEnabled", ctypes.c_uint16),
+                ("mode7RGBAPartitionEnabled", ctypes.c_uint64), ("mode7RGBPartitionEnabled", ctypes.c_uint64),
+                ("mode4SP", (ctypes.c_uint8 * 2) * 4), ("mode5SP", ctypes.c_uint8 * 4), ("mode6Enabled", ctypes.c_uint8),
+                ("seedPointsForShapeRGB", ctypes.c_uint8 * 243), ("seedPointsForShapeRGBA", ctypes.c_uint8 * 129),
+                ("rgbaShapeList", ctypes.c_uint8 * 129), ("rgbaNumShapesToEvaluate", ctypes.c_uint8),
+                ("rgbShapeList", ctypes.c_uint8 * 243), ("rgbNumShapesToEvaluate", ctypes.c_uint8)]
+
+    def __init__(self):
+        super().__init__()
+        _lib().cvttb200_bc7_plan_default(ctypes.byref(self))
+
+    def tobytes(self):
+        return bytes(memoryview(self))
+
+
+FORMATS = dict(BC1=1, BC2=2, BC3=3, BC4U=4, BC4S=5, BC5U=6, BC5S=7, BC6HU=8, BC6HS=9, BC7=10,
+               ETC1=11, ETC2=12, ETC2_RGBA=13, ETC2_PUNCHTHROUGH=14, ETC2_ALPHA=15, EAC_R11U=16, EAC_R11S=17)
+
+_LIB = None
+
+
+class CvttError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("cvttb200 status %d: %s" % (status, message))
+        self.status = status
+
+
+def library_path():
+    return _build.LIB
+
+
+def _lib():
+    """Loads libcvtt_b200.so (building it with nvcc first if it is missing or stale).  Raises if that fails."""
+    global _LIB
+    if _LIB is None:
+        path = _build.build()
+        L = ctypes.CDLL(path)
+        L.cvttb200_last_error.restype = ctypes.c_char_p
+        L.cvttb200_launch_count.restype = ctypes.c_uint64
+        L.cvttb200_input_block_bytes.restype = ctypes.c_size_t
+        L.cvttb200_output_block_bytes.restype = ctypes.c_size_t
+        L.cvttb200_encode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cvttb200_set_rcp_table.argtypes = [ctypes.c_void_p]
+        L.cvttb200_get_rcp_table.argtypes = [ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _check(status):
+    if status != 0:
+        raise CvttError(status, _lib().cvttb200_last_error().decode("utf-8", "replace"))
+
+
+def init(device=0):
+    _check(_lib().cvttb200_init(int(device)))
+
+
+def launch_count():
+    return int(_lib().cvttb200_launch_count())
+
+
+def set_rcp_table(table):
+    """table: 17 floats (rcp of 0..16) or None to restore this host's _mm_rcp_ps values."""
+    if table is None:
+        _check(_lib().cvttb200_set_rcp_table(None))
+    else:
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        assert t.size == 17
+        _check(_lib().cvttb200_set_rcp_table(t.ctypes.data))
+
+
+def get_rcp_table():
+    t = np.zeros(17, dtype=np.float32)
+    _check(_lib().cvttb200_get_rcp_table(t.ctypes.data))
+    return t
+
+
+def ConfigureBC7EncodingPlanFromQuality(encodingPlan, quality):
+    """reference ConvectionKernels.h:262"""
+    _lib().cvttb200_bc7_plan_from_quality(ctypes.byref(encodingPlan), int(quality))
+
+
+def ConfigureBC7EncodingPlanFromFineTuningParams(encodingPlan, params):
+    """reference ConvectionKernels.h:265"""
+    return bool(_lib().cvttb200_bc7_plan_from_fine_tuning(ctypes.byref(encodingPlan), ctypes.byref(params)))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _as_struct_ptr(obj, ctype):
+    if obj is None:
+        return None
+    if isinstance(obj, ctype):
+        return ctypes.byref(obj)
+    buf = np.ascontiguousarray(obj, dtype=np.uint8)      # raw bytes (e.g. produced by the oracle loader)
+    assert buf.size == ctypes.sizeof(ctype)
+    return ctypes.cast(buf.ctypes.data, ctypes.c_void_p), buf
+
+
+def encode(fmt, pBlocks, options, encodingPlan=None, out=None):
+    """Encodes pBlocks (numpy array or torch CUDA tensor holding n PixelBlocks, n % 8 == 0) to `fmt`.
+
+    Returns a (n, outBytes) uint8 array of the same kind as the input (or `out` if given)."""
+    L = _lib()
+    f = FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
+    inb, outb = L.cvttb200_input_block_bytes(f), L.cvttb200_output_block_bytes(f)
+    keep = []
+
+    def struct_arg(obj, ctype):
+        r = _as_struct_ptr(obj, ctype)
+        if isinstance(r, tuple):
+            keep.append(r[1])
+            return r[0]
+        return r
+
+    if _is_torch(pBlocks):
+        import torch
+        src = pBlocks.contiguous()
+        nbytes = src.numel() * src.element_size()
+        n = nbytes // inb
+        if out is None:
+            out = torch.empty((n, outb), dtype=torch.uint8, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream if src.is_cuda else None
+        with torch.cuda.device(src.device if src.is_cuda else torch.cuda.current_device()):
+            st = L.cvttb200_encode(f, src.data_ptr(), n, out.data_ptr(), struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan), stream)
+    else:
+        src = np.ascontiguousarray(pBlocks)
+        nbytes = src.size * src.itemsize
+        n = nbytes // inb
+        if out is None:
+            out = np.empty((n, outb), dtype=np.uint8)
+        optr = out.data_ptr() if _is_torch(out) else out.ctypes.data
+        st = L.cvttb200_encode(f, src.ctypes.data, n, optr, struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan), None)
+    if n * inb != nbytes:
+        raise ValueError("input size is not a whole number of blocks")
+    _check(st)
+    return out
+
+
+def EncodeBC7(pBlocks, options, encodingPlan, out=None):
+    """cvtt::Kernels::EncodeBC7, reference ConvectionKernels.h:252 / ConvectionKernels_API.cpp:41-54"""
+    return encode("BC7", pBlocks, options, encodingPlan, out)

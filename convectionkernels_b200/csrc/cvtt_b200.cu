@@ -1,0 +1,462 @@
+// libcvtt_b200.so: CUDA kernels (sm_100a) + the C ABI declared in include/cvtt_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ... (convectionkernels_b200/build.py).
+// -fmad=false is part of the numerical contract: the reference's fp32 expressions must round after every
+// operation.
+#include <cuda_runtime.h>
+#include <xmmintrin.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/cvtt_b200.h"
+#include "bc7_host.h"
+
+using namespace cvttb200;
+
+static_assert(sizeof(cvttb200_options) == 44 && sizeof(OptionsPOD) == 44, "cvtt::Options layout");
+static_assert(sizeof(cvttb200_bc7_plan) == 808 && sizeof(BC7PlanPOD) == 808, "cvtt::BC7EncodingPlan layout");
+static_assert(sizeof(cvttb200_bc7_fine_tuning) == 285 && sizeof(BC7FineTuningPOD) == 285, "cvtt::BC7FineTuningParams layout");
+
+// =========================================================================================================
+// Kernels
+
+namespace
+{
+    constexpr int kBC7Threads = 128;     // 4 warps = 16 reference groups per CTA
+
+    __constant__ BC7PackTables c_bc7PackTables;
+
+    // One thread per block, warp = 4 reference groups; see cvtt_common.cuh / bc7_core.cuh.
+    //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (a warp reads 2 KB contiguous)
+    //  * pixels are expanded once to (value + 1.5*2^23) fp32 in shared memory, laid out [pixel][thread] so that the
+    //    warp's 128-bit loads of one pixel are conflict-free
+    //  * output: one 128-bit store per thread (512 B contiguous per warp)
+    template<bool FAST>
+    __global__ void __launch_bounds__(kBC7Threads, 4)
+    bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
+    {
+        __shared__ F4 sPix[16 * kBC7Threads];
+
+        const uint32_t tid = threadIdx.x;
+        const uint32_t block = blockIdx.x * kBC7Threads + tid;
+        const bool active = block < nBlocks;
+        F4 *pix = sPix + tid;
+
+        int minAlpha = 255;
+        if (active)
+        {
+            const uint4 *src = in + (size_t)block * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    F4 p;
+                    p.x = __uint_as_float(kMagicBits | (w[k] & 0xffu));
+                    p.y = __uint_as_float(kMagicBits | ((w[k] >> 8) & 0xffu));
+                    p.z = __uint_as_float(kMagicBits | ((w[k] >> 16) & 0xffu));
+                    p.w = __uint_as_float(kMagicBits | (w[k] >> 24));
+                    minAlpha = min(minAlpha, (int)(w[k] >> 24));
+                    pix[(q * 4 + k) * kBC7Threads] = p;
+                }
+            }
+        }
+        else
+        {
+            F4 p;
+            p.x = p.y = p.z = kMagic;
+            p.w = kMagic + 255.0f;
+#pragma unroll
+            for (int px = 0; px < 16; px++)
+                pix[px * kBC7Threads] = p;
+        }
+
+        // group votes (reference AnySet over the 8 lanes of one call, BC67.cpp:1069-1072) and warp-level skips
+        const uint32_t segMask = 0xffu << (tid & 24);
+        const uint32_t hasAlphaBallot = __ballot_sync(0xffffffffu, active && minAlpha < 255);
+        const uint32_t allowRGBBallot = __ballot_sync(0xffffffffu, active && minAlpha > 250);
+        BC7LaneFlags lf;
+        lf.anyBlockHasAlpha = (hasAlphaBallot & segMask) != 0;
+        lf.allowRGBModes = (allowRGBBallot & segMask) != 0;
+        lf.blockHasNonMaxAlpha = minAlpha < 255;
+        const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;
+        const bool mode7 = lf.anyBlockHasAlpha || P.mode7RGBPartitionEnabled != 0;
+        lf.warpAnyRGB = __any_sync(0xffffffffu, active && lf.allowRGBModes);
+        lf.warpAnyPCA4 = __any_sync(0xffffffffu, active && usePCA4);
+        lf.warpAnyExpand = true;
+        lf.warpAnyMode7 = __any_sync(0xffffffffu, active && mode7);
+
+        uint32_t o[4];
+        bc7_encode_block<FAST>(P, c_bc7PackTables, pix, kBC7Threads, lf, o);
+
+        if (active)
+            out[block] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// =========================================================================================================
+// Host state
+
+namespace
+{
+    thread_local std::string t_lastError;
+    std::atomic<uint64_t> g_launches(0);
+
+    struct PlanCacheEntry
+    {
+        BC7PlanPOD plan;
+        uint32_t *dCmds;
+    };
+
+    struct DeviceContext
+    {
+        int device = -1;
+        bool ready = false;
+        std::vector<PlanCacheEntry> plans;
+        void *stageIn = nullptr, *stageOut = nullptr;
+        size_t stageInBytes = 0, stageOutBytes = 0;
+    };
+
+    std::mutex g_mutex;
+    std::vector<DeviceContext> g_contexts;
+    float g_rcpN[17];
+    bool g_rcpOverridden = false, g_rcpReady = false;
+
+    int fail(int code, const std::string &msg)
+    {
+        t_lastError = msg;
+        return code;
+    }
+
+    int fail_cuda(cudaError_t e, const char *what)
+    {
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? CVTTB200_ERR_NO_DEVICE : CVTTB200_ERR_CUDA,
+                    std::string(what) + ": " + cudaGetErrorString(e));
+    }
+
+#define CVTT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(e_, #call); } while (0)
+
+    void host_rcp_table(float *t)
+    {
+        for (int n = 0; n < 17; n++)
+            t[n] = _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
+    }
+
+    // caller holds g_mutex
+    int get_context(int device, DeviceContext **out)
+    {
+        if (!g_rcpReady)
+        {
+            host_rcp_table(g_rcpN);
+            g_rcpReady = true;
+        }
+        for (size_t i = 0; i < g_contexts.size(); i++)
+            if (g_contexts[i].device == device && g_contexts[i].ready)
+            {
+                *out = &g_contexts[i];
+                return CVTTB200_OK;
+            }
+
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return fail(CVTTB200_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + " (libcvtt_b200 has no CPU fallback)");
+        if (device < 0 || device >= count)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "device index out of range");
+        cudaDeviceProp prop;
+        CVTT_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(CVTTB200_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100; this library contains sm_100a code only");
+
+        int prev = 0;
+        CVTT_CUDA(cudaGetDevice(&prev));
+        CVTT_CUDA(cudaSetDevice(device));
+        CVTT_CUDA(cudaMemcpyToSymbol(c_bc7PackTables, &bc7_pack_tables(), sizeof(BC7PackTables)));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaDeviceSynchronize());
+        CVTT_CUDA(cudaSetDevice(prev));
+
+        g_contexts.emplace_back();
+        g_contexts.back().device = device;
+        g_contexts.back().ready = true;
+        *out = &g_contexts.back();
+        return CVTTB200_OK;
+    }
+
+    // caller holds g_mutex and has made ctx.device current
+    int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, const uint32_t **dCmds)
+    {
+        for (size_t i = 0; i < ctx.plans.size(); i++)
+            if (memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
+            {
+                *dCmds = ctx.plans[i].dCmds;
+                return CVTTB200_OK;
+            }
+        std::vector<uint32_t> cmds;
+        const int slots = bc7_compile_plan(plan, cmds);
+        if (slots > kBC7MaxSlots)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "BC7 plan needs more result slots than the kernel provides");
+        if (ctx.plans.size() >= 16)
+        {
+            cudaFree(ctx.plans.front().dCmds);
+            ctx.plans.erase(ctx.plans.begin());
+        }
+        PlanCacheEntry entry;
+        entry.plan = plan;
+        entry.dCmds = nullptr;
+        CVTT_CUDA(cudaMalloc(&entry.dCmds, cmds.size() * sizeof(uint32_t)));
+        CVTT_CUDA(cudaMemcpy(entry.dCmds, cmds.data(), cmds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx.plans.push_back(entry);
+        *dCmds = entry.dCmds;
+        return CVTTB200_OK;
+    }
+
+    bool is_device_pointer(const void *p)
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    }
+
+    int ensure_stage(void **buf, size_t *have, size_t need)
+    {
+        if (*have >= need)
+            return CVTTB200_OK;
+        if (*buf)
+            cudaFree(*buf);
+        *buf = nullptr;
+        *have = 0;
+        CVTT_CUDA(cudaMalloc(buf, need));
+        *have = need;
+        return CVTTB200_OK;
+    }
+
+    int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, cudaStream_t stream)
+    {
+        if (options.flags & (kFlag_BC7_TrySingleColor | kFlag_BC7_RespectPunchThrough))
+            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::BC7_TrySingleColor / BC7_RespectPunchThrough are not implemented yet");
+        if (nBlocks > 0xffffff00u)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
+
+        BC7Params P;
+        bc7_fill_params(P, options, plan, g_rcpN);
+        const uint32_t *dCmds = nullptr;
+        int rc = get_plan_commands(ctx, plan, &dCmds);
+        if (rc != CVTTB200_OK)
+            return rc;
+        P.cmds = dCmds;
+
+        const unsigned grid = (unsigned)((nBlocks + kBC7Threads - 1) / kBC7Threads);
+        if (options.flags & kFlag_BC7_FastIndexing)
+            bc7_encode_kernel<true><<<grid, kBC7Threads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks);
+        else
+            bc7_encode_kernel<false><<<grid, kBC7Threads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks);
+        g_launches++;
+        CVTT_CUDA(cudaGetLastError());
+        return CVTTB200_OK;
+    }
+}
+
+// =========================================================================================================
+// C ABI
+
+extern "C"
+{
+
+int cvttb200_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceContext *ctx = nullptr;
+    return get_context(device, &ctx);
+}
+
+void cvttb200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess)
+    {
+        cudaGetLastError();
+        g_contexts.clear();
+        return;
+    }
+    for (size_t i = 0; i < g_contexts.size(); i++)
+    {
+        DeviceContext &c = g_contexts[i];
+        if (cudaSetDevice(c.device) != cudaSuccess)
+            continue;
+        for (size_t k = 0; k < c.plans.size(); k++)
+            cudaFree(c.plans[k].dCmds);
+        if (c.stageIn) cudaFree(c.stageIn);
+        if (c.stageOut) cudaFree(c.stageOut);
+    }
+    g_contexts.clear();
+    cudaSetDevice(prev);
+}
+
+int cvttb200_set_rcp_table(const float *rcp17)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (rcp17)
+    {
+        memcpy(g_rcpN, rcp17, sizeof(g_rcpN));
+        g_rcpOverridden = true;
+    }
+    else
+    {
+        host_rcp_table(g_rcpN);
+        g_rcpOverridden = false;
+    }
+    g_rcpReady = true;
+    return CVTTB200_OK;
+}
+
+int cvttb200_get_rcp_table(float *rcp17)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!rcp17)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null table");
+    if (!g_rcpReady)
+    {
+        host_rcp_table(g_rcpN);
+        g_rcpReady = true;
+    }
+    memcpy(rcp17, g_rcpN, sizeof(g_rcpN));
+    return CVTTB200_OK;
+}
+
+const char *cvttb200_last_error(void) { return t_lastError.c_str(); }
+
+uint64_t cvttb200_launch_count(void) { return g_launches.load(); }
+
+void cvttb200_options_default(cvttb200_options *o)
+{
+    // cvtt::Options::Options(), ConvectionKernels.h:89-101
+    o->flags = CVTTB200_FLAG_BC7_FAST_INDEXING | CVTTB200_FLAG_S3TC_PARANOID;
+    o->threshold = 0.5f;
+    o->redWeight = 0.2125f / 0.7154f;
+    o->greenWeight = 1.0f;
+    o->blueWeight = 0.0721f / 0.7154f;
+    o->alphaWeight = 1.0f;
+    o->refineRoundsBC7 = 2;
+    o->refineRoundsBC6H = 3;
+    o->refineRoundsIIC = 8;
+    o->refineRoundsS3TC = 2;
+    o->seedPoints = 4;
+}
+
+void cvttb200_bc7_plan_default(cvttb200_bc7_plan *plan) { bc7_plan_default(*reinterpret_cast<BC7PlanPOD *>(plan)); }
+
+void cvttb200_bc7_plan_from_quality(cvttb200_bc7_plan *plan, int quality) { bc7_plan_from_quality(*reinterpret_cast<BC7PlanPOD *>(plan), quality); }
+
+int cvttb200_bc7_plan_from_fine_tuning(cvttb200_bc7_plan *plan, const cvttb200_bc7_fine_tuning *params)
+{
+    return bc7_plan_from_fine_tuning(*reinterpret_cast<BC7PlanPOD *>(plan), *reinterpret_cast<const BC7FineTuningPOD *>(params)) ? 1 : 0;
+}
+
+void cvttb200_bc7_fine_tuning_default(cvttb200_bc7_fine_tuning *params)
+{
+    memset(params, 4, sizeof(*params));   // BC7FineTuningParams(): every seed-point count is 4, ConvectionKernels.h:117-139
+}
+
+size_t cvttb200_input_block_bytes(int format)
+{
+    switch (format)
+    {
+    case CVTTB200_BC6HU: case CVTTB200_BC6HS: return 128;
+    case CVTTB200_EAC_R11U: case CVTTB200_EAC_R11S: return 32;
+    default: return (format >= CVTTB200_BC1 && format <= CVTTB200_EAC_R11S) ? 64 : 0;
+    }
+}
+
+size_t cvttb200_output_block_bytes(int format)
+{
+    switch (format)
+    {
+    case CVTTB200_BC1: case CVTTB200_BC4U: case CVTTB200_BC4S: case CVTTB200_ETC1: case CVTTB200_ETC2:
+    case CVTTB200_ETC2_PUNCHTHROUGH: case CVTTB200_ETC2_ALPHA: case CVTTB200_EAC_R11U: case CVTTB200_EAC_R11S:
+        return 8;
+    default:
+        return (format >= CVTTB200_BC1 && format <= CVTTB200_EAC_R11S) ? 16 : 0;
+    }
+}
+
+int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *streamPtr)
+{
+    if (!blocks || !out || !options)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
+    if (nBlocks % 8 != 0)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "nBlocks must be a multiple of 8 (cvtt::NumParallelBlocks)");
+    const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
+    if (!inBytes)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
+    if (format != CVTTB200_BC7)
+        return fail(CVTTB200_ERR_UNSUPPORTED, "format not implemented by this build (no CPU fallback exists)");
+    if (!plan)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
+    if (nBlocks == 0)
+        return CVTTB200_OK;
+
+    std::lock_guard<std::mutex> lock(g_mutex);
+
+    int device = 0;
+    {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "cudaGetDevice");
+    }
+    DeviceContext *ctx = nullptr;
+    int rc = get_context(device, &ctx);
+    if (rc != CVTTB200_OK)
+        return rc;
+
+    cudaStream_t stream = (cudaStream_t)streamPtr;
+    const bool inOnDevice = is_device_pointer(blocks), outOnDevice = is_device_pointer(out);
+    const void *dIn = blocks;
+    void *dOut = out;
+    if (!inOnDevice)
+    {
+        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, nBlocks * inBytes);
+        if (rc != CVTTB200_OK)
+            return rc;
+        CVTT_CUDA(cudaMemcpyAsync(ctx->stageIn, blocks, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
+        dIn = ctx->stageIn;
+    }
+    if (!outOnDevice)
+    {
+        rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, nBlocks * outBytes);
+        if (rc != CVTTB200_OK)
+            return rc;
+        dOut = ctx->stageOut;
+    }
+
+    OptionsPOD opt;
+    memcpy(&opt, options, sizeof(opt));
+    BC7PlanPOD planPOD;
+    memcpy(&planPOD, plan, sizeof(planPOD));
+    rc = launch_bc7(*ctx, dIn, nBlocks, dOut, opt, planPOD, stream);
+    if (rc != CVTTB200_OK)
+        return rc;
+
+    if (!outOnDevice)
+        CVTT_CUDA(cudaMemcpyAsync(out, dOut, nBlocks * outBytes, cudaMemcpyDeviceToHost, stream));
+    if (!inOnDevice || !outOnDevice)
+        CVTT_CUDA(cudaStreamSynchronize(stream));
+    return CVTTB200_OK;
+}
+
+} // extern "C"
