@@ -1,0 +1,275 @@
+#!/usr/bin/env python3
+"""Benchmark of the encode hot path: BC7, ConfigureBC7EncodingPlanFromQuality(100), default cvtt::Options, on a
+synthetic 4096x4096 RGBA8 texture (1 048 576 4x4 blocks) per GPU -- BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over the whole texture.  Prints ONE JSON line (rank 0).
+  value      Mblocks/s, whole job (all ranks), inputs resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e        same metric through the public call with HOST (pinned) buffers: H2D copy + kernel + D2H copy per step
+  roofline   HBM view of the kernel: algorithmic bytes (64 B read + 16 B written per block) / kernel time vs the
+             measured copy bandwidth.  The path is compute-bound by ~4 orders of magnitude, so `frac` is
+             tiny by construction; `issue_slot_frac_ncu` (from the committed ncu capture) is the fraction that matters.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, all host threads) on a bounded sample of the same texture
+With N > 1 (torchrun, one process per GPU) every rank encodes its own 4096x4096 texture (weak scaling) and the encoded
+ranges are gathered on rank 0 with one NCCL gather inside the timed step.
+`--impl reference` times the reference's own CPU implementation instead (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOAD = "EncodeBC7 plan=FromQuality(100) Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU"
+SIDE = 4096
+BLOCKS = (SIDE // 4) * (SIDE // 4)
+METRIC = "Mblocks/s (4x4) BC7 q100"
+ALGO_BYTES_PER_BLOCK = 64 + 16
+CPU_SAMPLE_BLOCKS = 262144               # first 1024 rows of the texture
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_constants():
+    """dram traffic per launch and issue-slot utilisation from the committed ncu capture (profiles/), if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "bc7_kernel_ncu_summary.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (nvidia-smi's clocks line, via NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {}
+            for n in dir(nv):
+                if n.startswith("nvmlClocksThrottleReason") or n.startswith("nvmlClocksEventReason"):
+                    v = getattr(nv, n)
+                    if isinstance(v, int) and v not in (0,) and bin(v).count("1") == 1:
+                        names.setdefault(v, n.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                except Exception:
+                    r = 0
+                for bit, name in names.items():
+                    if r & bit and name not in ("GpuIdle", "None", "All"):
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:          # never let monitoring break the benchmark
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified sources compiled by
+    oracle/Makefile), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.loader import Reference
+    from convectionkernels_b200 import synth
+    R = Reference()
+    threads = R.hardware_threads()
+    sample_blocks = 131072
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(SIDE, SIDE))[:sample_blocks]
+    opt, plan = R.default_options(), R.plan_from_quality(100)
+    for _ in range(args.warmup):
+        R.encode("BC7", blocks[:16384], opt, plan, threads=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.encode("BC7", blocks, opt, plan, threads=0)
+    dt = time.perf_counter() - t0
+    v = sample_blocks * args.steps / dt / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mblocks/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "first %d blocks of the texture per step" % sample_blocks},
+        "cpu_baseline": {"value": v, "unit": "Mblocks/s", "cores": threads, "kind": "reference", "sample": "%d blocks x %d steps, %d threads" % (sample_blocks, args.steps, threads)},
+        "e2e": {"value": v, "unit": "Mblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from convectionkernels_b200 import api, synth, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    api.init(local_rank)
+
+    # synthetic input: each rank owns one whole texture (weak scaling); pinned host copy for the e2e leg
+    blocks_np = synth.image_to_blocks(synth.mixed_rgba8(SIDE, SIDE, seed=1234 + rank))
+    host_in = torch.from_numpy(blocks_np.reshape(-1)).pin_memory()
+    host_out = torch.empty(BLOCKS * 16, dtype=torch.uint8).pin_memory()
+    d_in = host_in.to(dev)
+    d_out = torch.empty((BLOCKS, 16), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    opt = api.Options()
+    plan = api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(plan, 100)
+    total_blocks = BLOCKS * world
+
+    def step():
+        api.encode("BC7", d_in, opt, plan, out=d_out)
+        if distributed:
+            return sharding.gather_encoded(d_out, total_blocks, 16, dst=0)
+        return d_out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- device-timed leg -------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_events = []
+    launches0 = api.launch_count()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ms_total = 0.0
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                                   # L2 flush between timed iterations (outside the event pair)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        k0.record()
+        api.encode("BC7", d_in, opt, plan, out=d_out)
+        k1.record()
+        if distributed:
+            sharding.gather_encoded(d_out, total_blocks, 16, dst=0)
+        e_end.record()
+        torch.cuda.synchronize()
+        step_ms_total += e_start.elapsed_time(e_end)
+        kernel_events.append(k0.elapsed_time(k1))
+    barrier()
+    launches = api.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([step_ms_total], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = total_blocks * args.steps / (total_ms / 1e3) / 1e6
+    kernel_ms = float(np.mean(kernel_events))
+
+    # ---- end-to-end leg: public call with host buffers, copies inside the timed region ----------------------
+    host_out_np = host_out.numpy().reshape(BLOCKS, 16)
+    host_in_np = host_in.numpy()
+    api.encode("BC7", host_in_np, opt, plan, out=host_out_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        api.encode("BC7", host_in_np, opt, plan, out=host_out_np)       # returns when host_out is complete
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_blocks * args.steps / float(te.item()) / 1e6
+    same = bool((host_out_np == d_out.cpu().numpy()).all())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALGO_BYTES_PER_BLOCK * BLOCKS / (kernel_ms / 1e3) / 1e9
+        prof = profile_constants()
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                    "kernel": "bc7_encode_kernel<true>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BLOCK * BLOCKS,
+                    "note": "compute-bound path (~5e6 instructions per 80 bytes); see issue_slot_frac_ncu and DESIGN.md",
+                    "issue_slot_frac_ncu": prof.get("issue_slot_frac")}
+
+        # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same texture
+        cpu = None
+        try:
+            from oracle.loader import Reference
+            R = Reference()
+            threads = R.hardware_threads()
+            sample = blocks_np[:CPU_SAMPLE_BLOCKS]
+            ob, pb = np.frombuffer(bytes(memoryview(opt)), np.uint8), np.frombuffer(plan.tobytes(), np.uint8)
+            R.encode("BC7", sample[:8192], ob, pb, threads=0)
+            t0 = time.perf_counter()
+            ref_out = R.encode("BC7", sample, ob, pb, threads=0)
+            dt = time.perf_counter() - t0
+            cpu = {"value": CPU_SAMPLE_BLOCKS / dt / 1e6, "unit": "Mblocks/s", "cores": threads, "kind": "reference",
+                   "sample": "first %d blocks (1024 rows) of the texture, %d threads, %.1f s" % (CPU_SAMPLE_BLOCKS, threads, dt),
+                   "bit_exact_vs_gpu": bool((ref_out == host_out_np[:CPU_SAMPLE_BLOCKS]).all())}
+        except Exception as e:
+            cpu = {"value": None, "unit": "Mblocks/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Mblocks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "blocks_per_gpu": BLOCKS, "parallelism": "block-range shard x%d, NCCL gather of encoded ranges" % world if distributed else "single GPU",
+                       "l2": "256 MiB flush write between timed iterations", "plan": "ConfigureBC7EncodingPlanFromQuality(100)", "flags": "Default (BC7_FastIndexing|S3TC_Paranoid)"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "Mblocks/s", "h2d_bytes_per_step": BLOCKS * 64, "d2h_bytes_per_step": BLOCKS * 16,
+                    "host_equals_device_result": same},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }))
+
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

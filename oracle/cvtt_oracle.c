@@ -72,7 +72,22 @@ enum
 static float pm_min(float a, float b) { return (a < b) ? a : b; }   /* _mm_min_ps(a, b) */
 static float pm_max(float a, float b) { return (a > b) ? a : b; }   /* _mm_max_ps(a, b) */
 static float pm_clamp(float v, float lo, float hi) { return pm_max(pm_min(v, hi), lo); } /* ParallelMath.h:561-567 */
-static float pm_rcp(float v) { return _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps(v))); }     /* :569-575 */
+/* _mm_rcp_ps differs between CPU vendors/models.  On the BC7 path its argument is always a pixel count 1..16, so a
+ * 17-entry table recorded with a golden fixture can stand in for the instruction (tests/golden). */
+static float g_rcp_override[17];
+static int g_rcp_overridden = 0;
+static float pm_rcp(float v)                                                           /* :569-575 */
+{
+    if (g_rcp_overridden && v >= 1.0f && v <= 16.0f && v == (float)(int)v)
+        return g_rcp_override[(int)v];
+    return _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps(v)));
+}
+void cvtt_oracle_set_rcp_table(const float *t)
+{
+    g_rcp_overridden = (t != NULL);
+    if (t)
+        memcpy(g_rcp_override, t, sizeof(g_rcp_override));
+}
 static void pm_safe_denominator(float *v) { if (*v == 0.0f) *v = 1.0f; }               /* :472-475 */
 
 static uint16_t pm_round_u15(float v)                                                  /* :935-945 */

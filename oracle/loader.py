@@ -97,6 +97,11 @@ class Reference:
     def rcp(self, v):
         return float(self.lib.cvttref_rcp(ctypes.c_float(v)))
 
+    def rcp_table(self):
+        """_mm_rcp_ps(0..16) of this host as float32[17] (entry 0 is inf)."""
+        with np.errstate(all="ignore"):
+            return np.array([self.rcp(float(n)) for n in range(17)], dtype=np.float32)
+
     def hardware_threads(self):
         return int(self.lib.cvttref_hardware_threads())
 
@@ -111,7 +116,17 @@ class Oracle:
         L.cvtt_oracle_sizeof_plan.restype = ctypes.c_size_t
         L.cvtt_oracle_sizeof_options.restype = ctypes.c_size_t
         L.cvtt_oracle_encode_bc7.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cvtt_oracle_set_rcp_table.argtypes = [ctypes.c_void_p]
         assert L.cvtt_oracle_sizeof_plan() == 808 and L.cvtt_oracle_sizeof_options() == 44
+
+    def set_rcp_table(self, table):
+        """17 floats standing in for _mm_rcp_ps(0..16) (golden fixtures recorded on another CPU), or None."""
+        if table is None:
+            self.lib.cvtt_oracle_set_rcp_table(None)
+        else:
+            t = np.ascontiguousarray(table, dtype=np.float32)
+            assert t.size == 17
+            self.lib.cvtt_oracle_set_rcp_table(t.ctypes.data)
 
     def plan_from_quality(self, q):
         buf = np.zeros(808, dtype=np.uint8)

@@ -9,13 +9,13 @@
 
 using namespace cvttb200;
 
-extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const BC7PlanPOD *plan, int warpFlagsAllTrue)
+extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const BC7PlanPOD *plan, const float *rcpTable, int warpFlagsAllTrue)
 {
     if (nBlocks % 8)
         return -1;
     float rcpN[17];
     for (int n = 0; n < 17; n++)
-        rcpN[n] = _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
+        rcpN[n] = rcpTable ? rcpTable[n] : _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
     std::vector<uint32_t> cmds;
     int slots = bc7_compile_plan(*plan, cmds);
     if (slots > kBC7MaxSlots)

@@ -1,0 +1,150 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI (ctypes ->
+cvttb200_encode), against the golden vectors, the plain-C oracle, and -- where oracle/_ref travelled -- the unmodified
+reference on the same host.  Bit-exact is the bar everywhere."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, first_mismatch
+from convectionkernels_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt_bytes(o):
+    return np.frombuffer(bytes(memoryview(o)), np.uint8)
+
+
+def _plan_bytes(p):
+    return np.frombuffer(p.tobytes(), np.uint8)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.init(0)
+    yield
+    api.set_rcp_table(None)
+
+
+@pytest.mark.parametrize("name", golden_names("bc7_"))
+def test_golden_vectors(name):
+    g = load_golden(name)
+    api.set_rcp_table(g["rcp"])
+    try:
+        got = api.encode("BC7", g["blocks"], g["options"], g["plan"])
+    finally:
+        api.set_rcp_table(None)
+    assert (got == g["expected"]).all(), first_mismatch(g["expected"], got)
+
+
+@pytest.mark.parametrize("flags,refine", [(api.Flags.Default, 2), (api.Flags.Better, 2), (api.Flags.Default | api.Flags.Uniform, 2),
+                                          (api.Flags.Uniform, 1), (api.Flags.Default, 3), (api.Flags.Default, 0)])
+def test_against_oracle_random(oracle, flags, refine):
+    blocks = synth.random_blocks_rgba8(1024, seed=1000 + refine)
+    o = api.Options(flags=flags, refineRoundsBC7=refine)
+    for q in (100, 35):
+        p = api.BC7EncodingPlan()
+        api.ConfigureBC7EncodingPlanFromQuality(p, q)
+        want = oracle.encode_bc7(blocks, _opt_bytes(o), _plan_bytes(p))
+        got = api.encode("BC7", blocks, o, p)
+        assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_against_oracle_default_constructed_plan(oracle):
+    blocks = synth.random_blocks_rgba8(512, seed=31)
+    o, p = api.Options(), api.BC7EncodingPlan()
+    want = oracle.encode_bc7(blocks, _opt_bytes(o), _plan_bytes(p))
+    got = api.encode("BC7", blocks, o, p)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_edge_blocks_and_ragged_warps(oracle):
+    """flat / extreme / transparent blocks; 8, 24 and 40 blocks (partial warps); groups whose votes differ inside a warp"""
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    special = np.zeros((40, 16, 4), np.uint8)
+    special[1] = 255
+    special[2, :, 3] = 255
+    special[3, ::2] = 255
+    special[4] = (12, 200, 77, 255)
+    special[5] = (12, 200, 77, 128)
+    special[6, :, :3] = np.arange(16)[:, None] * 17
+    special[6, :, 3] = 255
+    special[7, :, 3] = np.arange(16) * 17
+    special[8:16] = synth.random_blocks_rgba8(8, seed=5)
+    special[8:16, :, 3] = 0                      # whole group transparent: RGB modes disabled for it
+    special[16:24] = synth.random_blocks_rgba8(8, seed=6)
+    special[16:24, :, 3] = 255
+    special[19, 7, 3] = 251                      # 250 < minAlpha < 255
+    special[24:40] = synth.random_blocks_rgba8(16, seed=7)
+    for n in (8, 24, 40):
+        want = oracle.encode_bc7(special[:n], _opt_bytes(o), _plan_bytes(p))
+        got = api.encode("BC7", special[:n], o, p)
+        assert got.shape == (n, 16)
+        assert (got == want).all(), first_mismatch(want, got)
+    assert api.encode("BC7", special[:0], o, p).shape == (0, 16)
+
+
+def test_argument_and_flag_errors():
+    o, p = api.Options(), api.BC7EncodingPlan()
+    with pytest.raises(api.CvttError) as e:
+        api.encode("BC7", np.zeros((12, 16, 4), np.uint8), o, p)
+    assert e.value.status == -1
+    with pytest.raises(api.CvttError) as e:
+        api.encode("BC1", np.zeros((8, 16, 4), np.uint8), o)
+    assert e.value.status == -2                   # not implemented is reported, never silently computed elsewhere
+
+
+def test_against_reference_on_this_host(reference):
+    """1024x1024 crop of the headline image, unmodified reference with all host threads vs the GPU path"""
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(1024, 1024))
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    want = reference.encode("BC7", blocks, _opt_bytes(o), _plan_bytes(p), threads=0)
+    got = api.encode("BC7", blocks, o, p)
+    assert (got == want).all(), first_mismatch(want, got)
+    # rcp table the library derived == the instruction the reference executes on this host
+    assert (api.get_rcp_table()[1:] == reference.rcp_table()[1:]).all()
+
+
+def test_device_pointers_match_host_pointers():
+    import torch
+    blocks = synth.random_blocks_rgba8(2048, seed=8)
+    o, p = api.Options(), api.BC7EncodingPlan()
+    host = api.encode("BC7", blocks, o, p)
+    dev_in = torch.from_numpy(blocks).cuda()
+    dev = api.encode("BC7", dev_in, o, p)
+    assert dev.is_cuda
+    assert (dev.cpu().numpy() == host).all()
+    before = api.launch_count()
+    api.encode("BC7", dev_in, o, p)
+    assert api.launch_count() == before + 1
+
+
+def test_full_size_properties(oracle):
+    """BASELINE.json configs[1] size (4096x4096 -> 1 048 576 blocks): determinism, independence of 8-block groups
+    (any aligned sub-range encodes to the same bytes), and a random sample of groups checked against the oracle."""
+    import torch
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(4096, 4096))
+    assert blocks.shape[0] == 1048576
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    d = torch.from_numpy(blocks).cuda()
+    full = api.encode("BC7", d, o, p).cpu().numpy()
+    again = api.encode("BC7", d, o, p).cpu().numpy()
+    assert (full == again).all()
+    # mode census: the synthetic image must exercise every mode
+    modes = np.bincount([(int(x) & -int(x)).bit_length() - 1 for x in full[:, 0]], minlength=8)
+    assert (modes[:8] > 0).all(), modes
+    # sub-range independence (what multi-GPU sharding relies on)
+    for first, n in ((8 * 1001, 8 * 37), (524288, 4096), (1048576 - 64, 64)):
+        part = api.encode("BC7", blocks[first:first + n], o, p)
+        assert (part == full[first:first + n]).all()
+    # sampled oracle comparison: 192 random groups
+    rng = np.random.default_rng(12)
+    groups = rng.choice(1048576 // 8, size=192, replace=False)
+    idx = (groups[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    want = oracle.encode_bc7(blocks[idx], _opt_bytes(o), _plan_bytes(p))
+    assert (full[idx] == want).all(), first_mismatch(want, full[idx])

@@ -1,0 +1,143 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports what include/cvtt_b200.h declares, plan
+configuration matches the oracle, the plan compiler emits a sane command stream, the per-thread device code compiled
+for the CPU (tests/hostsim, test-only) reproduces the golden vectors, and the product refuses to run without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, first_mismatch
+from convectionkernels_b200 import api, synth
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = api._lib()
+    header = open(os.path.join(ROOT, "include", "cvtt_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(cvttb200_\w+)\s*\(", header)))
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libcvtt_b200.so does not export " + n
+
+
+def test_struct_layouts_match_reference_sizes():
+    assert ctypes.sizeof(api.Options) == 44
+    assert ctypes.sizeof(api.BC7EncodingPlan) == 808
+    assert ctypes.sizeof(api.BC7FineTuningParams) == 285
+    o = api.Options()
+    assert o.flags == api.Flags.Default and o.refineRoundsBC7 == 2 and o.seedPoints == 4
+    assert abs(o.redWeight - 0.2125 / 0.7154) < 1e-7
+
+
+def test_block_sizes():
+    L = api._lib()
+    assert L.cvttb200_input_block_bytes(api.FORMATS["BC7"]) == 64 and L.cvttb200_output_block_bytes(api.FORMATS["BC7"]) == 16
+    assert L.cvttb200_input_block_bytes(api.FORMATS["BC6HU"]) == 128
+    assert L.cvttb200_output_block_bytes(api.FORMATS["BC1"]) == 8
+    assert L.cvttb200_input_block_bytes(99) == 0
+
+
+def test_plan_configuration_matches_oracle(oracle):
+    for q in list(range(1, 101)) + [0, 250]:
+        p = api.BC7EncodingPlan()
+        api.ConfigureBC7EncodingPlanFromQuality(p, q)
+        assert p.tobytes() == oracle.plan_from_quality(q).tobytes(), q
+    rng = np.random.default_rng(3)
+    for _ in range(25):
+        raw = rng.integers(0, 5, size=285, dtype=np.uint8)
+        raw[rng.random(285) < 0.4] = 0
+        ft = api.BC7FineTuningParams.from_buffer_copy(raw.tobytes())
+        p = api.BC7EncodingPlan()
+        assert api.ConfigureBC7EncodingPlanFromFineTuningParams(p, ft) is True
+        assert p.tobytes() == oracle.plan_from_finetune(raw).tobytes()
+
+
+def test_default_plan_matches_golden_default_plan():
+    g = load_golden("bc7_random_defaultplan")
+    assert api.BC7EncodingPlan().tobytes() == g["plan"].tobytes()
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(api.CvttError) as e:
+        api.encode("BC7", np.zeros((8, 16, 4), np.uint8), api.Options(), api.BC7EncodingPlan())
+    assert e.value.status == -3
+
+
+def test_argument_errors():
+    o, p = api.Options(), api.BC7EncodingPlan()
+    with pytest.raises(api.CvttError) as e:
+        api.encode("BC7", np.zeros((7, 16, 4), np.uint8), o, p)
+    assert e.value.status == -1
+    with pytest.raises(api.CvttError) as e:
+        api.encode("BC7", np.zeros((8, 16, 4), np.uint8), o, None)
+    assert e.value.status == -1
+
+
+# ---- the device code's per-thread logic, compiled for the CPU (test-only) ---------------------------------------------
+
+@pytest.fixture(scope="module")
+def hostsim():
+    out = os.path.join(ROOT, "tests", "_build", "libcvtt_hostsim.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    csrc = os.path.join(ROOT, "convectionkernels_b200", "csrc")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-w", "-I", csrc, "-o", out,
+                           os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"), os.path.join(csrc, "bc7_host.cpp")])
+    H = ctypes.CDLL(out)
+    H.hostsim_encode_bc7.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    return H
+
+
+def _hostsim_encode(H, blocks, options, plan, rcp, all_true=0):
+    src = np.ascontiguousarray(blocks).view(np.uint8).reshape(-1)
+    n = src.size // 64
+    out = np.zeros((n, 16), np.uint8)
+    options, plan = np.ascontiguousarray(options), np.ascontiguousarray(plan)
+    rcp = np.ascontiguousarray(rcp, dtype=np.float32)
+    rc = H.hostsim_encode_bc7(src.ctypes.data, n, out.ctypes.data, options.ctypes.data, plan.ctypes.data, rcp.ctypes.data, all_true)
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("name", golden_names("bc7_"))
+def test_device_logic_on_cpu_matches_golden(hostsim, name):
+    g = load_golden(name)
+    got = _hostsim_encode(hostsim, g["blocks"], g["options"], g["plan"], g["rcp"])
+    assert (got == g["expected"]).all(), first_mismatch(g["expected"], got)
+
+
+def test_device_logic_warp_skips_do_not_change_results(hostsim):
+    """warp-level 'does any lane need this' skips are pure work avoidance"""
+    g = load_golden("bc7_mixed_q100")
+    a = _hostsim_encode(hostsim, g["blocks"], g["options"], g["plan"], g["rcp"], 0)
+    b = _hostsim_encode(hostsim, g["blocks"], g["options"], g["plan"], g["rcp"], 1)
+    assert (a == b).all() and (a == g["expected"]).all()
+
+
+def test_device_logic_partial_warp_and_alpha_groups(hostsim, oracle):
+    blocks = synth.random_blocks_rgba8(40, seed=21)        # 1 full warp + 1 group
+    blocks[8:16, :, 3] = 0                                  # fully transparent group: RGB modes not allowed
+    blocks[16:24, :, 3] = 255
+    blocks[17, 3, 3] = 251                                  # nearly opaque
+    opt = np.frombuffer(bytes(memoryview(api.Options())), np.uint8)
+    for plan in (oracle.plan_from_quality(100), np.frombuffer(api.BC7EncodingPlan().tobytes(), np.uint8), oracle.plan_from_quality(5)):
+        rcp = _host_rcp()
+        want = oracle.encode_bc7(blocks, opt, plan)
+        got = _hostsim_encode(hostsim, blocks, opt, plan, rcp)
+        assert (got == want).all(), first_mismatch(want, got)
+
+
+def _host_rcp():
+    return api.get_rcp_table()
+
+
+def test_rcp_table_roundtrip():
+    t = api.get_rcp_table()
+    assert t.shape == (17,) and abs(t[2] - 0.5) < 1e-3 and abs(t[16] - 1 / 16) < 1e-4
+    api.set_rcp_table(np.arange(17, dtype=np.float32))
+    assert (api.get_rcp_table() == np.arange(17)).all()
+    api.set_rcp_table(None)
+    assert (api.get_rcp_table() == t).all()

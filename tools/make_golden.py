@@ -1,0 +1,51 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libcvtt_ref.so).  Run in the dev container
+(needs /root/reference to have been compiled by `make -C oracle ref`).  Each fixture stores the input PixelBlocks, the raw
+cvtt::Options / cvtt::BC7EncodingPlan bytes, the reference's output blocks and the generating host's _mm_rcp_ps(0..16)
+table (the reference's refinement step depends on that instruction; consumers replay it through set_rcp_table)."""
+import os, sys, struct
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle.loader import Reference
+from convectionkernels_b200 import synth
+
+R = Reference()
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+rcp = R.rcp_table()
+
+
+def options(flags=None, refine=None, weights=None):
+    o = R.default_options().copy()
+    if flags is not None:
+        o[0:4] = np.frombuffer(struct.pack("<I", flags), np.uint8)
+    if weights is not None:
+        o[8:24] = np.frombuffer(struct.pack("<4f", *weights), np.uint8)
+    if refine is not None:
+        o[24:28] = np.frombuffer(struct.pack("<i", refine), np.uint8)
+    return o
+
+
+def save(name, fmt, blocks, opt, plan=None):
+    out = R.encode(fmt, blocks, opt, plan)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), fmt=fmt, blocks=blocks, options=opt,
+                        plan=plan if plan is not None else np.zeros(0, np.uint8), expected=out, rcp=rcp)
+    print(name, fmt, blocks.shape, "->", out.shape)
+
+
+rb = synth.random_blocks_rgba8(256, seed=11)
+grad = synth.image_to_blocks(synth.gradient_rgba8(64, 64))          # config 1 content, 256 blocks
+mixed = synth.image_to_blocks(synth.mixed_rgba8(128, 128))[:512]
+q100, qdef, q40 = R.plan_from_quality(100), R.default_plan(), R.plan_from_quality(40)
+
+save("bc7_random_q100", "BC7", rb, options(), q100)
+save("bc7_random_defaultplan", "BC7", rb, options(), qdef)
+save("bc7_random_q40", "BC7", rb, options(), q40)
+save("bc7_random_better", "BC7", rb, options(flags=0x180), q100)                  # Flags::Better: no fast indexing
+save("bc7_random_uniform", "BC7", rb, options(flags=0x208), q100)
+save("bc7_random_refine3_weights", "BC7", rb, options(refine=3, weights=(1.0, 0.5, 2.0, 0.25)), q100)
+save("bc7_random_refine1", "BC7", rb, options(refine=1), q100)
+save("bc7_gradient_q100", "BC7", grad, options(), q100)
+save("bc7_mixed_q100", "BC7", mixed, options(), q100)
+# config 1 (plumbing, CPU only): EncodeBC1 on the 256x256 gradient
+save("bc1_gradient256", "BC1", synth.image_to_blocks(synth.gradient_rgba8(256, 256)), options())
