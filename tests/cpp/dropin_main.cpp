@@ -1,0 +1,47 @@
+// A reference-style caller (cf. reference etc2packer/etc2packer.cpp:215-282): packs 8 horizontally adjacent 4x4 blocks per
+// call and encodes them with cvtt::Kernels::EncodeBC7, then encodes the same image with the whole-image entry point and
+// checks both agree.  Prints a 64-bit FNV hash of the output so a harness can compare it with the oracle's.
+// usage: dropin_main <width> <height> <quality>
+#include <vector>
+#include <stdint.h>
+#include <string.h>
+#include "cvtt_b200_dropin.h"
+
+int main(int argc, char **argv)
+{
+    const int w = argc > 1 ? atoi(argv[1]) : 64, h = argc > 2 ? atoi(argv[2]) : 64, quality = argc > 3 ? atoi(argv[3]) : 100;
+    std::vector<uint8_t> image((size_t)w * h * 4);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+        {
+            uint8_t *p = &image[((size_t)y * w + x) * 4];
+            p[0] = (uint8_t)x; p[1] = (uint8_t)y; p[2] = (uint8_t)((x + y) / 2); p[3] = (uint8_t)(((x / 32) & 1) ? 255 : 255 - y);
+        }
+
+    cvtt::Options options;
+    cvtt::BC7EncodingPlan plan;
+    cvtt::Kernels::ConfigureBC7EncodingPlanFromQuality(plan, quality);
+
+    const int bw = w / 4, bh = h / 4;
+    std::vector<cvtt::PixelBlockU8> blocks((size_t)bw * bh);
+    for (int by = 0; by < bh; by++)
+        for (int bx = 0; bx < bw; bx++)
+            for (int py = 0; py < 4; py++)
+                memcpy(blocks[(size_t)by * bw + bx].m_pixels[py * 4], &image[(((size_t)by * 4 + py) * w + bx * 4) * 4], 16);
+
+    std::vector<uint8_t> perCall(blocks.size() * 16), whole(blocks.size() * 16);
+    for (size_t b = 0; b < blocks.size(); b += cvtt::NumParallelBlocks)
+        cvtt::Kernels::EncodeBC7(&perCall[b * 16], &blocks[b], options, plan);
+    cvtt::Kernels::B200::EncodeBC7(whole.data(), blocks.data(), blocks.size(), options, plan);
+
+    if (memcmp(perCall.data(), whole.data(), whole.size()) != 0)
+    {
+        fprintf(stderr, "8-block calls and whole-image call disagree\n");
+        return 2;
+    }
+    uint64_t hash = 1469598103934665603ull;
+    for (size_t i = 0; i < whole.size(); i++)
+        hash = (hash ^ whole[i]) * 1099511628211ull;
+    printf("%zu blocks, fnv64 %016llx\n", blocks.size(), (unsigned long long)hash);
+    return 0;
+}
