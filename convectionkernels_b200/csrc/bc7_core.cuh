@@ -119,10 +119,50 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // EndpointSelector<NCH, 8> over the pixels of `mask` (ascending pixel order), with unit pixel weights.
-    // Pixels are read as (value + kMagic); wv are the channel weights (possibly rotated for modes 4/5).
-    template<int NCH>
-    CVTT_HD void bc7_endpoint_selector(const F4 *pix, int stride, uint32_t mask, int n, const float *wv, float *base, float *offs)
+    // Per-lane pixel storage.  STRIDE is the element stride between consecutive entries of one lane (the CTA
+    // size in the kernel, 1 on the CPU), so that every unrolled access has a compile-time offset.
+    //   raw[px]  the block's 16 pixels as packed RGBA8 (never modified)
+    //   gv[i]    the i-th pixel of the current pixel subset as (value + kMagic), channels possibly rotated
+    //   gw[i]    the same pixel pre-weighted: (value * channelWeight), BCCommon::PreWeightPixelsLDR (BCCommon.h:81-99)
+    template<int STRIDE>
+    struct BC7Lane
+    {
+        const uint32_t *raw;
+        F4 *gv;
+        F4 *gw;
+    };
+
+    CVTT_HD F4 bc7_expand_pixel(uint32_t w)
+    {
+        F4 p;
+#if defined(__CUDA_ARCH__)
+        p.x = __uint_as_float(__byte_perm(w, kMagicBits, 0x7650));
+        p.y = __uint_as_float(__byte_perm(w, kMagicBits, 0x7651));
+        p.z = __uint_as_float(__byte_perm(w, kMagicBits, 0x7652));
+        p.w = __uint_as_float(__byte_perm(w, kMagicBits, 0x7653));
+#else
+        p.x = as_float(kMagicBits | (w & 0xffu));
+        p.y = as_float(kMagicBits | ((w >> 8) & 0xffu));
+        p.z = as_float(kMagicBits | ((w >> 16) & 0xffu));
+        p.w = as_float(kMagicBits | (w >> 24));
+#endif
+        return p;
+    }
+
+    // swaps the colour channel (rotation - 1) with alpha, BC67.cpp:1690-1716
+    CVTT_HD void bc7_rotate(F4 &p, int rotation)
+    {
+        const float t = p.w;
+        if (rotation == 1) { p.w = p.x; p.x = t; }
+        else if (rotation == 2) { p.w = p.y; p.y = t; }
+        else if (rotation == 3) { p.w = p.z; p.z = t; }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // EndpointSelector<NCH, 8> over the n gathered pixels, with unit pixel weights.  gw holds the pre-weighted
+    // pixels; wv are the channel weights they were weighted with (GetEndpoints divides by them again).
+    template<int NCH, int STRIDE>
+    CVTT_HD void bc7_endpoint_selector(const F4 *gw, int n, const float *wv, float *base, float *offs)
     {
         float centroid[NCH], cov[NCH * (NCH + 1) / 2];
 #pragma unroll
@@ -133,32 +173,32 @@ namespace cvttb200
             cov[i] = 0.0f;
 
         // pass 0: centroid (EndpointSelector.h:73-86)
-        for (uint32_t m = mask; m; m &= m - 1)
+#pragma unroll 2
+        for (int i = 0; i < n; i++)
         {
-            int px = ctz32(m);
-            F4 p = pix[px * stride];
+            const F4 p = gw[i * STRIDE];
             const float pv[4] = { p.x, p.y, p.z, p.w };
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
-                centroid[ch] = fadd(centroid[ch], fmul(fsub(pv[ch], kMagic), wv[ch]));
+                centroid[ch] = fadd(centroid[ch], pv[ch]);
         }
         {
-            float denom = (float)n;
+            const float denom = (float)n;
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
                 centroid[ch] = fdiv(centroid[ch], denom);
         }
 
         // pass 1: covariance (EndpointSelector.h:88-95, PackedCovarianceMatrix.h:29-40)
-        for (uint32_t m = mask; m; m &= m - 1)
+#pragma unroll 2
+        for (int i = 0; i < n; i++)
         {
-            int px = ctz32(m);
-            F4 p = pix[px * stride];
+            const F4 p = gw[i * STRIDE];
             const float pv[4] = { p.x, p.y, p.z, p.w };
             float diff[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
-                diff[ch] = fsub(fmul(fsub(pv[ch], kMagic), wv[ch]), centroid[ch]);
+                diff[ch] = fsub(pv[ch], centroid[ch]);
             int index = 0;
 #pragma unroll
             for (int row = 0; row < NCH; row++)
@@ -176,6 +216,7 @@ namespace cvttb200
         for (int ch = 0; ch < NCH; ch++)
             approx[ch] = 1.0f;
 
+#pragma unroll 1
         for (int it = 0; it < 8; it++)
         {
             float product[NCH];
@@ -214,15 +255,15 @@ namespace cvttb200
 
         // pass 2: extent along the axis (EndpointSelector.h:132-140)
         float minDist = FLT_MAX, maxDist = -FLT_MAX;
-        for (uint32_t m = mask; m; m &= m - 1)
+#pragma unroll 2
+        for (int i = 0; i < n; i++)
         {
-            int px = ctz32(m);
-            F4 p = pix[px * stride];
+            const F4 p = gw[i * STRIDE];
             const float pv[4] = { p.x, p.y, p.z, p.w };
             float dist = 0.0f;
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
-                dist = fadd(dist, fmul(direction[ch], fsub(fmul(fsub(pv[ch], kMagic), wv[ch]), centroid[ch])));
+                dist = fadd(dist, fmul(direction[ch], fsub(pv[ch], centroid[ch])));
             minDist = sse_min(minDist, dist);
             maxDist = sse_max(maxDist, dist);
         }
@@ -231,41 +272,191 @@ namespace cvttb200
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
         {
-            float mn = fadd(centroid[ch], fmul(direction[ch], minDist));
-            float mx = fadd(centroid[ch], fmul(direction[ch], maxDist));
+            const float mn = fadd(centroid[ch], fmul(direction[ch], minDist));
+            const float mx = fadd(centroid[ch], fmul(direction[ch], maxDist));
             base[ch] = fdiv(mn, wv[ch]);
             offs[ch] = fdiv(fsub(mx, mn), wv[ch]);
         }
     }
 
     // ---------------------------------------------------------------------------------------------------------
+    // Compile-time description of the single-plane modes: g_modes (BC67.cpp:108-119), the parity-bit loop bounds
+    // (BC67.cpp:1183-1189) and CompressEndpoints0-7 (BC67.cpp:862-938) in the exact-fp32 form of QuantConst.
+    template<int MODE> struct BC7ModeT;
+    template<> struct BC7ModeT<0> { enum { NCH = 3, BITS = 4, WITHP = 1, UNQ = 5, PMAX = 4, SHAREDP = 0, IB = 3 }; };
+    template<> struct BC7ModeT<1> { enum { NCH = 3, BITS = 6, WITHP = 1, UNQ = 7, PMAX = 2, SHAREDP = 1, IB = 3 }; };
+    template<> struct BC7ModeT<2> { enum { NCH = 3, BITS = 5, WITHP = 0, UNQ = 5, PMAX = 1, SHAREDP = 0, IB = 2 }; };
+    template<> struct BC7ModeT<3> { enum { NCH = 3, BITS = 7, WITHP = 1, UNQ = 0, PMAX = 4, SHAREDP = 0, IB = 2 }; };
+    template<> struct BC7ModeT<6> { enum { NCH = 4, BITS = 7, WITHP = 1, UNQ = 0, PMAX = 4, SHAREDP = 0, IB = 4 }; };
+    template<> struct BC7ModeT<7> { enum { NCH = 4, BITS = 5, WITHP = 1, UNQ = 6, PMAX = 4, SHAREDP = 0, IB = 2 }; };
+
+    // Quantises the integer-valued endpoint channel c to the mode's precision with parity bit p and expands it
+    // back to 8 bits; the result is returned biased (value + kMagic).  qAddP = qAdd[p], pM = p + kMagic.
+    template<int MODE>
+    CVTT_HD float bc7_quant_biased(float c, float qAddP, float p, float pM)
+    {
+        typedef BC7ModeT<MODE> M;
+        const float qMul = M::WITHP ? (float)((1 << (M::BITS + 1)) - 1) / 512.0f : (float)((1 << M::BITS) - 1) / 256.0f;
+        const float vb = xfma(c, qMul, qAddP) + kMagic;
+        if (M::UNQ)
+        {
+            const int s = M::UNQ ? 2 * M::UNQ - 8 : 0;
+            const float uMul = (float)(1 << (8 - M::UNQ)), uScale = 1.0f / (float)(1 << s), uOff = -(float)((1 << s) - 1) / (float)(1 << (s + 1));
+            const float v = vb - kMagic;
+            const float v2 = M::WITHP ? xfma(v, 2.0f, p) : v;
+            const float flb = xfma(v2, uScale, uOff) + kMagic;
+            return xfma(v2, uMul, flb);
+        }
+        else if (M::WITHP)
+            return xfma(vb - kMagic, 2.0f, pM);
+        else
+            return vb;
+    }
+
+    template<int MODE>
+    CVTT_HD float bc7_quant_add(int p)
+    {
+        typedef BC7ModeT<MODE> M;
+        if (M::WITHP)
+        {
+            const float a0 = (float)(2 * 255 - 511) / 1024.0f, a1 = (float)(2 * ((1 << (8 - M::BITS)) - 1) - 511) / 1024.0f;
+            return p ? a1 : a0;
+        }
+        return (float)(2 * (127 + (1 << (7 - M::BITS))) - 255) / 512.0f;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // One trial of the inner search: index selection, reconstruction error and (REFINE) the refiner's sums over the
+    // n gathered pixels (BC67.cpp:1355-1392).
+    template<int NCH, int IB, bool FAST, bool REFINE, int STRIDE>
+    CVTT_HD float bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const float *om, const float *axis, const float *d64,
+        const float *bq, float *tv, float &tt, float &ts)
+    {
+        const float maxV = (float)((1 << IB) - 1), wScale = 64.0f / (float)((1 << IB) - 1), rcpMaxIndex = 1.0f / (float)((1 << IB) - 1);
+        float acc[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+            acc[ch] = 0.0f;
+        float slowErr = 0.0f;
+
+#pragma unroll 2
+        for (int i = 0; i < n; i++)
+        {
+            const F4 p = gv[i * STRIDE];
+            const float pv[4] = { p.x, p.y, p.z, p.w };
+
+            // SelectIndexLDR (IndexSelector.h:124-131)
+            float dist = fmul(fsub(pv[0], om[0]), axis[0]);
+#pragma unroll
+            for (int ch = 1; ch < NCH; ch++)
+                dist = fadd(dist, fmul(fsub(pv[ch], om[ch]), axis[ch]));
+            float idxf = rne(clamp_for_round(dist, 0.0f, maxV));
+
+            // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43)
+            const float wf = xfma(idxf, wScale, kMagic) - kMagic;
+            float d2[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+            {
+                const float df = (xfma(wf, d64[ch], bq[ch]) + kMagic) - pv[ch];
+                if (FAST)
+                    acc[ch] = xfma(df, df, acc[ch]);                // exact (< 2^24)
+                else
+                    d2[ch] = df * df;                               // exact (< 2^16)
+            }
+
+            if (!FAST)
+            {
+                // BC67.cpp:1364-1386: probe index-1 and index+1 in weighted float error (wSq is 1 under Flags::Uniform)
+                float error = fmul(d2[0], P.wSq[0]);
+#pragma unroll
+                for (int ch = 1; ch < NCH; ch++)
+                    error = fadd(error, fmul(d2[ch], P.wSq[ch]));
+                const float alt[2] = { fmaxf(idxf, 1.0f) - 1.0f, fminf(idxf + 1.0f, maxV) };
+#pragma unroll
+                for (int ii = 0; ii < 2; ii++)
+                {
+                    const float awf = xfma(alt[ii], wScale, kMagic) - kMagic;
+                    float altError = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++)
+                    {
+                        const float df = (xfma(awf, d64[ch], bq[ch]) + kMagic) - pv[ch];
+                        const float sq = df * df;
+                        altError = (ch == 0) ? fmul(sq, P.wSq[0]) : fadd(altError, fmul(sq, P.wSq[ch]));
+                    }
+                    const bool better = altError < error;
+                    error = sse_min(error, altError);
+                    if (better)
+                        idxf = alt[ii];
+                }
+                slowErr = fadd(slowErr, error);
+            }
+
+            // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92)
+            if (REFINE)
+            {
+                const F4 q = gw[i * STRIDE];
+                const float qv[4] = { q.x, q.y, q.z, q.w };
+                const float t = fmul(idxf, rcpMaxIndex);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                    tv[ch] = fadd(tv[ch], fmul(t, qv[ch]));
+                tt = fadd(tt, fmul(t, t));
+                ts = fadd(ts, t);
+            }
+        }
+
+        // AggregatedError::Finalize (AggregatedError.h:25-46)
+        if (!FAST)
+            return slowErr;
+        float shapeError;
+        if (P.flags & kFlag_Uniform)
+        {
+            shapeError = acc[0];
+#pragma unroll
+            for (int ch = 1; ch < NCH; ch++)
+                shapeError = shapeError + acc[ch];
+        }
+        else
+        {
+            shapeError = fmul(acc[0], P.wSq[0]);
+#pragma unroll
+            for (int ch = 1; ch < NCH; ch++)
+                shapeError = fadd(shapeError, fmul(acc[ch], P.wSq[ch]));
+        }
+        return shapeError;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
     // The inner search of TrySinglePlane for one (mode, shape): tweaks x parity bits x refine rounds
-    // (BC67.cpp:1298-1432).  NCH = numRealChannels.  Result: best error / endpoints / indexes of the shape.
+    // (BC67.cpp:1298-1432).  Result: best error and endpoints of the shape; the indexes of the overall winner are
+    // re-derived from its endpoints at the end (bc7_derive_indices), they are a pure function of them.
     struct BC7ShapeBest
     {
         float err;
         uint32_t e0, e1;      // packed endpoint bytes
-        uint32_t idxLo, idxHi;
     };
 
-    template<int NCH, bool FAST>
-    CVTT_HD void bc7_shape_trials(const BC7Params &P, const BC7ModeConst &mc, const F4 *pix, int stride, uint32_t mask, int n,
-        int seeds, const float *base, const float *offs, const float *sumV, float staticAlphaError, BC7ShapeBest &out)
+    template<int MODE, bool FAST, int STRIDE>
+    CVTT_HD void bc7_shape_trials(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
+        const float *sumV, float staticAlphaError, BC7ShapeBest &out)
     {
-        const IndexConst &ic = P.ic[mc.indexBits - 2];
-        const float maxV = ic.maxValue, wScale = ic.wScale, rcpMaxIndex = ic.rcpMaxIndex;
+        typedef BC7ModeT<MODE> M;
+        enum { NCH = M::NCH };
+        const IndexConst &ic = P.ic[M::IB - 2];
+        const float maxV = (float)((1 << M::IB) - 1);
         const int R = P.refineRounds;
-        const bool uniform = (P.flags & kFlag_Uniform) != 0;
         const float wN = (float)n, wRcp = P.rcpN[n];
 
         float bestErr = FLT_MAX;
         int bestSeq = 0x7fffffff;
         float bE0[NCH], bE1[NCH];
-        uint32_t bLo = 0, bHi = 0;
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
-            bE0[ch] = bE1[ch] = 0.0f;
+            bE0[ch] = bE1[ch] = kMagic;
 
+#pragma unroll 1
         for (int tweak = 0; tweak < seeds; tweak++)
         {
             // UnfinishedEndpoints::FinishLDR (UnfinishedEndpoints.h:75-91)
@@ -278,10 +469,13 @@ namespace cvttb200
                 u1[ch] = rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf1)), 0.0f, 255.0f));
             }
 
-            for (int pIter = 0; pIter < mc.parityBitMax; pIter++)
+#pragma unroll 1
+            for (int pIter = 0; pIter < M::PMAX; pIter++)
             {
                 const int p0 = pIter & 1;
-                const int p1 = mc.sharedP ? p0 : ((pIter >> 1) & 1);
+                const int p1 = M::SHAREDP ? p0 : ((pIter >> 1) & 1);
+                const float qA0 = bc7_quant_add<MODE>(p0), qA1 = bc7_quant_add<MODE>(p1);
+                const float pf0 = (float)p0, pf1 = (float)p1, pM0 = kMagic + pf0, pM1 = kMagic + pf1;
 
                 float e0[NCH], e1[NCH];
 #pragma unroll
@@ -291,26 +485,30 @@ namespace cvttb200
                     e1[ch] = u1[ch];
                 }
 
+#pragma unroll 1
                 for (int refine = 0; refine < R; refine++)
                 {
                     const int seq = ((pIter * 4 + tweak) << 16) + refine;   // reference order: pIter, tweak, refine
                     const bool lastRound = (refine == R - 1);
 
-                    // CompressEndpointsN (BC67.cpp:862-938)
-                    float q0[NCH], q1[NCH];
+                    // CompressEndpointsN (BC67.cpp:862-938); q0b/q1b are biased
+                    float q0b[NCH], q1b[NCH];
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
                     {
-                        q0[ch] = quant_one(mc.q, e0[ch], p0);
-                        q1[ch] = quant_one(mc.q, e1[ch], p1);
+                        q0b[ch] = bc7_quant_biased<MODE>(e0[ch], qA0, pf0, pM0);
+                        q1b[ch] = bc7_quant_biased<MODE>(e1[ch], qA1, pf1, pM1);
                     }
 
                     // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
                     // the fourth channel contributes exactly +0 to every sum below and is left out.
-                    float dW[NCH], axis[NCH], om[NCH], d64[NCH], bq[NCH];
+                    float dq[NCH], dW[NCH], axis[NCH], d64[NCH], bq[NCH];
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
-                        dW[ch] = fmul(fsub(q1[ch], q0[ch]), P.w[ch]);
+                    {
+                        dq[ch] = q1b[ch] - q0b[ch];                             // exact
+                        dW[ch] = fmul(dq[ch], P.w[ch]);
+                    }
                     float lenSq = fmul(dW[0], dW[0]);
 #pragma unroll
                     for (int ch = 1; ch < NCH; ch++)
@@ -321,126 +519,20 @@ namespace cvttb200
                     for (int ch = 0; ch < NCH; ch++)
                     {
                         axis[ch] = fmul(fmul(dW[ch], P.w[ch]), mdl);
-                        om[ch] = q0[ch] + kMagic;                               // exact
-                        d64[ch] = (q1[ch] - q0[ch]) * 0.015625f;                // exact
-                        bq[ch] = q0[ch] + 0.0078125f;                           // exact
+                        d64[ch] = dq[ch] * 0.015625f;                           // exact
+                        bq[ch] = (q0b[ch] - kMagic) + 0.0078125f;               // exact
                     }
 
-                    float acc[NCH], tv[NCH];
+                    float tv[NCH], tt = 0.0f, ts = 0.0f;
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
-                        acc[ch] = tv[ch] = 0.0f;
-                    float tt = 0.0f, ts = 0.0f, slowErr = 0.0f;
-                    uint32_t iLo = 0, iHi = 0;
+                        tv[ch] = 0.0f;
 
-                    for (uint32_t m = mask; m; m &= m - 1)
-                    {
-                        const int px = ctz32(m);
-                        const F4 p = pix[px * stride];
-                        const float pv[4] = { p.x, p.y, p.z, p.w };
-
-                        // SelectIndexLDR (IndexSelector.h:124-131)
-                        float dist = fmul(fsub(pv[0], om[0]), axis[0]);
-#pragma unroll
-                        for (int ch = 1; ch < NCH; ch++)
-                            dist = fadd(dist, fmul(fsub(pv[ch], om[ch]), axis[ch]));
-                        float idxf = rne(clamp_for_round(dist, 0.0f, maxV));
-
-                        // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43)
-                        float wf = xfma(idxf, wScale, kMagic) - kMagic;
-                        float d2[NCH];
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ch++)
-                        {
-                            const float df = (xfma(wf, d64[ch], bq[ch]) + kMagic) - pv[ch];
-                            if (FAST)
-                                acc[ch] = xfma(df, df, acc[ch]);                // exact (< 2^24)
-                            else
-                                d2[ch] = df * df;                               // exact (< 2^16)
-                        }
-
-                        if (!FAST)
-                        {
-                            // BC67.cpp:1364-1386: probe index-1 and index+1 in weighted float error
-                            float error;
-                            if (uniform)
-                            {
-                                error = d2[0];
-#pragma unroll
-                                for (int ch = 1; ch < NCH; ch++)
-                                    error = error + d2[ch];
-                            }
-                            else
-                            {
-                                error = fmul(d2[0], P.wSq[0]);
-#pragma unroll
-                                for (int ch = 1; ch < NCH; ch++)
-                                    error = fadd(error, fmul(d2[ch], P.wSq[ch]));
-                            }
-                            const float alt[2] = { fmaxf(idxf, 1.0f) - 1.0f, fminf(idxf + 1.0f, maxV) };
-#pragma unroll
-                            for (int ii = 0; ii < 2; ii++)
-                            {
-                                float awf = xfma(alt[ii], wScale, kMagic) - kMagic;
-                                float altError;
-#pragma unroll
-                                for (int ch = 0; ch < NCH; ch++)
-                                {
-                                    float df = (xfma(awf, d64[ch], bq[ch]) + kMagic) - pv[ch];
-                                    float sq = df * df;
-                                    if (uniform)
-                                        altError = (ch == 0) ? sq : altError + sq;
-                                    else
-                                        altError = (ch == 0) ? fmul(sq, P.wSq[0]) : fadd(altError, fmul(sq, P.wSq[ch]));
-                                }
-                                const bool better = altError < error;
-                                error = sse_min(error, altError);
-                                if (better)
-                                    idxf = alt[ii];
-                            }
-                            slowErr = fadd(slowErr, error);
-                        }
-
-                        // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92); the sum of v is the
-                        // per-shape constant sumV
-                        if (!lastRound)
-                        {
-                            const float t = fmul(idxf, rcpMaxIndex);
-#pragma unroll
-                            for (int ch = 0; ch < NCH; ch++)
-                                tv[ch] = fadd(tv[ch], fmul(t, fmul(fsub(pv[ch], kMagic), P.w[ch])));
-                            tt = fadd(tt, fmul(t, t));
-                            ts = fadd(ts, t);
-                        }
-
-                        const uint32_t nib = as_uint(idxf + kMagic) & 15u;
-                        if (px < 8)
-                            iLo |= nib << (4 * px);
-                        else
-                            iHi |= nib << (4 * (px - 8));
-                    }
-
-                    // AggregatedError::Finalize (AggregatedError.h:25-46)
                     float shapeError;
-                    if (FAST)
-                    {
-                        if (uniform)
-                        {
-                            shapeError = acc[0];
-#pragma unroll
-                            for (int ch = 1; ch < NCH; ch++)
-                                shapeError = shapeError + acc[ch];
-                        }
-                        else
-                        {
-                            shapeError = fmul(acc[0], P.wSq[0]);
-#pragma unroll
-                            for (int ch = 1; ch < NCH; ch++)
-                                shapeError = fadd(shapeError, fmul(acc[ch], P.wSq[ch]));
-                        }
-                    }
+                    if (lastRound)
+                        shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, q0b, axis, d64, bq, tv, tt, ts);
                     else
-                        shapeError = slowErr;
+                        shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, q0b, axis, d64, bq, tv, tt, ts);
                     if (NCH == 3)
                         shapeError = fadd(shapeError, staticAlphaError);
 
@@ -451,11 +543,9 @@ namespace cvttb200
 #pragma unroll
                         for (int ch = 0; ch < NCH; ch++)
                         {
-                            bE0[ch] = q0[ch];
-                            bE1[ch] = q1[ch];
+                            bE0[ch] = q0b[ch];
+                            bE1[ch] = q1b[ch];
                         }
-                        bLo = iLo;
-                        bHi = iHi;
                     }
 
                     // EndpointRefiner::GetRefinedEndpointsLDR (EndpointRefiner.h:99-152)
@@ -468,8 +558,8 @@ namespace cvttb200
 #pragma unroll
                         for (int ch = 0; ch < NCH; ch++)
                         {
-                            float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sumV[ch]), wRcp)), adenom);
-                            float b = fmul(fsub(sumV[ch], fmul(a, ts)), wRcp);
+                            const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sumV[ch]), wRcp)), adenom);
+                            const float b = fmul(fsub(sumV[ch], fmul(a, ts)), wRcp);
                             float p1v = b, p2v = fadd(a, b);
                             if (adenomZero)
                                 p1v = p2v = fmul(sumV[ch], wRcp);
@@ -482,22 +572,26 @@ namespace cvttb200
         }
 
         out.err = bestErr;
-        out.e0 = pack_ep_bytes(bE0, NCH);
-        out.e1 = pack_ep_bytes(bE1, NCH);
-        out.idxLo = bLo;
-        out.idxHi = bHi;
+        uint32_t r0 = 0, r1 = 0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+        {
+            r0 |= (as_uint(bE0[ch]) & 0xffu) << (8 * ch);
+            r1 |= (as_uint(bE1[ch]) & 0xffu) << (8 * ch);
+        }
+        out.e0 = r0;
+        out.e1 = r1;
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // One (mode, rotation, indexSelector) of TryDualPlane (BC67.cpp:1664-1965).  The caller has swapped the
-    // rotation's colour channel with alpha in the pixel store, so .xyz is the rotated RGB and .w the scalar
-    // plane; wr/wSqr/rcpWr are the weights permuted the same way.
-    template<bool FAST>
-    CVTT_HD void bc7_dual_plane(const BC7Params &P, const F4 *pix, int stride, int mode, int rotation, int indexSelector, int seeds,
+    // One (mode, rotation, indexSelector) of TryDualPlane (BC67.cpp:1664-1965).  The caller has gathered the 16
+    // pixels with the rotation's colour channel swapped with alpha, so .xyz is the rotated RGB and .w the scalar
+    // plane; wr/wSqr/rcpWr are the weights permuted the same way (gw is weighted with wr).
+    template<bool FAST, int STRIDE>
+    CVTT_HD void bc7_dual_plane(const BC7Params &P, const F4 *gv, const F4 *gw, int mode, int rotation, int indexSelector, int seeds,
         const float *wr, const float *wSqr, const float *rcpWr, BC7Work &work)
     {
         const int R = P.refineRounds;
-        const bool uniform = (P.flags & kFlag_Uniform) != 0;
         const int rgbPrec = (mode == 4 && indexSelector) ? 3 : 2;
         const int alphaPrec = (mode == 4 && !indexSelector) ? 3 : 2;
         const IndexConst &icRGB = P.ic[rgbPrec - 2], &icA = P.ic[alphaPrec - 2];
@@ -505,13 +599,15 @@ namespace cvttb200
         const float wN = 16.0f, wRcp = P.rcpN[16];
 
         float base[3], offs[3];
-        bc7_endpoint_selector<3>(pix, stride, 0xffffu, 16, wr, base, offs);
+        bc7_endpoint_selector<3, STRIDE>(gw, 16, wr, base, offs);
 
         // alpha range, sums of the refiner's v terms (identical for every trial)
-        float aMin, aMax, sumV[3] = { 0.0f, 0.0f, 0.0f }, sumA = 0.0f;
+        float aMin = 0.0f, aMax = 0.0f, sumV[3] = { 0.0f, 0.0f, 0.0f }, sumA = 0.0f;
+#pragma unroll 2
         for (int px = 0; px < 16; px++)
         {
-            const F4 p = pix[px * stride];
+            const F4 p = gv[px * STRIDE];
+            const F4 q = gw[px * STRIDE];
             const float a = p.w - kMagic;
             if (px == 0)
                 aMin = aMax = a;
@@ -520,16 +616,16 @@ namespace cvttb200
                 aMin = fminf(aMin, a);
                 aMax = fmaxf(aMax, a);
             }
-            sumV[0] = fadd(sumV[0], fmul(p.x - kMagic, wr[0]));
-            sumV[1] = fadd(sumV[1], fmul(p.y - kMagic, wr[1]));
-            sumV[2] = fadd(sumV[2], fmul(p.z - kMagic, wr[2]));
+            sumV[0] = fadd(sumV[0], q.x);
+            sumV[1] = fadd(sumV[1], q.y);
+            sumV[2] = fadd(sumV[2], q.z);
             sumA = fadd(sumA, a);
         }
 
         float bestRGBError = FLT_MAX, bestAlphaError = FLT_MAX;
         float bRGB0[3] = { 0, 0, 0 }, bRGB1[3] = { 0, 0, 0 }, bA0 = 0.0f, bA1 = 0.0f;
-        uint32_t bRGBIdx[2] = { 0, 0 }, bAIdx[2] = { 0, 0 };
 
+#pragma unroll 1
         for (int tweak = 0; tweak < seeds; tweak++)
         {
             float e0[3], e1[3], a0, a1;
@@ -548,6 +644,7 @@ namespace cvttb200
                 a1 = rne(clamp_for_round(fadd(aMin, fmul(aoffs, af1)), 0.0f, 255.0f));
             }
 
+#pragma unroll 1
             for (int refine = 0; refine < R; refine++)
             {
                 const bool lastRound = (refine == R - 1);
@@ -592,11 +689,11 @@ namespace cvttb200
 
                 float acc[3] = { 0, 0, 0 }, accA = 0.0f, tv[3] = { 0, 0, 0 }, tt = 0.0f, ts = 0.0f, tvA = 0.0f, ttA = 0.0f, tsA = 0.0f;
                 float slowRGB = 0.0f, slowA = 0.0f;
-                uint32_t rgbIdx[2] = { 0, 0 }, aIdx[2] = { 0, 0 };
 
+#pragma unroll 2
                 for (int px = 0; px < 16; px++)
                 {
-                    const F4 p = pix[px * stride];
+                    const F4 p = gv[px * STRIDE];
                     const float pv[4] = { p.x, p.y, p.z, p.w };
 
                     float dist = fmul(fsub(pv[0], om[0]), axis[0]);
@@ -605,8 +702,8 @@ namespace cvttb200
                     float rgbIndex = rne(clamp_for_round(dist, 0.0f, icRGB.maxValue));
                     float alphaIndex = rne(clamp_for_round(fmul(fsub(pv[3], omA), axisA), 0.0f, icA.maxValue));
 
-                    float wf = xfma(rgbIndex, icRGB.wScale, kMagic) - kMagic;
-                    float wfA = xfma(alphaIndex, icA.wScale, kMagic) - kMagic;
+                    const float wf = xfma(rgbIndex, icRGB.wScale, kMagic) - kMagic;
+                    const float wfA = xfma(alphaIndex, icA.wScale, kMagic) - kMagic;
                     float d2[3], d2A;
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++)
@@ -627,45 +724,27 @@ namespace cvttb200
 
                     if (!FAST)
                     {
-                        // BC67.cpp:1822-1868
-                        float rgbError, alphaError;
-                        if (uniform)
-                        {
-                            rgbError = d2[0] + d2[1] + d2[2];
-                            alphaError = d2A;
-                        }
-                        else
-                        {
-                            rgbError = fadd(fadd(fmul(d2[0], wSqr[0]), fmul(d2[1], wSqr[1])), fmul(d2[2], wSqr[2]));
-                            alphaError = fmul(d2A, wSqr[3]);
-                        }
+                        // BC67.cpp:1822-1868 (wSqr is 1 under Flags::Uniform)
+                        float rgbError = fadd(fadd(fmul(d2[0], wSqr[0]), fmul(d2[1], wSqr[1])), fmul(d2[2], wSqr[2]));
+                        float alphaError = fmul(d2A, wSqr[3]);
                         const float altRGB[2] = { fmaxf(rgbIndex, 1.0f) - 1.0f, fminf(rgbIndex + 1.0f, icRGB.maxValue) };
                         const float altA[2] = { fmaxf(alphaIndex, 1.0f) - 1.0f, fminf(alphaIndex + 1.0f, icA.maxValue) };
 #pragma unroll
                         for (int ii = 0; ii < 2; ii++)
                         {
-                            float awf = xfma(altRGB[ii], icRGB.wScale, kMagic) - kMagic;
-                            float awfA = xfma(altA[ii], icA.wScale, kMagic) - kMagic;
+                            const float awf = xfma(altRGB[ii], icRGB.wScale, kMagic) - kMagic;
+                            const float awfA = xfma(altA[ii], icA.wScale, kMagic) - kMagic;
                             float s[3];
 #pragma unroll
                             for (int ch = 0; ch < 3; ch++)
                             {
-                                float df = (xfma(awf, d64[ch], bq[ch]) + kMagic) - pv[ch];
+                                const float df = (xfma(awf, d64[ch], bq[ch]) + kMagic) - pv[ch];
                                 s[ch] = df * df;
                             }
-                            float dfA = (xfma(awfA, d64A, bqA) + kMagic) - pv[3];
-                            float sA = dfA * dfA;
-                            float altRGBError, altAlphaError;
-                            if (uniform)
-                            {
-                                altRGBError = s[0] + s[1] + s[2];
-                                altAlphaError = sA;
-                            }
-                            else
-                            {
-                                altRGBError = fadd(fadd(fmul(s[0], wSqr[0]), fmul(s[1], wSqr[1])), fmul(s[2], wSqr[2]));
-                                altAlphaError = fmul(sA, wSqr[3]);
-                            }
+                            const float dfA = (xfma(awfA, d64A, bqA) + kMagic) - pv[3];
+                            const float sA = dfA * dfA;
+                            const float altRGBError = fadd(fadd(fmul(s[0], wSqr[0]), fmul(s[1], wSqr[1])), fmul(s[2], wSqr[2]));
+                            const float altAlphaError = fmul(sA, wSqr[3]);
                             const bool rgbBetter = altRGBError < rgbError, alphaBetter = altAlphaError < alphaError;
                             rgbError = sse_min(altRGBError, rgbError);
                             alphaError = sse_min(altAlphaError, alphaError);
@@ -680,10 +759,12 @@ namespace cvttb200
 
                     if (!lastRound)
                     {
+                        const F4 q = gw[px * STRIDE];
+                        const float qv[3] = { q.x, q.y, q.z };
                         const float t = fmul(rgbIndex, icRGB.rcpMaxIndex);
 #pragma unroll
                         for (int ch = 0; ch < 3; ch++)
-                            tv[ch] = fadd(tv[ch], fmul(t, fmul(fsub(pv[ch], kMagic), wr[ch])));
+                            tv[ch] = fadd(tv[ch], fmul(t, qv[ch]));
                         tt = fadd(tt, fmul(t, t));
                         ts = fadd(ts, t);
                         const float tA = fmul(alphaIndex, icA.rcpMaxIndex);
@@ -691,16 +772,12 @@ namespace cvttb200
                         ttA = fadd(ttA, fmul(tA, tA));
                         tsA = fadd(tsA, tA);
                     }
-
-                    const uint32_t nibRGB = as_uint(rgbIndex + kMagic) & 15u, nibA = as_uint(alphaIndex + kMagic) & 15u;
-                    rgbIdx[px >> 3] |= nibRGB << (4 * (px & 7));
-                    aIdx[px >> 3] |= nibA << (4 * (px & 7));
                 }
 
                 float errorRGB, errorA;
                 if (FAST)
                 {
-                    if (uniform)
+                    if (P.flags & kFlag_Uniform)
                     {
                         errorRGB = acc[0] + acc[1] + acc[2];
                         errorA = accA;
@@ -720,8 +797,6 @@ namespace cvttb200
                 if (errorRGB < bestRGBError)
                 {
                     bestRGBError = errorRGB;
-                    bRGBIdx[0] = rgbIdx[0];
-                    bRGBIdx[1] = rgbIdx[1];
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++)
                     {
@@ -732,8 +807,6 @@ namespace cvttb200
                 if (errorA < bestAlphaError)
                 {
                     bestAlphaError = errorA;
-                    bAIdx[0] = aIdx[0];
-                    bAIdx[1] = aIdx[1];
                     bA0 = qa0;
                     bA1 = qa1;
                 }
@@ -748,8 +821,8 @@ namespace cvttb200
 #pragma unroll
                         for (int ch = 0; ch < 3; ch++)
                         {
-                            float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sumV[ch]), wRcp)), adenom);
-                            float b = fmul(fsub(sumV[ch], fmul(a, ts)), wRcp);
+                            const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sumV[ch]), wRcp)), adenom);
+                            const float b = fmul(fsub(sumV[ch], fmul(a, ts)), wRcp);
                             float p1v = b, p2v = fadd(a, b);
                             if (adenomZero)
                                 p1v = p2v = fmul(sumV[ch], wRcp);
@@ -762,8 +835,8 @@ namespace cvttb200
                         const bool adenomZero = (adenom == 0.0f);
                         if (adenomZero)
                             adenom = 1.0f;
-                        float a = fdiv(fsub(tvA, fmul(fmul(tsA, sumA), wRcp)), adenom);
-                        float b = fmul(fsub(sumA, fmul(a, tsA)), wRcp);
+                        const float a = fdiv(fsub(tvA, fmul(fmul(tsA, sumA), wRcp)), adenom);
+                        const float b = fmul(fsub(sumA, fmul(a, tsA)), wRcp);
                         float p1v = b, p2v = fadd(a, b);
                         if (adenomZero)
                             p1v = p2v = fmul(sumA, wRcp);
@@ -786,12 +859,94 @@ namespace cvttb200
             const float c0[4] = { bRGB0[0], bRGB0[1], bRGB0[2], bA0 }, c1[4] = { bRGB1[0], bRGB1[1], bRGB1[2], bA1 };
             work.ep[0][0] = pack_ep_bytes(c0, 4);
             work.ep[0][1] = pack_ep_bytes(c1, 4);
-            for (int h = 0; h < 2; h++)
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // Indexes of the winning configuration.  Index selection (IndexSelector.h:124-131, and the +-1 probe of
+    // BC67.cpp:1364-1386 / 1822-1868 without FastIndexing) is a pure function of the quantised endpoints and the
+    // pixel, so the trial loops above do not carry indexes; they are re-derived here, once per block, with exactly
+    // the operations of the trial that produced the endpoints.
+    //   first/nch: the channels of `p` this selector covers (RGB: 0..2, RGBA: 0..3, the dual-plane scalar: 3)
+    struct BC7IndexSelector
+    {
+        float om[4], axis[4], d64[4], bq[4], wSq[4];
+        float maxV, wScale;
+        int first, nch;
+    };
+
+    CVTT_HD void bc7_selector_init(BC7IndexSelector &S, int first, int nch, int indexBits, uint32_t ep0, uint32_t ep1, const float *w, const float *wSq)
+    {
+        S.first = first;
+        S.nch = nch;
+        S.maxV = (float)((1 << indexBits) - 1);
+        S.wScale = 64.0f / (float)((1 << indexBits) - 1);
+        float dW[4], q0[4], q1[4];
+        for (int k = 0; k < nch; k++)
+        {
+            const int ch = first + k;
+            q0[k] = (float)((ep0 >> (8 * ch)) & 0xffu);
+            q1[k] = (float)((ep1 >> (8 * ch)) & 0xffu);
+            dW[k] = fmul(fsub(q1[k], q0[k]), w[ch]);
+            S.wSq[k] = wSq[ch];
+        }
+        float lenSq = fmul(dW[0], dW[0]);
+        for (int k = 1; k < nch; k++)
+            lenSq = fadd(lenSq, fmul(dW[k], dW[k]));
+        safe_denominator(lenSq);
+        const float mdl = fdiv(S.maxV, lenSq);
+        for (int k = 0; k < nch; k++)
+        {
+            const int ch = first + k;
+            // the scalar plane's selector is IndexSelector<1> with unit weight: axis = d * (maxV / d^2)
+            S.axis[k] = fmul(fmul(dW[k], w[ch]), mdl);
+            S.om[k] = q0[k] + kMagic;
+            S.d64[k] = (q1[k] - q0[k]) * 0.015625f;
+            S.bq[k] = q0[k] + 0.0078125f;
+        }
+    }
+
+    template<bool FAST>
+    CVTT_HD uint32_t bc7_select_index(const BC7IndexSelector &S, const F4 &p)
+    {
+        const float pAll[4] = { p.x, p.y, p.z, p.w };
+        float pv[4];
+        for (int k = 0; k < S.nch; k++)
+            pv[k] = pAll[S.first + k];
+        float dist = fmul(fsub(pv[0], S.om[0]), S.axis[0]);
+        for (int k = 1; k < S.nch; k++)
+            dist = fadd(dist, fmul(fsub(pv[k], S.om[k]), S.axis[k]));
+        float idxf = rne(clamp_for_round(dist, 0.0f, S.maxV));
+        if (!FAST)
+        {
+            float error = 0.0f;
             {
-                work.idx[h] = indexSelector ? bAIdx[h] : bRGBIdx[h];
-                work.idx2[h] = indexSelector ? bRGBIdx[h] : bAIdx[h];
+                const float wf = xfma(idxf, S.wScale, kMagic) - kMagic;
+                for (int k = 0; k < S.nch; k++)
+                {
+                    const float df = (xfma(wf, S.d64[k], S.bq[k]) + kMagic) - pv[k];
+                    const float sq = df * df;
+                    error = (k == 0) ? fmul(sq, S.wSq[0]) : fadd(error, fmul(sq, S.wSq[k]));
+                }
+            }
+            const float alt[2] = { fmaxf(idxf, 1.0f) - 1.0f, fminf(idxf + 1.0f, S.maxV) };
+            for (int ii = 0; ii < 2; ii++)
+            {
+                const float awf = xfma(alt[ii], S.wScale, kMagic) - kMagic;
+                float altError = 0.0f;
+                for (int k = 0; k < S.nch; k++)
+                {
+                    const float df = (xfma(awf, S.d64[k], S.bq[k]) + kMagic) - pv[k];
+                    const float sq = df * df;
+                    altError = (k == 0) ? fmul(sq, S.wSq[0]) : fadd(altError, fmul(sq, S.wSq[k]));
+                }
+                const bool better = altError < error;
+                error = sse_min(error, altError);
+                if (better)
+                    idxf = alt[ii];
             }
         }
+        return as_uint(idxf + kMagic) & 15u;
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -985,10 +1140,41 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // The whole search for one block.  `pix` holds the block's 16 pixels as (value + kMagic), element px at
-    // pix[px * stride]; it is modified in place during the dual-plane rotations and restored.
-    template<bool FAST>
-    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, F4 *pix, int stride, const BC7LaneFlags &lf, uint32_t out[4])
+    // Gathers the pixels of `mask` (ascending pixel order = the reference's iteration order) into gv/gw, optionally
+    // rotated, weighted with wv.  Returns the sums the trials share: the refiner's per-channel sum of v
+    // (EndpointRefiner.h:85-88) and the squared error of replacing alpha by 255 (BC67.cpp:1250-1264).
+    template<int STRIDE>
+    CVTT_HD void bc7_gather(const BC7Lane<STRIDE> &L, uint32_t mask, int rotation, const float *wv, float *sumV, float &accA)
+    {
+        sumV[0] = sumV[1] = sumV[2] = sumV[3] = 0.0f;
+        accA = 0.0f;
+        int i = 0;
+        for (uint32_t m = mask; m; m &= m - 1, i++)
+        {
+            const int px = ctz32(m);
+            F4 p = bc7_expand_pixel(L.raw[px * STRIDE]);
+            if (rotation)
+                bc7_rotate(p, rotation);
+            F4 q;
+            q.x = fmul(p.x - kMagic, wv[0]);
+            q.y = fmul(p.y - kMagic, wv[1]);
+            q.z = fmul(p.z - kMagic, wv[2]);
+            q.w = fmul(p.w - kMagic, wv[3]);
+            L.gv[i * STRIDE] = p;
+            L.gw[i * STRIDE] = q;
+            sumV[0] = fadd(sumV[0], q.x);
+            sumV[1] = fadd(sumV[1], q.y);
+            sumV[2] = fadd(sumV[2], q.z);
+            sumV[3] = fadd(sumV[3], q.w);
+            const float da = (255.0f + kMagic) - p.w;
+            accA = xfma(da, da, accA);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // The whole search for one block.
+    template<bool FAST, int STRIDE>
+    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, uint32_t out[4])
     {
         BC7Work work;
         work.error = FLT_MAX;
@@ -999,8 +1185,8 @@ namespace cvttb200
             work.ep[s][0] = work.ep[s][1] = 0;
         work.idx[0] = work.idx[1] = work.idx2[0] = work.idx2[1] = 0;
 
-        // per-(mode, shape) results, indexed by the slot numbers the host assigned
-        uint32_t res[kBC7MaxSlots][5];
+        // per-(mode, shape) results, indexed by the slot numbers the host assigned: error, endpoint 0, endpoint 1
+        uint32_t res[kBC7MaxSlots][3];
 
         const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;                   // BC67.cpp:1121
         const bool allowMode7 = lf.anyBlockHasAlpha || (P.mode7RGBPartitionEnabled != 0); // BC67.cpp:1078
@@ -1009,6 +1195,9 @@ namespace cvttb200
         const uint32_t *pc = P.cmds;
         for (;;)
         {
+            // Every warp of the CTA walks the same command stream; keeping them on the same command keeps the code they
+            // execute (one mode's trial loops, a few KB) resident in the SM's 32 KB instruction cache.
+            cta_sync();
             const uint32_t w0 = pc[0];
             const int op = w0 & 0xff;
             if (op == kCmdEnd)
@@ -1022,20 +1211,8 @@ namespace cvttb200
                 const uint32_t mask = w1 & 0xffffu;
                 const int n = (w1 >> 16) & 0xff;
 
-                // per-shape constants: sum of pre-weighted pixels (the refiner's v sums, EndpointRefiner.h:85-88)
-                // and the error of replacing alpha by 255 (BC67.cpp:1250-1264)
-                float sumV[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, accA = 0.0f;
-                for (uint32_t m = mask; m; m &= m - 1)
-                {
-                    const int px = ctz32(m);
-                    const F4 p = pix[px * stride];
-                    sumV[0] = fadd(sumV[0], fmul(p.x - kMagic, P.w[0]));
-                    sumV[1] = fadd(sumV[1], fmul(p.y - kMagic, P.w[1]));
-                    sumV[2] = fadd(sumV[2], fmul(p.z - kMagic, P.w[2]));
-                    sumV[3] = fadd(sumV[3], fmul(p.w - kMagic, P.w[3]));
-                    const float da = (255.0f + kMagic) - p.w;
-                    accA = xfma(da, da, accA);
-                }
+                float sumV[4], accA;
+                bc7_gather<STRIDE>(L, mask, 0, P.w, sumV, accA);
                 const float staticAlphaError = uniform ? accA : fmul(accA, P.wSq[3]);
 
                 // endpoint fits.  Shapes the plan does not list keep the all-zero "unfinished" endpoints the
@@ -1044,7 +1221,7 @@ namespace cvttb200
                 if (listedRGB && lf.warpAnyRGB)
                 {
                     float b3[3], o3[3];
-                    bc7_endpoint_selector<3>(pix, stride, mask, n, P.w, b3, o3);
+                    bc7_endpoint_selector<3, STRIDE>(L.gw, n, P.w, b3, o3);
                     if (lf.allowRGBModes)                                       // BC67.cpp:1085
                         for (int ch = 0; ch < 3; ch++)
                         {
@@ -1066,7 +1243,7 @@ namespace cvttb200
                     if (lf.warpAnyPCA4)
                     {
                         float b4[4], o4[4];
-                        bc7_endpoint_selector<4>(pix, stride, mask, n, P.w, b4, o4);
+                        bc7_endpoint_selector<4, STRIDE>(L.gw, n, P.w, b4, o4);
                         if (usePCA4)
                             for (int ch = 0; ch < 4; ch++)
                             {
@@ -1085,19 +1262,25 @@ namespace cvttb200
                     {
                         if (!lf.warpAnyRGB)
                             continue;
-                        bc7_shape_trials<3, FAST>(P, P.mc[mode], pix, stride, mask, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
+                        switch (mode)
+                        {
+                        case 0: bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
+                        case 1: bc7_shape_trials<1, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
+                        case 2: bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
+                        default: bc7_shape_trials<3, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
+                        }
                     }
+                    else if (mode == 6)
+                        bc7_shape_trials<6, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
                     else
                     {
-                        if (mode == 7 && !lf.warpAnyMode7)
+                        if (!lf.warpAnyMode7)
                             continue;
-                        bc7_shape_trials<4, FAST>(P, P.mc[mode], pix, stride, mask, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
+                        bc7_shape_trials<7, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
                     }
                     res[slot][0] = as_uint(best.err);
                     res[slot][1] = best.e0;
                     res[slot][2] = best.e1;
-                    res[slot][3] = best.idxLo;
-                    res[slot][4] = best.idxHi;
                 }
                 pc += 2 + nRuns;
             }
@@ -1131,16 +1314,11 @@ namespace cvttb200
                     work.key = key;
                     work.mode = mode;
                     work.sub = partition;
-                    uint32_t lo = 0, hi = 0;
                     for (int s = 0; s < numSubsets; s++)
                     {
                         work.ep[s][0] = res[slots[s]][1];
                         work.ep[s][1] = res[slots[s]][2];
-                        lo |= res[slots[s]][3];
-                        hi |= res[slots[s]][4];
                     }
-                    work.idx[0] = lo;
-                    work.idx[1] = hi;
                 }
             }
             else // kCmdDual
@@ -1154,37 +1332,86 @@ namespace cvttb200
                 if (rotation)
                 {
                     const int c = rotation - 1;
-                    for (int px = 0; px < 16; px++)
-                    {
-                        F4 p = pix[px * stride];
-                        float t = p.w;
-                        if (c == 0) { p.w = p.x; p.x = t; }
-                        else if (c == 1) { p.w = p.y; p.y = t; }
-                        else { p.w = p.z; p.z = t; }
-                        pix[px * stride] = p;
-                    }
                     float t;
                     t = wr[3]; wr[3] = wr[c]; wr[c] = t;
                     t = wSqr[3]; wSqr[3] = wSqr[c]; wSqr[c] = t;
                     t = rcpWr[3]; rcpWr[3] = rcpWr[c]; rcpWr[c] = t;
                 }
+                {
+                    float sumV[4], accA;
+                    bc7_gather<STRIDE>(L, 0xffffu, rotation, wr, sumV, accA);
+                }
+                bc7_dual_plane<FAST, STRIDE>(P, L.gv, L.gw, mode, rotation, indexSelector, seeds, wr, wSqr, rcpWr, work);
+            }
+        }
 
-                bc7_dual_plane<FAST>(P, pix, stride, mode, rotation, indexSelector, seeds, wr, wSqr, rcpWr, work);
-
+        // indexes of the winner
+        {
+            const int mode = work.mode;
+            uint32_t idx[2] = { 0, 0 }, idx2[2] = { 0, 0 };
+            if (mode == 4 || mode == 5)
+            {
+                const int rotation = work.sub & 3, indexSelector = (work.sub >> 2) & 1;
+                const int rgbPrec = (mode == 4 && indexSelector) ? 3 : 2;
+                const int alphaPrec = (mode == 4 && !indexSelector) ? 3 : 2;
+                float wr[4] = { P.w[0], P.w[1], P.w[2], P.w[3] }, wSqr[4] = { P.wSq[0], P.wSq[1], P.wSq[2], P.wSq[3] };
                 if (rotation)
                 {
                     const int c = rotation - 1;
-                    for (int px = 0; px < 16; px++)
+                    float t;
+                    t = wr[3]; wr[3] = wr[c]; wr[c] = t;
+                    t = wSqr[3]; wSqr[3] = wSqr[c]; wSqr[c] = t;
+                }
+                const float unit[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+                BC7IndexSelector sRGB, sA;
+                bc7_selector_init(sRGB, 0, 3, rgbPrec, work.ep[0][0], work.ep[0][1], wr, wSqr);
+                bc7_selector_init(sA, 3, 1, alphaPrec, work.ep[0][0], work.ep[0][1], unit, wSqr);
+                uint32_t rgbIdx[2] = { 0, 0 }, aIdx[2] = { 0, 0 };
+                for (int px = 0; px < 16; px++)
+                {
+                    F4 p = bc7_expand_pixel(L.raw[px * STRIDE]);
+                    bc7_rotate(p, rotation);
+                    rgbIdx[px >> 3] |= bc7_select_index<FAST>(sRGB, p) << (4 * (px & 7));
+                    aIdx[px >> 3] |= bc7_select_index<FAST>(sA, p) << (4 * (px & 7));
+                }
+                for (int h = 0; h < 2; h++)
+                {
+                    idx[h] = indexSelector ? aIdx[h] : rgbIdx[h];
+                    idx2[h] = indexSelector ? rgbIdx[h] : aIdx[h];
+                }
+            }
+            else
+            {
+                const int numSubsets = (mode == 0 || mode == 2) ? 3 : ((mode == 1 || mode == 3 || mode == 7) ? 2 : 1);
+                const int nch = (mode < 4) ? 3 : 4;
+                const int indexBits = (mode < 2) ? 3 : (mode == 6 ? 4 : 2);
+                const int partition = work.sub;
+                for (int s = 0; s < numSubsets; s++)
+                {
+                    uint32_t mask = 0xffffu;
+                    if (numSubsets == 2)
+                        mask = s ? T.partitionMask2[partition] : (uint32_t)(~T.partitionMask2[partition]) & 0xffffu;
+                    else if (numSubsets == 3)
                     {
-                        F4 p = pix[px * stride];
-                        float t = p.w;
-                        if (c == 0) { p.w = p.x; p.x = t; }
-                        else if (c == 1) { p.w = p.y; p.y = t; }
-                        else { p.w = p.z; p.z = t; }
-                        pix[px * stride] = p;
+                        mask = 0;
+                        for (int px = 0; px < 16; px++)
+                            if ((int)((T.partitionMap3[partition] >> (px * 2)) & 3) == s)
+                                mask |= 1u << px;
+                    }
+                    BC7IndexSelector S;
+                    bc7_selector_init(S, 0, nch, indexBits, work.ep[s][0], work.ep[s][1], P.w, P.wSq);
+                    for (uint32_t m = mask; m; m &= m - 1)
+                    {
+                        const int px = ctz32(m);
+                        const F4 p = bc7_expand_pixel(L.raw[px * STRIDE]);
+                        idx[px >> 3] |= bc7_select_index<FAST>(S, p) << (4 * (px & 7));
                     }
                 }
             }
+            work.idx[0] = idx[0];
+            work.idx[1] = idx[1];
+            work.idx2[0] = idx2[0];
+            work.idx2[1] = idx2[1];
         }
 
         bc7_pack_block(work, T, out);

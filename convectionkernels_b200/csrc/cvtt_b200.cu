@@ -28,27 +28,26 @@ static_assert(sizeof(cvttb200_bc7_fine_tuning) == 285 && sizeof(BC7FineTuningPOD
 
 namespace
 {
-    constexpr int kBC7Threads = 128;     // 4 warps = 16 reference groups per CTA
+    constexpr int kBC7Threads = 384;     // 12 warps = 48 reference groups per CTA, one CTA per SM
+    constexpr int kBC7CtasPerSM = 1;
+    // per thread: 16 packed pixels + 16 gathered biased pixels + 16 gathered pre-weighted pixels
+    constexpr size_t kBC7SmemBytes = (size_t)kBC7Threads * 16 * (sizeof(uint32_t) + 2 * sizeof(F4));
 
     __constant__ BC7PackTables c_bc7PackTables;
 
-    // One thread per block, warp = 4 reference groups; see cvtt_common.cuh / bc7_core.cuh.
-    //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (a warp reads 2 KB contiguous)
-    //  * pixels are expanded once to (value + 1.5*2^23) fp32 in shared memory, laid out [pixel][thread] so that the
-    //    warp's 128-bit loads of one pixel are conflict-free
-    //  * output: one 128-bit store per thread (512 B contiguous per warp)
-    template<bool FAST>
-    __global__ void __launch_bounds__(kBC7Threads, 4)
-    bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
+    // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
+    // group-wide votes of BC7Computer::TrySinglePlane (BC67.cpp:1069-1072), so that every warp of the encode kernel
+    // holds four groups that walk the same set of modes.  Pure scheduling: the encode kernel recomputes the votes.
+    //   class 0: opaque group (RGB modes, no 4-channel fits, mode 7 only if the plan asks for it on RGB)
+    //   class 1: some block has alpha and some block is (nearly) opaque: every mode runs
+    //   class 2: every block has alpha <= 250 somewhere: RGB modes 0-3 are off
+    // lists[c * nGroups + i] = i-th group of class c (order within a class is not deterministic and does not matter).
+    __global__ void __launch_bounds__(256)
+    bc7_classify_kernel(const uint4 *__restrict__ in, uint32_t nBlocks, uint32_t nGroups, uint32_t *__restrict__ counts, uint32_t *__restrict__ lists)
     {
-        __shared__ F4 sPix[16 * kBC7Threads];
-
-        const uint32_t tid = threadIdx.x;
-        const uint32_t block = blockIdx.x * kBC7Threads + tid;
+        const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
         const bool active = block < nBlocks;
-        F4 *pix = sPix + tid;
-
-        int minAlpha = 255;
+        uint32_t minAlpha = 255;
         if (active)
         {
             const uint4 *src = in + (size_t)block * 4;
@@ -56,32 +55,82 @@ namespace
             for (int q = 0; q < 4; q++)
             {
                 const uint4 v = __ldg(src + q);
-                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                minAlpha = min(minAlpha, min(min(v.x >> 24, v.y >> 24), min(v.z >> 24, v.w >> 24)));
+            }
+        }
+        const uint32_t segMask = 0xffu << (threadIdx.x & 24);
+        const bool anyAlpha = (__ballot_sync(0xffffffffu, active && minAlpha < 255) & segMask) != 0;
+        const bool allowRGB = (__ballot_sync(0xffffffffu, active && minAlpha > 250) & segMask) != 0;
+        if (active && (threadIdx.x & 7) == 0)
+        {
+            const int cls = !anyAlpha ? 0 : (allowRGB ? 1 : 2);
+            const uint32_t pos = atomicAdd(counts + cls, 1u);
+            lists[(size_t)cls * nGroups + pos] = block >> 3;
+        }
+    }
+
+    // One thread per block, warp = 4 reference groups of one class; see cvtt_common.cuh / bc7_core.cuh.
+    //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (512 B contiguous per group) and
+    //    keeps it packed in shared memory, laid out [pixel][thread] (conflict-free)
+    //  * per pixel subset the search gathers the subset's pixels once into two [index][thread] arrays of fp32x4 (biased
+    //    value, pre-weighted value); every trial then streams them with 128-bit conflict-free loads
+    //  * output: one 128-bit store per thread
+    template<bool FAST>
+    __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
+    bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists)
+    {
+        extern __shared__ __align__(16) unsigned char smem[];
+        F4 *sGv = reinterpret_cast<F4 *>(smem);
+        F4 *sGw = sGv + 16 * kBC7Threads;
+        uint32_t *sRaw = reinterpret_cast<uint32_t *>(sGw + 16 * kBC7Threads);
+
+        const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+        // warp -> (class, four groups of that class); the expensive classes go first so that the tail of the launch is
+        // filled by the cheap opaque warps
+        const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
+        const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
+        uint32_t warp = blockIdx.x * (kBC7Threads / 32) + (tid >> 5);
+        uint32_t cls, clsCount;
+        if (warp < w1) { cls = 1; clsCount = n1; }
+        else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
+        else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
+        else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
+        const uint32_t slot = warp * 4 + (lane >> 3);
+        const bool active = slot < clsCount;
+        const uint32_t block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
+
+        BC7Lane<kBC7Threads> L;
+        L.raw = sRaw + tid;
+        L.gv = sGv + tid;
+        L.gw = sGw + tid;
+
+        uint32_t minAlpha = 255;
+        if (active)
+        {
+            const uint4 *src = in + (size_t)block * 4;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                {
-                    F4 p;
-                    p.x = __uint_as_float(kMagicBits | (w[k] & 0xffu));
-                    p.y = __uint_as_float(kMagicBits | ((w[k] >> 8) & 0xffu));
-                    p.z = __uint_as_float(kMagicBits | ((w[k] >> 16) & 0xffu));
-                    p.w = __uint_as_float(kMagicBits | (w[k] >> 24));
-                    minAlpha = min(minAlpha, (int)(w[k] >> 24));
-                    pix[(q * 4 + k) * kBC7Threads] = p;
-                }
+            for (int q = 0; q < 4; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                minAlpha = min(minAlpha, min(min(v.x >> 24, v.y >> 24), min(v.z >> 24, v.w >> 24)));
+                sRaw[(q * 4 + 0) * kBC7Threads + tid] = v.x;
+                sRaw[(q * 4 + 1) * kBC7Threads + tid] = v.y;
+                sRaw[(q * 4 + 2) * kBC7Threads + tid] = v.z;
+                sRaw[(q * 4 + 3) * kBC7Threads + tid] = v.w;
             }
         }
         else
         {
-            F4 p;
-            p.x = p.y = p.z = kMagic;
-            p.w = kMagic + 255.0f;
 #pragma unroll
             for (int px = 0; px < 16; px++)
-                pix[px * kBC7Threads] = p;
+                sRaw[px * kBC7Threads + tid] = 0xff000000u;
         }
+        __syncwarp();
 
         // group votes (reference AnySet over the 8 lanes of one call, BC67.cpp:1069-1072) and warp-level skips
-        const uint32_t segMask = 0xffu << (tid & 24);
+        const uint32_t segMask = 0xffu << (lane & 24);
         const uint32_t hasAlphaBallot = __ballot_sync(0xffffffffu, active && minAlpha < 255);
         const uint32_t allowRGBBallot = __ballot_sync(0xffffffffu, active && minAlpha > 250);
         BC7LaneFlags lf;
@@ -96,7 +145,7 @@ namespace
         lf.warpAnyMode7 = __any_sync(0xffffffffu, active && mode7);
 
         uint32_t o[4];
-        bc7_encode_block<FAST>(P, c_bc7PackTables, pix, kBC7Threads, lf, o);
+        bc7_encode_block<FAST, kBC7Threads>(P, c_bc7PackTables, L, lf, o);
 
         if (active)
             out[block] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -181,6 +230,8 @@ namespace
         CVTT_CUDA(cudaGetDevice(&prev));
         CVTT_CUDA(cudaSetDevice(device));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc7PackTables, &bc7_pack_tables(), sizeof(BC7PackTables)));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaDeviceSynchronize());
@@ -260,12 +311,23 @@ namespace
             return rc;
         P.cmds = dCmds;
 
-        const unsigned grid = (unsigned)((nBlocks + kBC7Threads - 1) / kBC7Threads);
-        if (options.flags & kFlag_BC7_FastIndexing)
-            bc7_encode_kernel<true><<<grid, kBC7Threads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks);
-        else
-            bc7_encode_kernel<false><<<grid, kBC7Threads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks);
+        // stream-ordered scratch for the group classification: counts[4] then lists[3][nGroups]
+        const uint32_t nGroups = (uint32_t)(nBlocks / 8);
+        uint32_t *dScratch = nullptr;
+        CVTT_CUDA(cudaMallocAsync((void **)&dScratch, (4 + 3 * (size_t)nGroups) * sizeof(uint32_t), stream));
+        CVTT_CUDA(cudaMemsetAsync(dScratch, 0, 4 * sizeof(uint32_t), stream));
+        bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
         g_launches++;
+
+        // at most three partially filled warps (one per class)
+        const unsigned warps = nGroups / 4 + 3;
+        const unsigned grid = (warps + kBC7Threads / 32 - 1) / (kBC7Threads / 32);
+        if (options.flags & kFlag_BC7_FastIndexing)
+            bc7_encode_kernel<true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else
+            bc7_encode_kernel<false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        g_launches++;
+        CVTT_CUDA(cudaFreeAsync(dScratch, stream));
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
     }

@@ -60,20 +60,18 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
             lf[l].warpAnyPCA4 = warpFlagsAllTrue ? true : wPCA4;
             lf[l].warpAnyExpand = true;
             lf[l].warpAnyMode7 = warpFlagsAllTrue ? true : wM7;
-            F4 pix[16];
-            for (int px = 0; px < 16; px++)
-            {
-                const uint8_t *s = blocks + (warpBase + l) * 64 + px * 4;
-                pix[px].x = as_float(kMagicBits | s[0]);
-                pix[px].y = as_float(kMagicBits | s[1]);
-                pix[px].z = as_float(kMagicBits | s[2]);
-                pix[px].w = as_float(kMagicBits | s[3]);
-            }
+            uint32_t raw[16];
+            memcpy(raw, blocks + (warpBase + l) * 64, 64);
+            F4 gv[16], gw[16];
+            BC7Lane<1> L;
+            L.raw = raw;
+            L.gv = gv;
+            L.gw = gw;
             uint32_t o[4];
             if (fast)
-                bc7_encode_block<true>(P, T, pix, 1, lf[l], o);
+                bc7_encode_block<true, 1>(P, T, L, lf[l], o);
             else
-                bc7_encode_block<false>(P, T, pix, 1, lf[l], o);
+                bc7_encode_block<false, 1>(P, T, L, lf[l], o);
             memcpy(out + (warpBase + l) * 16, o, 16);
         }
     }
