@@ -127,6 +127,15 @@ def launch_count():
     return int(_lib().cvttb200_launch_count())
 
 
+def selftest(samples=1 << 28, seed=1):
+    """Runs the device self-test (two-lane division vs IEEE division); returns the number of mismatching quotients."""
+    bad = ctypes.c_uint64(0)
+    L = _lib()
+    L.cvttb200_selftest.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    _check(L.cvttb200_selftest(int(samples), int(seed), ctypes.byref(bad)))
+    return int(bad.value)
+
+
 def set_rcp_table(table):
     """table: 17 floats (rcp of 0..16) or None to restore this host's _mm_rcp_ps values."""
     if table is None:

@@ -291,24 +291,24 @@ namespace cvttb200
     template<> struct BC7ModeT<7> { enum { NCH = 4, BITS = 5, WITHP = 1, UNQ = 6, PMAX = 4, SHAREDP = 0, IB = 2 }; };
 
     // Quantises the integer-valued endpoint channel c to the mode's precision with parity bit p and expands it
-    // back to 8 bits; the result is returned biased (value + kMagic).  qAddP = qAdd[p], pM = p + kMagic.
+    // back to 8 bits; the result is returned biased (value + kMagic).  qAddP = qAdd[p], pM = p + kMagic.  Both lanes.
     template<int MODE>
-    CVTT_HD float bc7_quant_biased(float c, float qAddP, float p, float pM)
+    CVTT_HD f2 bc7_quant_biased(f2 c, f2 qAddP, f2 p, f2 pM)
     {
         typedef BC7ModeT<MODE> M;
         const float qMul = M::WITHP ? (float)((1 << (M::BITS + 1)) - 1) / 512.0f : (float)((1 << M::BITS) - 1) / 256.0f;
-        const float vb = xfma(c, qMul, qAddP) + kMagic;
+        const f2 vb = f2_add(f2_fma(c, qMul, qAddP), kMagic);
         if (M::UNQ)
         {
             const int s = M::UNQ ? 2 * M::UNQ - 8 : 0;
             const float uMul = (float)(1 << (8 - M::UNQ)), uScale = 1.0f / (float)(1 << s), uOff = -(float)((1 << s) - 1) / (float)(1 << (s + 1));
-            const float v = vb - kMagic;
-            const float v2 = M::WITHP ? xfma(v, 2.0f, p) : v;
-            const float flb = xfma(v2, uScale, uOff) + kMagic;
-            return xfma(v2, uMul, flb);
+            const f2 v = f2_sub(vb, kMagic);
+            const f2 v2 = M::WITHP ? f2_fma(v, 2.0f, p) : v;
+            const f2 flb = f2_add(f2_fma(v2, uScale, uOff), kMagic);
+            return f2_fma(v2, uMul, flb);
         }
         else if (M::WITHP)
-            return xfma(vb - kMagic, 2.0f, pM);
+            return f2_fma(f2_sub(vb, kMagic), 2.0f, pM);
         else
             return vb;
     }
@@ -326,18 +326,19 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // One trial of the inner search: index selection, reconstruction error and (REFINE) the refiner's sums over the
-    // n gathered pixels (BC67.cpp:1355-1392).
+    // One pair of trials of the inner search (one per fp32 lane): index selection, reconstruction error and
+    // (REFINE) the refiner's sums over the n gathered pixels (BC67.cpp:1355-1392).
+    //   nom = -(q0 + kMagic), nd64 = -(q1 - q0) / 64, nbq = -(q0 + 1/128): negated so that the loop only adds
     template<int NCH, int IB, bool FAST, bool REFINE, int STRIDE>
-    CVTT_HD float bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const float *om, const float *axis, const float *d64,
-        const float *bq, float *tv, float &tt, float &ts)
+    CVTT_HD f2 bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const f2 *nom, const f2 *axis, const f2 *nd64,
+        const f2 *nbq, f2 *tv, f2 &tt, f2 &ts)
     {
         const float maxV = (float)((1 << IB) - 1), wScale = 64.0f / (float)((1 << IB) - 1), rcpMaxIndex = 1.0f / (float)((1 << IB) - 1);
-        float acc[NCH];
+        f2 acc[NCH];
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
-            acc[ch] = 0.0f;
-        float slowErr = 0.0f;
+            acc[ch] = f2_splat(0.0f);
+        f2 slowErr = f2_splat(0.0f);
 
 #pragma unroll 2
         for (int i = 0; i < n; i++)
@@ -346,51 +347,56 @@ namespace cvttb200
             const float pv[4] = { p.x, p.y, p.z, p.w };
 
             // SelectIndexLDR (IndexSelector.h:124-131)
-            float dist = fmul(fsub(pv[0], om[0]), axis[0]);
+            f2 dist = f2_mul(f2_add(nom[0], pv[0]), axis[0]);
 #pragma unroll
             for (int ch = 1; ch < NCH; ch++)
-                dist = fadd(dist, fmul(fsub(pv[ch], om[ch]), axis[ch]));
-            float idxf = rne(clamp_for_round(dist, 0.0f, maxV));
+                dist = f2_add(dist, f2_mul(f2_add(nom[ch], pv[ch]), axis[ch]));
+            f2 idxf = f2_rne(f2_clamp_for_round(dist, 0.0f, maxV));
 
-            // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43)
-            const float wf = xfma(idxf, wScale, kMagic) - kMagic;
-            float d2[NCH];
+            // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43); df is the negated difference
+            const f2 wf = f2_sub(f2_fma(idxf, wScale, kMagic), kMagic);
+            f2 d2[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
-                const float df = (xfma(wf, d64[ch], bq[ch]) + kMagic) - pv[ch];
+                const f2 df = f2_add(f2_sub(f2_fma(wf, nd64[ch], nbq[ch]), kMagic), pv[ch]);
                 if (FAST)
-                    acc[ch] = xfma(df, df, acc[ch]);                // exact (< 2^24)
+                    acc[ch] = f2_fma(df, df, acc[ch]);              // exact (< 2^24)
                 else
-                    d2[ch] = df * df;                               // exact (< 2^16)
+                    d2[ch] = f2_mul(df, df);                        // exact (< 2^16)
             }
 
             if (!FAST)
             {
                 // BC67.cpp:1364-1386: probe index-1 and index+1 in weighted float error (wSq is 1 under Flags::Uniform)
-                float error = fmul(d2[0], P.wSq[0]);
+                f2 error = f2_mul(d2[0], P.wSq[0]);
 #pragma unroll
                 for (int ch = 1; ch < NCH; ch++)
-                    error = fadd(error, fmul(d2[ch], P.wSq[ch]));
-                const float alt[2] = { fmaxf(idxf, 1.0f) - 1.0f, fminf(idxf + 1.0f, maxV) };
+                    error = f2_add(error, f2_mul(d2[ch], P.wSq[ch]));
+                f2 alt[2];
+                alt[0] = f2_sub(f2_make(fmaxf(idxf.x, 1.0f), fmaxf(idxf.y, 1.0f)), 1.0f);
+                alt[1] = f2_add(idxf, 1.0f);
+                alt[1] = f2_make(fminf(alt[1].x, maxV), fminf(alt[1].y, maxV));
 #pragma unroll
                 for (int ii = 0; ii < 2; ii++)
                 {
-                    const float awf = xfma(alt[ii], wScale, kMagic) - kMagic;
-                    float altError = 0.0f;
+                    const f2 awf = f2_sub(f2_fma(alt[ii], wScale, kMagic), kMagic);
+                    f2 altError = f2_splat(0.0f);
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
                     {
-                        const float df = (xfma(awf, d64[ch], bq[ch]) + kMagic) - pv[ch];
-                        const float sq = df * df;
-                        altError = (ch == 0) ? fmul(sq, P.wSq[0]) : fadd(altError, fmul(sq, P.wSq[ch]));
+                        const f2 df = f2_add(f2_sub(f2_fma(awf, nd64[ch], nbq[ch]), kMagic), pv[ch]);
+                        const f2 sq = f2_mul(df, df);
+                        altError = (ch == 0) ? f2_mul(sq, P.wSq[0]) : f2_add(altError, f2_mul(sq, P.wSq[ch]));
                     }
-                    const bool better = altError < error;
-                    error = sse_min(error, altError);
-                    if (better)
-                        idxf = alt[ii];
+                    const bool betterX = altError.x < error.x, betterY = altError.y < error.y;
+                    error = f2_make(sse_min(error.x, altError.x), sse_min(error.y, altError.y));
+                    if (betterX)
+                        idxf.x = alt[ii].x;
+                    if (betterY)
+                        idxf.y = alt[ii].y;
                 }
-                slowErr = fadd(slowErr, error);
+                slowErr = f2_add(slowErr, error);
             }
 
             // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92)
@@ -398,32 +404,32 @@ namespace cvttb200
             {
                 const F4 q = gw[i * STRIDE];
                 const float qv[4] = { q.x, q.y, q.z, q.w };
-                const float t = fmul(idxf, rcpMaxIndex);
+                const f2 t = f2_mul(idxf, rcpMaxIndex);
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++)
-                    tv[ch] = fadd(tv[ch], fmul(t, qv[ch]));
-                tt = fadd(tt, fmul(t, t));
-                ts = fadd(ts, t);
+                    tv[ch] = f2_add(tv[ch], f2_mul(t, qv[ch]));
+                tt = f2_add(tt, f2_mul(t, t));
+                ts = f2_add(ts, t);
             }
         }
 
         // AggregatedError::Finalize (AggregatedError.h:25-46)
         if (!FAST)
             return slowErr;
-        float shapeError;
+        f2 shapeError;
         if (P.flags & kFlag_Uniform)
         {
             shapeError = acc[0];
 #pragma unroll
             for (int ch = 1; ch < NCH; ch++)
-                shapeError = shapeError + acc[ch];
+                shapeError = f2_add(shapeError, acc[ch]);
         }
         else
         {
-            shapeError = fmul(acc[0], P.wSq[0]);
+            shapeError = f2_mul(acc[0], P.wSq[0]);
 #pragma unroll
             for (int ch = 1; ch < NCH; ch++)
-                shapeError = fadd(shapeError, fmul(acc[ch], P.wSq[ch]));
+                shapeError = f2_add(shapeError, f2_mul(acc[ch], P.wSq[ch]));
         }
         return shapeError;
     }
@@ -432,11 +438,151 @@ namespace cvttb200
     // The inner search of TrySinglePlane for one (mode, shape): tweaks x parity bits x refine rounds
     // (BC67.cpp:1298-1432).  Result: best error and endpoints of the shape; the indexes of the overall winner are
     // re-derived from its endpoints at the end (bc7_derive_indices), they are a pure function of them.
+    //
+    // Two trial chains run side by side in the two fp32 lanes: the two values of the first parity bit (modes with
+    // parity bits) or two tweaks (mode 2).  Each lane keeps its own best; the reference's "first strictly better in
+    // (pIter, tweak, refine) order" is the lexicographic minimum of (error, sequence number) over both lanes.
     struct BC7ShapeBest
     {
         float err;
         uint32_t e0, e1;      // packed endpoint bytes
     };
+
+    template<int NCH>
+    struct BC7PairBest
+    {
+        f2 err;
+        int seqX, seqY;
+        f2 e0[NCH], e1[NCH];  // biased
+    };
+
+    // refine rounds of one pair of trial chains starting from the tweaked endpoints u0/u1
+    template<int MODE, bool FAST, int STRIDE>
+    CVTT_HD void bc7_trial_pair(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const float *sumV, float staticAlphaError,
+        const f2 *u0, const f2 *u1, int p0x, int p0y, int p1x, int p1y, int seqX, int seqY, BC7PairBest<BC7ModeT<MODE>::NCH> &best)
+    {
+        typedef BC7ModeT<MODE> M;
+        enum { NCH = M::NCH };
+        const float maxV = (float)((1 << M::IB) - 1);
+        const int R = P.refineRounds;
+        const float wN = (float)n, wRcp = P.rcpN[n];
+
+        const f2 qA0 = f2_make(bc7_quant_add<MODE>(p0x), bc7_quant_add<MODE>(p0y)), qA1 = f2_make(bc7_quant_add<MODE>(p1x), bc7_quant_add<MODE>(p1y));
+        const f2 pf0 = f2_make((float)p0x, (float)p0y), pf1 = f2_make((float)p1x, (float)p1y);
+        const f2 pM0 = f2_add(pf0, kMagic), pM1 = f2_add(pf1, kMagic);
+
+        f2 e0[NCH], e1[NCH];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch++)
+        {
+            e0[ch] = u0[ch];
+            e1[ch] = u1[ch];
+        }
+
+#pragma unroll 1
+        for (int refine = 0; refine < R; refine++)
+        {
+            const bool lastRound = (refine == R - 1);
+
+            // CompressEndpointsN (BC67.cpp:862-938); q0b/q1b are biased
+            f2 q0b[NCH], q1b[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+            {
+                q0b[ch] = bc7_quant_biased<MODE>(e0[ch], qA0, pf0, pM0);
+                q1b[ch] = bc7_quant_biased<MODE>(e1[ch], qA1, pf1, pM1);
+            }
+
+            // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
+            // the fourth channel contributes exactly +0 to every sum below and is left out.
+            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH], nbq[NCH];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+            {
+                dq[ch] = f2_sub(q1b[ch], q0b[ch]);                      // exact
+                dW[ch] = f2_mul(dq[ch], P.w[ch]);
+            }
+            f2 lenSq = f2_mul(dW[0], dW[0]);
+#pragma unroll
+            for (int ch = 1; ch < NCH; ch++)
+                lenSq = f2_add(lenSq, f2_mul(dW[ch], dW[ch]));
+            safe_denominator(lenSq.x);
+            safe_denominator(lenSq.y);
+            const f2 mdl = f2_div(f2_splat(maxV), lenSq);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+            {
+                axis[ch] = f2_mul(f2_mul(dW[ch], P.w[ch]), mdl);
+                nom[ch] = f2_neg(q0b[ch]);
+                nd64[ch] = f2_mul(dq[ch], -0.015625f);                  // exact
+                nbq[ch] = f2_sub(f2_sub(kMagic, q0b[ch]), 0.0078125f);  // -(q0 + 1/128), both steps exact
+            }
+
+            f2 tv[NCH], tt = f2_splat(0.0f), ts = f2_splat(0.0f);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+                tv[ch] = f2_splat(0.0f);
+
+            f2 shapeError;
+            if (lastRound)
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, nbq, tv, tt, ts);
+            else
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, nbq, tv, tt, ts);
+            if (NCH == 3)
+                shapeError = f2_add(shapeError, staticAlphaError);
+
+            {
+                const int sx = seqX + refine, sy = seqY + refine;
+                if (shapeError.x < best.err.x || (shapeError.x == best.err.x && sx < best.seqX))
+                {
+                    best.err.x = shapeError.x;
+                    best.seqX = sx;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++)
+                    {
+                        best.e0[ch].x = q0b[ch].x;
+                        best.e1[ch].x = q1b[ch].x;
+                    }
+                }
+                if (shapeError.y < best.err.y || (shapeError.y == best.err.y && sy < best.seqY))
+                {
+                    best.err.y = shapeError.y;
+                    best.seqY = sy;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++)
+                    {
+                        best.e0[ch].y = q0b[ch].y;
+                        best.e1[ch].y = q1b[ch].y;
+                    }
+                }
+            }
+
+            // EndpointRefiner::GetRefinedEndpointsLDR (EndpointRefiner.h:99-152)
+            if (!lastRound)
+            {
+                f2 adenom = f2_mul(f2_sub(f2_mul(tt, wN), f2_mul(ts, ts)), wRcp);
+                const bool zeroX = (adenom.x == 0.0f), zeroY = (adenom.y == 0.0f);
+                if (zeroX)
+                    adenom.x = 1.0f;
+                if (zeroY)
+                    adenom.y = 1.0f;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                {
+                    const f2 a = f2_div(f2_sub(tv[ch], f2_mul(f2_mul(ts, sumV[ch]), wRcp)), adenom);
+                    const f2 b = f2_mul(f2_sub(sumV[ch], f2_mul(a, ts)), wRcp);
+                    f2 p1v = b, p2v = f2_add(a, b);
+                    const float flat = fmul(sumV[ch], wRcp);
+                    if (zeroX)
+                        p1v.x = p2v.x = flat;
+                    if (zeroY)
+                        p1v.y = p2v.y = flat;
+                    e0[ch] = f2_rne(f2_clamp_for_round(f2_mul(p1v, P.rcpW[ch]), 0.0f, 255.0f));
+                    e1[ch] = f2_rne(f2_clamp_for_round(f2_mul(p2v, P.rcpW[ch]), 0.0f, 255.0f));
+                }
+            }
+        }
+    }
 
     template<int MODE, bool FAST, int STRIDE>
     CVTT_HD void bc7_shape_trials(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
@@ -445,139 +591,67 @@ namespace cvttb200
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
         const IndexConst &ic = P.ic[M::IB - 2];
-        const float maxV = (float)((1 << M::IB) - 1);
-        const int R = P.refineRounds;
-        const float wN = (float)n, wRcp = P.rcpN[n];
 
-        float bestErr = FLT_MAX;
-        int bestSeq = 0x7fffffff;
-        float bE0[NCH], bE1[NCH];
+        BC7PairBest<NCH> best;
+        best.err = f2_splat(FLT_MAX);
+        best.seqX = best.seqY = 0x7fffffff;
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
-            bE0[ch] = bE1[ch] = kMagic;
+            best.e0[ch] = best.e1[ch] = f2_splat(kMagic);
 
-#pragma unroll 1
-        for (int tweak = 0; tweak < seeds; tweak++)
+        // sequence number of a trial: reference order is pIter, tweak, refine
+        if (M::PMAX >= 2)
         {
-            // UnfinishedEndpoints::FinishLDR (UnfinishedEndpoints.h:75-91)
-            const float tf0 = ic.tweak[tweak][0], tf1 = ic.tweak[tweak][1];
-            float u0[NCH], u1[NCH];
-#pragma unroll
-            for (int ch = 0; ch < NCH; ch++)
-            {
-                u0[ch] = rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf0)), 0.0f, 255.0f));
-                u1[ch] = rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf1)), 0.0f, 255.0f));
-            }
-
 #pragma unroll 1
-            for (int pIter = 0; pIter < M::PMAX; pIter++)
+            for (int tweak = 0; tweak < seeds; tweak++)
             {
-                const int p0 = pIter & 1;
-                const int p1 = M::SHAREDP ? p0 : ((pIter >> 1) & 1);
-                const float qA0 = bc7_quant_add<MODE>(p0), qA1 = bc7_quant_add<MODE>(p1);
-                const float pf0 = (float)p0, pf1 = (float)p1, pM0 = kMagic + pf0, pM1 = kMagic + pf1;
-
-                float e0[NCH], e1[NCH];
+                // UnfinishedEndpoints::FinishLDR (UnfinishedEndpoints.h:75-91), shared by both lanes
+                const float tf0 = ic.tweak[tweak][0], tf1 = ic.tweak[tweak][1];
+                f2 u0[NCH], u1[NCH];
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++)
                 {
-                    e0[ch] = u0[ch];
-                    e1[ch] = u1[ch];
+                    u0[ch] = f2_splat(rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf0)), 0.0f, 255.0f)));
+                    u1[ch] = f2_splat(rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf1)), 0.0f, 255.0f)));
                 }
-
 #pragma unroll 1
-                for (int refine = 0; refine < R; refine++)
+                for (int pp = 0; pp < M::PMAX / 2; pp++)
                 {
-                    const int seq = ((pIter * 4 + tweak) << 16) + refine;   // reference order: pIter, tweak, refine
-                    const bool lastRound = (refine == R - 1);
-
-                    // CompressEndpointsN (BC67.cpp:862-938); q0b/q1b are biased
-                    float q0b[NCH], q1b[NCH];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                    {
-                        q0b[ch] = bc7_quant_biased<MODE>(e0[ch], qA0, pf0, pM0);
-                        q1b[ch] = bc7_quant_biased<MODE>(e1[ch], qA1, pf1, pM1);
-                    }
-
-                    // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
-                    // the fourth channel contributes exactly +0 to every sum below and is left out.
-                    float dq[NCH], dW[NCH], axis[NCH], d64[NCH], bq[NCH];
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                    {
-                        dq[ch] = q1b[ch] - q0b[ch];                             // exact
-                        dW[ch] = fmul(dq[ch], P.w[ch]);
-                    }
-                    float lenSq = fmul(dW[0], dW[0]);
-#pragma unroll
-                    for (int ch = 1; ch < NCH; ch++)
-                        lenSq = fadd(lenSq, fmul(dW[ch], dW[ch]));
-                    safe_denominator(lenSq);
-                    const float mdl = fdiv(maxV, lenSq);
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                    {
-                        axis[ch] = fmul(fmul(dW[ch], P.w[ch]), mdl);
-                        d64[ch] = dq[ch] * 0.015625f;                           // exact
-                        bq[ch] = (q0b[ch] - kMagic) + 0.0078125f;               // exact
-                    }
-
-                    float tv[NCH], tt = 0.0f, ts = 0.0f;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                        tv[ch] = 0.0f;
-
-                    float shapeError;
-                    if (lastRound)
-                        shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, q0b, axis, d64, bq, tv, tt, ts);
-                    else
-                        shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, q0b, axis, d64, bq, tv, tt, ts);
-                    if (NCH == 3)
-                        shapeError = fadd(shapeError, staticAlphaError);
-
-                    if (shapeError < bestErr || (shapeError == bestErr && seq < bestSeq))
-                    {
-                        bestErr = shapeError;
-                        bestSeq = seq;
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ch++)
-                        {
-                            bE0[ch] = q0b[ch];
-                            bE1[ch] = q1b[ch];
-                        }
-                    }
-
-                    // EndpointRefiner::GetRefinedEndpointsLDR (EndpointRefiner.h:99-152)
-                    if (!lastRound)
-                    {
-                        float adenom = fmul(fsub(fmul(tt, wN), fmul(ts, ts)), wRcp);
-                        const bool adenomZero = (adenom == 0.0f);
-                        if (adenomZero)
-                            adenom = 1.0f;
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ch++)
-                        {
-                            const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sumV[ch]), wRcp)), adenom);
-                            const float b = fmul(fsub(sumV[ch], fmul(a, ts)), wRcp);
-                            float p1v = b, p2v = fadd(a, b);
-                            if (adenomZero)
-                                p1v = p2v = fmul(sumV[ch], wRcp);
-                            e0[ch] = rne(clamp_for_round(fmul(p1v, P.rcpW[ch]), 0.0f, 255.0f));
-                            e1[ch] = rne(clamp_for_round(fmul(p2v, P.rcpW[ch]), 0.0f, 255.0f));
-                        }
-                    }
+                    // lanes: pIter = 2 pp and 2 pp + 1, i.e. first parity bit 0 and 1
+                    const int p1 = M::SHAREDP ? 0 : pp;
+                    const int seqX = ((pp * 2) * 4 + tweak) << 16, seqY = ((pp * 2 + 1) * 4 + tweak) << 16;
+                    bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 1, M::SHAREDP ? 0 : p1, M::SHAREDP ? 1 : p1, seqX, seqY, best);
                 }
             }
         }
+        else
+        {
+#pragma unroll 1
+            for (int tweak = 0; tweak < seeds; tweak += 2)
+            {
+                // lanes: tweak and tweak + 1; an odd tail repeats the last tweak with a sequence number that loses every tie
+                const bool pairFull = tweak + 1 < seeds;
+                const int tweakY = pairFull ? tweak + 1 : tweak;
+                const f2 tf0 = f2_make(ic.tweak[tweak][0], ic.tweak[tweakY][0]), tf1 = f2_make(ic.tweak[tweak][1], ic.tweak[tweakY][1]);
+                f2 u0[NCH], u1[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                {
+                    u0[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf0, offs[ch]), base[ch]), 0.0f, 255.0f));
+                    u1[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf1, offs[ch]), base[ch]), 0.0f, 255.0f));
+                }
+                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 0, 0, 0, tweak << 16, pairFull ? (tweakY << 16) : 0x7ff00000, best);
+            }
+        }
 
-        out.err = bestErr;
+        const bool takeY = best.err.y < best.err.x || (best.err.y == best.err.x && best.seqY < best.seqX);
+        out.err = takeY ? best.err.y : best.err.x;
         uint32_t r0 = 0, r1 = 0;
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
         {
-            r0 |= (as_uint(bE0[ch]) & 0xffu) << (8 * ch);
-            r1 |= (as_uint(bE1[ch]) & 0xffu) << (8 * ch);
+            r0 |= (as_uint(takeY ? best.e0[ch].y : best.e0[ch].x) & 0xffu) << (8 * ch);
+            r1 |= (as_uint(takeY ? best.e1[ch].y : best.e1[ch].x) & 0xffu) << (8 * ch);
         }
         out.e0 = r0;
         out.e1 = r1;

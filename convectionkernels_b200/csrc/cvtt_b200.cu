@@ -69,6 +69,45 @@ namespace
         }
     }
 
+    // cvttb200_selftest: f2_div against the compiler's IEEE division
+    __device__ __forceinline__ uint32_t selftest_hash(uint64_t x)
+    {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+        return (uint32_t)x;
+    }
+
+    __device__ __forceinline__ float selftest_operand(uint32_t h)
+    {
+        // sign | exponent in [127 - 40, 127 + 40] | 23 random mantissa bits
+        const uint32_t e = 127u - 40u + (h >> 23) % 81u;
+        return __uint_as_float((h & 0x80000000u) | (e << 23) | (h & 0x007fffffu));
+    }
+
+    __global__ void selftest_div_kernel(uint64_t samples, uint64_t seed, unsigned long long *mismatches)
+    {
+        unsigned long long bad = 0;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < samples; i += (uint64_t)gridDim.x * blockDim.x)
+        {
+            const uint32_t h0 = selftest_hash(seed + 4 * i), h1 = selftest_hash(seed + 4 * i + 1), h2 = selftest_hash(seed + 4 * i + 2), h3 = selftest_hash(seed + 4 * i + 3);
+            f2 a = f2_make(selftest_operand(h0), selftest_operand(h1));
+            const f2 b = f2_make(selftest_operand(h2), selftest_operand(h3));
+            if ((h0 & 0xff) == 0)
+                a.x = 0.0f;
+            if ((h1 & 0xff) == 1)       // small integers over small integers, the shape of maxV / lenSq
+            {
+                a.y = (float)(1 + (h1 >> 8) % 15);
+            }
+            const f2 q = f2_div(a, b);
+            const float wx = __fdiv_rn(a.x, b.x), wy = __fdiv_rn(a.y, b.y);
+            if (__float_as_uint(q.x) != __float_as_uint(wx) && !(q.x == 0.0f && wx == 0.0f))
+                bad++;
+            if (__float_as_uint(q.y) != __float_as_uint(wy) && !(q.y == 0.0f && wy == 0.0f))
+                bad++;
+        }
+        if (bad)
+            atomicAdd(mismatches, bad);
+    }
+
     // One thread per block, warp = 4 reference groups of one class; see cvtt_common.cuh / bc7_core.cuh.
     //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (512 B contiguous per group) and
     //    keeps it packed in shared memory, laid out [pixel][thread] (conflict-free)
@@ -402,6 +441,35 @@ int cvttb200_get_rcp_table(float *rcp17)
 }
 
 const char *cvttb200_last_error(void) { return t_lastError.c_str(); }
+
+int cvttb200_selftest(uint64_t samples, uint64_t seed, uint64_t *mismatches)
+{
+    if (!mismatches)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int device = 0;
+    {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "cudaGetDevice");
+    }
+    DeviceContext *ctx = nullptr;
+    int rc = get_context(device, &ctx);
+    if (rc != CVTTB200_OK)
+        return rc;
+    unsigned long long *dBad = nullptr;
+    CVTT_CUDA(cudaMalloc((void **)&dBad, sizeof(unsigned long long)));
+    CVTT_CUDA(cudaMemset(dBad, 0, sizeof(unsigned long long)));
+    selftest_div_kernel<<<148 * 8, 256>>>(samples, seed, dBad);
+    g_launches++;
+    unsigned long long bad = 0;
+    cudaError_t e = cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost);
+    cudaFree(dBad);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "selftest_div_kernel");
+    *mismatches = bad;
+    return CVTTB200_OK;
+}
 
 uint64_t cvttb200_launch_count(void) { return g_launches.load(); }
 

@@ -137,6 +137,12 @@ const char *cvttb200_last_error(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t cvttb200_launch_count(void);
 
+/* Device self-test of the arithmetic building blocks the kernels rely on for bit-exactness: the two-lane fp32
+ * division used by the BC7 search is compared with the compiler's IEEE division on `samples` pseudo-random operand
+ * pairs (log-uniform magnitudes in 2^-40 .. 2^40, both signs, zero numerators).  *mismatches receives the number of
+ * quotients whose bits differ (a differing sign of a zero quotient is not counted).  Returns a cvttb200_status. */
+int cvttb200_selftest(uint64_t samples, uint64_t seed, uint64_t *mismatches);
+
 /* ---- configuration (pure host code) ---------------------------------------------------------------------- */
 
 void cvttb200_options_default(cvttb200_options *options);

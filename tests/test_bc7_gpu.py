@@ -148,3 +148,8 @@ def test_full_size_properties(oracle):
     idx = (groups[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
     want = oracle.encode_bc7(blocks[idx], _opt_bytes(o), _plan_bytes(p))
     assert (full[idx] == want).all(), first_mismatch(want, full[idx])
+
+
+def test_two_lane_division_is_ieee():
+    """f2_div (the packed reciprocal / Newton / remainder sequence of cvtt_common.cuh) against __fdiv_rn on 2^29 operand pairs"""
+    assert api.selftest(samples=1 << 28, seed=7) == 0

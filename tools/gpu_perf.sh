@@ -1,7 +1,7 @@
 #!/bin/bash
 # Quick perf iteration on the GPU box: golden parity + reference crop parity, bench (our arm), light ncu of the BC7 kernel.
 mkdir -p gpurun_out
-python -m pytest tests/test_bc7_gpu.py -x -q -m gpu -k "golden or reference_on_this_host or ragged" 2>&1 | tail -5 | tee gpurun_out/pytest_quick.log
+python -m pytest tests/test_bc7_gpu.py -x -q -m gpu -k "golden or reference_on_this_host or ragged or division or oracle" 2>&1 | tail -5 | tee gpurun_out/pytest_quick.log
 python bench.py --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_quick.json
 cat > /tmp/prof_small.py <<'PY'
 import sys; sys.path.insert(0, '.')
