@@ -1271,9 +1271,10 @@ namespace cvttb200
         {
             // Every warp of the CTA walks the same command stream; keeping them on the same command keeps the code they
             // execute (one mode's trial loops, a few KB) resident in the SM's 32 KB instruction cache.
-            cta_sync();
             const uint32_t w0 = pc[0];
             const int op = w0 & 0xff;
+            if (op != kCmdEval)          // EVAL is a handful of instructions; the stream is uniform, so every thread agrees
+                cta_sync();
             if (op == kCmdEnd)
                 break;
 

@@ -16,7 +16,12 @@ m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
 keep = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__inst_executed.avg.per_cycle_active", "sm__inst_executed.sum.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -49,6 +54,8 @@ summary = {
     "dram_bytes_per_launch_note": "dram__bytes_read.sum + dram__bytes_write.sum of the captured launch scaled to the 1 048 576-block bench launch",
     "issue_slot_frac": float(m["sm__inst_executed.avg.per_cycle_active"][0]) / 4.0,
     "issue_slot_frac_note": "sm__inst_executed.avg.per_cycle_active / 4 warp-instructions per SM cycle",
+    "fma_pipe_frac": float(m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0]) / 100.0 if "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active" in m else None,
+    "fma_pipe_frac_note": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active: share of cycles the FP32 FMA pipe is busy (packed FFMA2/FADD2 occupy it for two cycles)",
     "registers_per_thread": int(float(m["launch__registers_per_thread"][0])),
     "warp_instructions_per_block": float(m["smsp__inst_executed.sum"][0].replace(",", "")) / (blocks / 32.0) if "smsp__inst_executed.sum" in m else None,
 }
