@@ -219,3 +219,14 @@ def encode(fmt, pBlocks, options, encodingPlan=None, out=None):
 def EncodeBC7(pBlocks, options, encodingPlan, out=None):
     """cvtt::Kernels::EncodeBC7, reference ConvectionKernels.h:252 / ConvectionKernels_API.cpp:41-54"""
     return encode("BC7", pBlocks, options, encodingPlan, out)
+
+
+def EncodeBC6HU(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC6HU, reference ConvectionKernels.h:250 / ConvectionKernels_API.cpp:56-69.  pBlocks: PixelBlockF16
+    (int16 half bit patterns, [n][16][4], alpha ignored)."""
+    return encode("BC6HU", pBlocks, options, None, out)
+
+
+def EncodeBC6HS(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC6HS, reference ConvectionKernels.h:251 / ConvectionKernels_API.cpp:71-84"""
+    return encode("BC6HS", pBlocks, options, None, out)

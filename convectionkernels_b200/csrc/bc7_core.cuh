@@ -27,7 +27,10 @@
 
 namespace cvttb200
 {
+#ifndef CVTT_F4_DEFINED
+#define CVTT_F4_DEFINED
     struct alignas(16) F4 { float x, y, z, w; };
+#endif
 
     // Per-mode constants of the endpoint quantisers in exact-fp32 form.
     //   QuantizeP(bits, p): ((c << (bits+1)) - c + addend(p)) >> 9, then (v << 1) | p      BC67.cpp:835-851

@@ -16,6 +16,7 @@
 
 #include "../../include/cvtt_b200.h"
 #include "bc7_host.h"
+#include "bc6h_host.h"
 
 using namespace cvttb200;
 
@@ -191,6 +192,63 @@ namespace
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// BC6H
+
+namespace
+{
+    constexpr int kBC6HThreads = 128;
+    constexpr size_t kBC6HSmemBytes = (size_t)kBC6HThreads * 16 * 2 * sizeof(F4);
+
+    __constant__ BC6HTables c_bc6hTables;
+
+    // The reference's AnySet / AllSet over the 8 lanes of one call (ParallelMath.h:1260-1278): ballots restricted to
+    // the lane's 8-lane segment.  Every lane of the warp executes every vote (control flow around votes is uniform).
+    struct SegmentVote
+    {
+        uint32_t segMask;
+        __device__ __forceinline__ bool any(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) != 0; }
+        __device__ __forceinline__ bool all(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) == segMask; }
+        __device__ __forceinline__ bool warp_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
+    };
+
+    // One thread per block, warp = 4 reference groups.  Input: PixelBlockF16 = int16 [16][4] (128 B, alpha ignored), read
+    // with eight 128-bit loads per thread; converted once into two [pixel][thread] fp32x4 arrays in shared memory.
+    template<bool SIGNED, bool FAST>
+    __global__ void __launch_bounds__(kBC6HThreads, 3)
+    bc6h_encode_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
+    {
+        extern __shared__ __align__(16) unsigned char smem[];
+        F4 *sLin = reinterpret_cast<F4 *>(smem);
+        F4 *sPw = sLin + 16 * kBC6HThreads;
+
+        const uint32_t tid = threadIdx.x;
+        const uint32_t block = blockIdx.x * kBC6HThreads + tid;
+        const bool active = block < nBlocks;
+
+        BC6HLane<kBC6HThreads> L;
+        L.lin = sLin + tid;
+        L.pw = sPw + tid;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (active)
+                v = __ldg(in + (size_t)block * 8 + q);
+            bc6h_load_pixel<SIGNED, kBC6HThreads>(P, L, 2 * q, (int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu));
+            bc6h_load_pixel<SIGNED, kBC6HThreads>(P, L, 2 * q + 1, (int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu));
+        }
+        __syncwarp();
+
+        SegmentVote vote;
+        vote.segMask = 0xffu << (tid & 24);
+        uint32_t o[4];
+        bc6h_encode_block<SIGNED, FAST, kBC6HThreads>(P, c_bc6hTables, L, vote, o);
+        if (active)
+            out[block] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // =========================================================================================================
 // Host state
 
@@ -273,6 +331,11 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
         CVTT_CUDA(cudaDeviceSynchronize());
         CVTT_CUDA(cudaSetDevice(prev));
 
@@ -332,6 +395,31 @@ namespace
         *have = 0;
         CVTT_CUDA(cudaMalloc(buf, need));
         *have = need;
+        return CVTTB200_OK;
+    }
+
+    int launch_bc6h(const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, bool isSigned, cudaStream_t stream)
+    {
+        if (nBlocks > 0xffffff00u)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
+        BC6HParams P;
+        bc6h_fill_params(P, options, g_rcpN);
+        const unsigned grid = (unsigned)((nBlocks + kBC6HThreads - 1) / kBC6HThreads);
+        const bool fast = (options.flags & kFlag_BC6H_FastIndexing) != 0;
+        const uint4 *in = (const uint4 *)dIn;
+        uint4 *out = (uint4 *)dOut;
+        if (isSigned)
+        {
+            if (fast) bc6h_encode_kernel<true, true><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+            else bc6h_encode_kernel<true, false><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+        }
+        else
+        {
+            if (fast) bc6h_encode_kernel<false, true><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+            else bc6h_encode_kernel<false, false><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+        }
+        g_launches++;
+        CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
     }
 
@@ -534,9 +622,9 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
     const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
     if (!inBytes)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
-    if (format != CVTTB200_BC7)
+    if (format != CVTTB200_BC7 && format != CVTTB200_BC6HU && format != CVTTB200_BC6HS)
         return fail(CVTTB200_ERR_UNSUPPORTED, "format not implemented by this build (no CPU fallback exists)");
-    if (!plan)
+    if (format == CVTTB200_BC7 && !plan)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
     if (nBlocks == 0)
         return CVTTB200_OK;
@@ -576,9 +664,14 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
 
     OptionsPOD opt;
     memcpy(&opt, options, sizeof(opt));
-    BC7PlanPOD planPOD;
-    memcpy(&planPOD, plan, sizeof(planPOD));
-    rc = launch_bc7(*ctx, dIn, nBlocks, dOut, opt, planPOD, stream);
+    if (format == CVTTB200_BC7)
+    {
+        BC7PlanPOD planPOD;
+        memcpy(&planPOD, plan, sizeof(planPOD));
+        rc = launch_bc7(*ctx, dIn, nBlocks, dOut, opt, planPOD, stream);
+    }
+    else
+        rc = launch_bc6h(dIn, nBlocks, dOut, opt, format == CVTTB200_BC6HS, stream);
     if (rc != CVTTB200_OK)
         return rc;
 

@@ -126,3 +126,32 @@ def hdr_ramp_f16(h=4096, w=4096, seed=99, signed=False):
         img[neg, :3] *= -1.0
     img = np.clip(img, -65000.0, 65000.0).astype(np.float16)
     return img.view(np.int16)
+
+
+def random_blocks_f16(n, seed=0, signed=False):
+    """n PixelBlockF16 blocks (int16 half bit patterns, RGBA) covering flat, noisy, ramp, two-colour, wide-range and
+    (signed) negative content, so that BC6H single- and two-subset modes of every precision get chosen."""
+    rng = np.random.default_rng(seed)
+    b = np.zeros((n, 16, 4), np.float32)
+    for i in range(n):
+        kind = i % 6
+        base = rng.uniform(0, 4, 3) * rng.choice([0.01, 0.1, 1, 10, 100])
+        if kind == 0:
+            px = base[None, :] * np.ones((16, 1))
+        elif kind == 1:
+            px = base[None, :] * (1 + rng.uniform(-0.3, 0.3, (16, 3)))
+        elif kind == 2:
+            g = np.linspace(0, 1, 16)[:, None]
+            px = base[None, :] * (0.2 + g) + rng.uniform(0, 0.02, (16, 3))
+        elif kind == 3:
+            m = (rng.random(16) < 0.5)[:, None]
+            px = np.where(m, base[None, :], rng.uniform(0, 2, 3)[None, :]) * (1 + rng.uniform(-0.05, 0.05, (16, 3)))
+        elif kind == 4:
+            px = rng.uniform(0, 65000, (16, 3)) * rng.choice([1, 1e-3, 1e-6])
+        else:
+            px = rng.normal(0, 1, (16, 3)) * base[None, :]
+        if not signed and kind != 5:
+            px = np.abs(px)
+        b[i, :, :3] = px
+        b[i, :, 3] = 1
+    return np.ascontiguousarray(b.astype(np.float16).view(np.int16))

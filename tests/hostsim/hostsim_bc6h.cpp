@@ -1,0 +1,99 @@
+// TEST INFRASTRUCTURE ONLY.  CPU build of the BC6H per-thread device code (convectionkernels_b200/csrc/bc6h_core.cuh).
+// The eight lanes of a reference group run as eight host threads; the group votes of the kernel (ballots over an
+// 8-lane segment) become a spin barrier with an OR reduction.  Not part of the product library.
+#include <atomic>
+#include <thread>
+#include <vector>
+#include <xmmintrin.h>
+
+#include "../../convectionkernels_b200/csrc/bc6h_host.h"
+
+using namespace cvttb200;
+
+namespace
+{
+    struct GroupShared
+    {
+        std::atomic<int> count{0};
+        std::atomic<int> sense{0};
+        std::atomic<unsigned> bits[2];
+        GroupShared() { bits[0] = 0; bits[1] = 0; }
+    };
+
+    struct HostVote
+    {
+        GroupShared *g;
+        int localSense = 0;
+        int phase = 0;
+
+        bool any(bool x)
+        {
+            const int slot = phase & 1;
+            phase++;
+            localSense ^= 1;
+            if (x)
+                g->bits[slot].fetch_or(1u);
+            if (g->count.fetch_add(1) == 7)
+            {
+                g->bits[slot ^ 1].store(0u);
+                g->count.store(0);
+                g->sense.store(localSense);
+            }
+            else
+            {
+                int spins = 0;
+                while (g->sense.load() != localSense)
+                    if (++spins > 64)
+                        std::this_thread::yield();
+            }
+            return g->bits[slot].load() != 0;
+        }
+        bool all(bool x) { return !any(!x); }
+        bool warp_any(bool x) { return x; }      // the argument is uniform over the group
+    };
+
+    template<bool SIGNED, bool FAST>
+    void run_lane(int lane, GroupShared *shared, const BC6HParams *P, const int16_t *blocks, size_t nBlocks, uint8_t *out)
+    {
+        HostVote vote;
+        vote.g = shared;
+        const BC6HTables &T = bc6h_tables();
+        for (size_t base = 0; base < nBlocks; base += 8)
+        {
+            const int16_t *src = blocks + (base + lane) * 64;
+            F4 lin[16], pw[16];
+            BC6HLane<1> L;
+            L.lin = lin;
+            L.pw = pw;
+            for (int px = 0; px < 16; px++)
+                bc6h_load_pixel<SIGNED, 1>(*P, L, px, src[px * 4 + 0], src[px * 4 + 1], src[px * 4 + 2]);
+            uint32_t o[4];
+            bc6h_encode_block<SIGNED, FAST, 1>(*P, T, L, vote, o);
+            memcpy(out + (base + lane) * 16, o, 16);
+        }
+    }
+}
+
+extern "C" int hostsim_encode_bc6h(const int16_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, int isSigned, const float *rcpTable)
+{
+    if (nBlocks % 8)
+        return -1;
+    float rcpN[17];
+    for (int n = 0; n < 17; n++)
+        rcpN[n] = rcpTable ? rcpTable[n] : _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
+    BC6HParams P;
+    bc6h_fill_params(P, *options, rcpN);
+    const bool fast = (options->flags & kFlag_BC6H_FastIndexing) != 0;
+    GroupShared shared;
+    std::vector<std::thread> threads;
+    for (int lane = 0; lane < 8; lane++)
+    {
+        if (isSigned)
+            threads.emplace_back(fast ? run_lane<true, true> : run_lane<true, false>, lane, &shared, &P, blocks, nBlocks, out);
+        else
+            threads.emplace_back(fast ? run_lane<false, true> : run_lane<false, false>, lane, &shared, &P, blocks, nBlocks, out);
+    }
+    for (auto &t : threads)
+        t.join();
+    return 0;
+}

@@ -1,0 +1,37 @@
+"""CPU tests of the BC6H device logic: convectionkernels_b200/csrc/bc6h_core.cuh compiled for the CPU (tests/hostsim, test-only; the
+eight lanes of a reference group run as eight threads and the kernel's segment ballots become a barrier vote) against the golden
+vectors recorded from the unmodified reference."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, first_mismatch
+
+
+@pytest.fixture(scope="module")
+def hostsim_bc6h():
+    out = os.path.join(ROOT, "tests", "_build", "libcvtt_hostsim_bc6h.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    csrc = os.path.join(ROOT, "convectionkernels_b200", "csrc")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-pthread", "-w", "-I", csrc, "-o", out,
+                           os.path.join(ROOT, "tests", "hostsim", "hostsim_bc6h.cpp"), os.path.join(csrc, "bc6h_host.cpp")])
+    H = ctypes.CDLL(out)
+    H.hostsim_encode_bc6h.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    return H
+
+
+@pytest.mark.parametrize("name", golden_names("bc6h"))
+def test_bc6h_device_logic_on_cpu_matches_golden(hostsim_bc6h, name):
+    g = load_golden(name)
+    blocks = np.ascontiguousarray(g["blocks"])
+    n = blocks.shape[0]
+    out = np.zeros((n, 16), np.uint8)
+    opt = np.ascontiguousarray(g["options"])
+    rcp = np.ascontiguousarray(g["rcp"], dtype=np.float32)
+    signed = 1 if str(g["fmt"]) == "BC6HS" else 0
+    rc = hostsim_bc6h.hostsim_encode_bc6h(blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data)
+    assert rc == 0
+    assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)

@@ -15,7 +15,7 @@ os.makedirs(OUT, exist_ok=True)
 rcp = R.rcp_table()
 
 
-def options(flags=None, refine=None, weights=None):
+def options(flags=None, refine=None, weights=None, refine_bc6h=None, seeds=None):
     o = R.default_options().copy()
     if flags is not None:
         o[0:4] = np.frombuffer(struct.pack("<I", flags), np.uint8)
@@ -26,7 +26,12 @@ def options(flags=None, refine=None, weights=None):
     return o
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
 def save(name, fmt, blocks, opt, plan=None):
+    if not name.startswith(ONLY):
+        return
     out = R.encode(fmt, blocks, opt, plan)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), fmt=fmt, blocks=blocks, options=opt,
                         plan=plan if plan is not None else np.zeros(0, np.uint8), expected=out, rcp=rcp)
@@ -49,3 +54,14 @@ save("bc7_gradient_q100", "BC7", grad, options(), q100)
 save("bc7_mixed_q100", "BC7", mixed, options(), q100)
 # config 1 (plumbing, CPU only): EncodeBC1 on the 256x256 gradient
 save("bc1_gradient256", "BC1", synth.image_to_blocks(synth.gradient_rgba8(256, 256)), options())
+
+# config 3 content: BC6H (unsigned / signed, slow and fast indexing, fewer rounds, uniform weights)
+hu, hs = synth.random_blocks_f16(128, seed=31), synth.random_blocks_f16(128, seed=32, signed=True)
+ramp = synth.image_to_blocks(synth.hdr_ramp_f16(64, 128))[:128]
+save("bc6hu_random", "BC6HU", hu, options())
+save("bc6hs_random", "BC6HS", hs, options())
+save("bc6hu_random_fast", "BC6HU", hu, options(flags=0x148))
+save("bc6hs_random_fast_uniform", "BC6HS", hs, options(flags=0x348))
+save("bc6hu_random_rounds22", "BC6HU", hu, options(refine_bc6h=2, seeds=2))
+save("bc6hs_random_rounds13_weights", "BC6HS", hs, options(refine_bc6h=1, seeds=3, weights=(1.0, 0.5, 2.0, 1.0)))
+save("bc6hu_ramp", "BC6HU", ramp, options())
