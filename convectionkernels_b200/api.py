@@ -230,3 +230,32 @@ def EncodeBC6HU(pBlocks, options, out=None):
 def EncodeBC6HS(pBlocks, options, out=None):
     """cvtt::Kernels::EncodeBC6HS, reference ConvectionKernels.h:251 / ConvectionKernels_API.cpp:71-84"""
     return encode("BC6HS", pBlocks, options, None, out)
+
+
+def EncodeETC1(pBlocks, options, compressionData=None, out=None):
+    """cvtt::Kernels::EncodeETC1, reference ConvectionKernels.h:253 / ConvectionKernels_API.cpp:200-213.  The reference's
+    ETC1CompressionData is scratch memory; the library allocates its device equivalent per call (stream-ordered), so the
+    argument is accepted for signature compatibility and ignored."""
+    return encode("ETC1", pBlocks, options, None, out)
+
+
+def EncodeETC2(pBlocks, options, compressionData=None, out=None):
+    """cvtt::Kernels::EncodeETC2, reference ConvectionKernels.h:254 / ConvectionKernels_API.cpp:215-228"""
+    return encode("ETC2", pBlocks, options, None, out)
+
+
+def EncodeETC2RGBA(pBlocks, options, compressionData=None, out=None):
+    """cvtt::Kernels::EncodeETC2RGBA, reference ConvectionKernels.h:255 / ConvectionKernels_API.cpp:270-286: EAC alpha in bytes
+    0-7, ETC2 colour in bytes 8-15"""
+    return encode("ETC2_RGBA", pBlocks, options, None, out)
+
+
+def EncodeETC2Alpha(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeETC2Alpha, reference ConvectionKernels.h:258 / ConvectionKernels_API.cpp:245-255"""
+    return encode("ETC2_ALPHA", pBlocks, options, None, out)
+
+
+def EncodeETC2Alpha11(pBlocks, isSigned, options, out=None):
+    """cvtt::Kernels::EncodeETC2Alpha11, reference ConvectionKernels.h:259 / ConvectionKernels_API.cpp:257-268.  pBlocks:
+    PixelBlockScalarS16 (int16 [n][16])"""
+    return encode("EAC_R11S" if isSigned else "EAC_R11U", pBlocks, options, None, out)

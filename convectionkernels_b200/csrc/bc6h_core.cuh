@@ -82,11 +82,6 @@ namespace cvttb200
     inline int f2i_rn(float a) { return _mm_cvtss_si32(_mm_set_ss(a)); }
 #endif
 
-    // ---- 16-bit integer semantics of the SSE2 lanes ----
-    CVTT_HD int wrap_s16(int v) { return (int)(int16_t)(uint16_t)(uint32_t)v; }
-    CVTT_HD int wrap_u16(int v) { return v & 0xffff; }
-    CVTT_HD int packs_s16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }    // _mm_packs_epi32
-
     // _mm_max_ps(_mm_min_ps(v, hi), lo), ParallelMath.h:561-567
     CVTT_HD float sse_clamp(float v, float lo, float hi) { return sse_max(sse_min(v, hi), lo); }
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <xmmintrin.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "../../include/cvtt_b200.h"
 #include "bc7_host.h"
 #include "bc6h_host.h"
+#include "etc_host.h"
 
 using namespace cvttb200;
 
@@ -249,6 +251,149 @@ namespace
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ETC1 / ETC2 / EAC
+
+namespace
+{
+    constexpr int kETCThreads = 128;
+    constexpr int kETCCtasPerSM = 4;
+
+    __constant__ ETCTables c_etcTables;
+
+    // group maximum (the reference's per-call maximum over its 8 lanes): butterfly over the lane's 8-lane segment
+    struct SegmentMax
+    {
+        __device__ __forceinline__ int max(int v) const
+        {
+            v = ::max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = ::max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+            v = ::max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            return v;
+        }
+    };
+
+    enum { kETCKindETC1 = 0, kETCKindETC2 = 1, kETCKindETC2RGBA = 2 };
+
+    // Persistent kernel: the grid is sized to the device (SMs x resident CTAs), every warp walks 32-block slices of the
+    // input.  One thread per block; the per-thread scratch of the differential / H-mode searches (the reference's
+    // ETC2CompressionData) is a slice of one global allocation, laid out [entry][thread].
+    template<int KIND, bool UNIFORM>
+    __global__ void __launch_bounds__(kETCThreads, kETCCtasPerSM)
+    etc_encode_kernel(const __grid_constant__ ETCParams P, const uint4 *__restrict__ in, uint32_t *__restrict__ out, uint32_t nBlocks, ETCScratch scratch)
+    {
+        __shared__ F4 sPw[16 * kETCThreads];
+        const uint32_t tid = threadIdx.x;
+        const uint32_t gthread = blockIdx.x * kETCThreads + tid;
+        const uint32_t totalThreads = gridDim.x * kETCThreads;
+
+        ETCScratch S = scratch;
+        S.drsErr += gthread;
+        S.drsMeta += gthread;
+        S.hErr += gthread;
+        S.hMeta += gthread;
+
+        ETCLane<kETCThreads> L;
+        L.pw = sPw + tid;
+        SegmentMax vote;
+
+        for (uint32_t base = (gthread & ~31u); base < nBlocks; base += totalThreads)
+        {
+            const uint32_t block = base + (tid & 31);
+            const bool active = block < nBlocks;
+            int alpha[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (active)
+                    v = __ldg(in + (size_t)block * 4 + q);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                {
+                    F4 p;
+                    const float r = (float)(w[k] & 0xffu), g = (float)((w[k] >> 8) & 0xffu), b = (float)((w[k] >> 16) & 0xffu);
+                    p.x = UNIFORM ? r : r * P.w[0];
+                    p.y = UNIFORM ? g : g * P.w[1];
+                    p.z = UNIFORM ? b : b * P.w[2];
+                    p.w = __uint_as_float(w[k]);
+                    sPw[(q * 4 + k) * kETCThreads + tid] = p;
+                    alpha[q * 4 + k] = (int)(w[k] >> 24);
+                }
+            }
+            __syncwarp();
+
+            uint32_t color[2];
+            if (KIND == kETCKindETC1)
+                etc1_encode_block<UNIFORM, kETCThreads>(P, c_etcTables, L, S, color);
+            else
+                etc2_encode_block<UNIFORM, kETCThreads>(P, c_etcTables, L, S, vote, color);
+
+            if (KIND == kETCKindETC2RGBA)
+            {
+                uint32_t a[2];
+                etc_alpha_encode_block(c_etcTables, alpha, false, false, a);
+                if (active)
+                    reinterpret_cast<uint4 *>(out)[block] = make_uint4(etc_bswap(a[0]), etc_bswap(a[1]), etc_bswap(color[0]), etc_bswap(color[1]));
+            }
+            else if (active)
+                reinterpret_cast<uint2 *>(out)[block] = make_uint2(etc_bswap(color[0]), etc_bswap(color[1]));
+            __syncwarp();
+        }
+    }
+
+    // EncodeETC2Alpha (8-bit alpha of PixelBlockU8) and EncodeETC2Alpha11 (PixelBlockScalarS16): pure integer, one thread per block
+    // kind: 0 = 8-bit alpha, 1 = EAC R11 unsigned, 2 = EAC R11 signed
+    template<int KIND>
+    __global__ void __launch_bounds__(128)
+    eac_encode_kernel(const void *__restrict__ in, uint2 *__restrict__ out, uint32_t nBlocks)
+    {
+        const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
+        if (block >= nBlocks)
+            return;
+        int a[16];
+        if (KIND == 0)
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(in) + (size_t)block * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                a[q * 4 + 0] = (int)(v.x >> 24);
+                a[q * 4 + 1] = (int)(v.y >> 24);
+                a[q * 4 + 2] = (int)(v.z >> 24);
+                a[q * 4 + 3] = (int)(v.w >> 24);
+            }
+        }
+        else
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(in) + (size_t)block * 2;
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    for (int h = 0; h < 2; h++)
+                    {
+                        // CompressEACBlock, ETC.cpp:2087-2110
+                        int px = (int)(int16_t)(uint16_t)(w[k] >> (16 * h));
+                        if (KIND == 2)
+                            px = ::max(1, ::min(px, 1023) + 1024);
+                        else
+                            px = ::max(0, ::min(px, 2047));
+                        a[q * 8 + k * 2 + h] = px;
+                    }
+            }
+        }
+        uint32_t o[2];
+        etc_alpha_encode_block(c_etcTables, a, KIND != 0, KIND == 2, o);
+        out[block] = make_uint2(etc_bswap(o[0]), etc_bswap(o[1]));
+    }
+}
+
 // =========================================================================================================
 // Host state
 
@@ -267,6 +412,7 @@ namespace
     {
         int device = -1;
         bool ready = false;
+        int numSMs = 0;
         std::vector<PlanCacheEntry> plans;
         void *stageIn = nullptr, *stageOut = nullptr;
         size_t stageInBytes = 0, stageOutBytes = 0;
@@ -332,6 +478,7 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
+        CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
@@ -340,6 +487,7 @@ namespace
         CVTT_CUDA(cudaSetDevice(prev));
 
         g_contexts.emplace_back();
+        g_contexts.back().numSMs = prop.multiProcessorCount;
         g_contexts.back().device = device;
         g_contexts.back().ready = true;
         *out = &g_contexts.back();
@@ -421,6 +569,59 @@ namespace
         g_launches++;
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
+    }
+
+    template<int KIND>
+    int launch_etc_color(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const ETCParams &P, bool uniform, cudaStream_t stream)
+    {
+        // resident threads: the whole device, or fewer for small inputs
+        const size_t warpsNeeded = (nBlocks + 31) / 32;
+        const size_t maxCtas = (size_t)ctx.numSMs * kETCCtasPerSM;
+        const unsigned grid = (unsigned)std::min(maxCtas, (warpsNeeded + kETCThreads / 32 - 1) / (kETCThreads / 32));
+        const size_t threads = (size_t)grid * kETCThreads;
+        void *dScratch = nullptr;
+        CVTT_CUDA(cudaMallocAsync(&dScratch, etc_scratch_bytes(threads), stream));
+        ETCScratch S;
+        etc_scratch_layout(S, dScratch, threads);
+        if (uniform)
+            etc_encode_kernel<KIND, true><<<grid, kETCThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+        else
+            etc_encode_kernel<KIND, false><<<grid, kETCThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+        g_launches++;
+        CVTT_CUDA(cudaGetLastError());
+        CVTT_CUDA(cudaFreeAsync(dScratch, stream));
+        return CVTTB200_OK;
+    }
+
+    int launch_etc(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, cudaStream_t stream)
+    {
+        if (nBlocks > 0xffffff00u)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
+        const unsigned grid = (unsigned)((nBlocks + 127) / 128);
+        if (format == CVTTB200_ETC2_ALPHA || format == CVTTB200_EAC_R11U || format == CVTTB200_EAC_R11S)
+        {
+            if (format == CVTTB200_ETC2_ALPHA)
+                eac_encode_kernel<0><<<grid, 128, 0, stream>>>(dIn, (uint2 *)dOut, (uint32_t)nBlocks);
+            else if (format == CVTTB200_EAC_R11U)
+                eac_encode_kernel<1><<<grid, 128, 0, stream>>>(dIn, (uint2 *)dOut, (uint32_t)nBlocks);
+            else
+                eac_encode_kernel<2><<<grid, 128, 0, stream>>>(dIn, (uint2 *)dOut, (uint32_t)nBlocks);
+            g_launches++;
+            CVTT_CUDA(cudaGetLastError());
+            return CVTTB200_OK;
+        }
+        if (options.flags & (kFlag_ETC_UseFakeBT709 | kFlag_ETC_FakeBT709Accurate))
+            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::ETC_UseFakeBT709 is not implemented yet");
+        ETCParams P;
+        etc_fill_params(P, options);
+        const bool uniform = (options.flags & kFlag_Uniform) != 0;
+        switch (format)
+        {
+        case CVTTB200_ETC1: return launch_etc_color<kETCKindETC1>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
+        case CVTTB200_ETC2: return launch_etc_color<kETCKindETC2>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
+        case CVTTB200_ETC2_RGBA: return launch_etc_color<kETCKindETC2RGBA>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
+        default: return fail(CVTTB200_ERR_UNSUPPORTED, "ETC2 punch-through alpha is not implemented yet");
+        }
     }
 
     int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, cudaStream_t stream)
@@ -622,7 +823,7 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
     const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
     if (!inBytes)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
-    if (format != CVTTB200_BC7 && format != CVTTB200_BC6HU && format != CVTTB200_BC6HS)
+    if (format < CVTTB200_BC6HU || format == CVTTB200_ETC2_PUNCHTHROUGH)
         return fail(CVTTB200_ERR_UNSUPPORTED, "format not implemented by this build (no CPU fallback exists)");
     if (format == CVTTB200_BC7 && !plan)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
@@ -670,8 +871,10 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
         memcpy(&planPOD, plan, sizeof(planPOD));
         rc = launch_bc7(*ctx, dIn, nBlocks, dOut, opt, planPOD, stream);
     }
-    else
+    else if (format == CVTTB200_BC6HU || format == CVTTB200_BC6HS)
         rc = launch_bc6h(dIn, nBlocks, dOut, opt, format == CVTTB200_BC6HS, stream);
+    else
+        rc = launch_etc(*ctx, format, dIn, nBlocks, dOut, opt, stream);
     if (rc != CVTTB200_OK)
         return rc;
 

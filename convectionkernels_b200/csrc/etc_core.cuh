@@ -1,0 +1,1117 @@
+// ETC1 / ETC2 RGB / EAC alpha encode search, one 4x4 block per thread (lane = block; see cvtt_common.cuh).
+//
+// What it reproduces (reference elasota/ConvectionKernels, file:line):
+//   ETCComputer::CompressETC2Block            ConvectionKernels_ETC.cpp:1664-1887 (without punch-through)
+//   ETCComputer::EncodePlanar                 :1274-1662
+//   ETCComputer::EncodeTMode / EncodeHMode    :396-647 / :649-885
+//   ETCComputer::CompressETC1BlockInternal    :2624-2882, TestHalfBlock :94-149,
+//   FindBestDifferentialCombination           :219-362 (the scalar sorted search, here per lane without a sort)
+//   CompressETC2AlphaBlockInternal            :1902-2085, QuantizeETC2Alpha :2366-2411 (8-bit alpha and EAC R11)
+//   EmitTModeBlock / EmitHModeBlock / EmitETC1Block  :2414-2622
+//   tables                                    ConvectionKernels_ETC1.h, ConvectionKernels_ETC2.h, ConvectionKernels_ETC2_Rounding.h
+//
+// Not implemented (rejected by the host with CVTTB200_ERR_UNSUPPORTED): Flags::ETC_UseFakeBT709 and the
+// punch-through variants.
+//
+// Cross-lane semantics: every AnySet guard of these functions is idempotent except one.  In T
+// mode the candidate list of a lane with fewer unique line colours than the largest count in its group of 8 has a
+// never-written slot (ETC.cpp:570-577: the fill loop starts at numUnique + 1), which the zero-initialised
+// reference build evaluates as colour 0.  The kernel therefore needs the group maximum of the unique-colour count
+// (Vote::max) and evaluates that extra candidate.
+//
+// Scratch (the reference's DifferentialResolveStorage and HModeEval, ETC.h:36-55, "AllocETC2Data") lives in global
+// memory, laid out [entry][thread] so that a warp's accesses to one entry are contiguous.
+#pragma once
+
+#include "cvtt_common.cuh"
+
+namespace cvttb200
+{
+#ifndef CVTT_F4_DEFINED
+#define CVTT_F4_DEFINED
+    struct alignas(16) F4 { float x, y, z, w; };
+#endif
+
+    enum { kETCMaxAttempts = 624, kETCHColors = 62 };
+
+    struct ETCParams
+    {
+        float w[3];                 // options.redWeight / greenWeight / blueWeight (the ETC path does not use FillWeights)
+        float wSq[3];               // w * w, the per-channel factors of EncodePlanar (ETC.cpp:1561-1577)
+        float chromaAxis0[3], chromaAxis1[3];       // ETC2CompressionDataInternal ctor, ETC.cpp:3117-3145
+        // scalar constants of EncodePlanar's 3x3 solve (ETC.cpp:1294-1386), identical for every block and channel
+        float pl_r0to1, pl_r0to2, pl_r1to2, pl_n2, pl_r2to1, pl_elim2, pl_elim1, pl_d, pl_k1;
+        uint32_t flags;
+    };
+
+    struct ETCTables
+    {
+        int16_t potentialOffsets[8 * 82];           // per table: count, then the offsets (Tables::ETC1::g_potentialOffsets4)
+        int16_t thModifier[8];                      // g_thModifierTable
+        int16_t alphaModifier[16][4];               // Tables::ETC2::g_alphaModifierTablePositive
+        uint8_t alphaRounding[16][16];              // Tables::ETC2::g_alphaRoundingTables (13 wide)
+        int16_t etc1Modifiers[8][4];                // modifierTables of CompressETC1BlockInternal, ETC.cpp:2665-2675
+    };
+
+    template<int STRIDE>
+    struct ETCLane
+    {
+        const F4 *pw;               // pw[px * STRIDE]: .xyz = pre-weighted pixel (ExtractBlocks, ETC.cpp:2128-2155), .w = bits r | g << 8 | b << 16 | a << 24
+    };
+
+    // per-thread scratch; element i of an array is at [i * stride]
+    struct ETCScratch
+    {
+        float *drsErr;              // [2 * kETCMaxAttempts]   DifferentialResolveStorage::diffErrors
+        uint32_t *drsMeta;          // [2 * kETCMaxAttempts]   packed colour | table << 15
+        float *hErr;                // [kETCHColors * 16]      HModeEval::errors
+        uint32_t *hMeta;            // [kETCHColors]           signBits | uniqueQuantizedColor << 16
+        size_t stride;
+    };
+
+    struct ETCBest
+    {
+        float error;
+        uint32_t hi, lo;            // the 8 output bytes as two big-endian words
+    };
+
+    CVTT_HD int etc_px(const F4 &p, int ch) { return (int)((as_uint(p.w) >> (8 * ch)) & 0xffu); }
+    CVTT_HD int imin(int a, int b) { return a < b ? a : b; }
+    CVTT_HD int imax(int a, int b) { return a > b ? a : b; }
+
+    // ComputeErrorUniform (ETC.cpp:59-71) / ComputeErrorWeighted (:73-80).  cw = (float)colour * weight per channel.
+    template<bool UNIFORM>
+    CVTT_HD float etc_error(const F4 &p, const int *c, const float *cw)
+    {
+        if (UNIFORM)
+        {
+            const float d0 = (float)(etc_px(p, 0) - c[0]), d1 = (float)(etc_px(p, 1) - c[1]), d2 = (float)(etc_px(p, 2) - c[2]);
+            return fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fmul(d2, d2));
+        }
+        else
+        {
+            const float dr = fsub(cw[0], p.x), dg = fsub(cw[1], p.y), db = fsub(cw[2], p.z);
+            return fadd(fadd(fmul(dr, dr), fmul(dg, dg)), fmul(db, db));
+        }
+    }
+
+    template<bool UNIFORM>
+    CVTT_HD void etc_weigh(const ETCParams &P, const int *c, float *cw)
+    {
+        if (!UNIFORM)
+            for (int ch = 0; ch < 3; ch++)
+                cw[ch] = fmul((float)c[ch], P.w[ch]);
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // emitters (ETC.cpp:2414-2622)
+    CVTT_HD void etc_emit_t(ETCBest &best, const int *lineColor, const int *isolatedColor, uint32_t packedSelectors, int table, bool opaque)
+    {
+        uint32_t lowBits = 0, highBits = 0;
+        const int rh = (isolatedColor[0] >> 2) & 3, rl = isolatedColor[0] & 3;
+        if (rh + rl < 4)
+            highBits |= 1u << (58 - 32);
+        else
+            highBits |= 7u << (61 - 32);
+        highBits |= (uint32_t)rh << (59 - 32);
+        highBits |= (uint32_t)rl << (56 - 32);
+        highBits |= (uint32_t)isolatedColor[1] << (52 - 32);
+        highBits |= (uint32_t)isolatedColor[2] << (48 - 32);
+        highBits |= (uint32_t)lineColor[0] << (44 - 32);
+        highBits |= (uint32_t)lineColor[1] << (40 - 32);
+        highBits |= (uint32_t)lineColor[2] << (36 - 32);
+        highBits |= (uint32_t)((table >> 1) & 3) << (34 - 32);
+        if (opaque)
+            highBits |= 1u << (33 - 32);
+        highBits |= (uint32_t)(table & 1);
+        for (int px = 0; px < 16; px++)
+        {
+            const int order = (px & 3) * 4 + (px >> 2);       // selectorOrder
+            const uint32_t sel = (packedSelectors >> (2 * order)) & 3u;
+            if (sel & 1u)
+                lowBits |= 1u << px;
+            if (sel & 2u)
+                lowBits |= 1u << (16 + px);
+        }
+        best.hi = highBits;
+        best.lo = lowBits;
+    }
+
+    CVTT_HD void etc_emit_h(ETCBest &best, const int *blockColors, uint32_t sectorBits, uint32_t signBits, int table, bool opaque)
+    {
+        if (blockColors[0] == blockColors[1])
+        {
+            int lineColor[3], isolatedColor[3];
+            lineColor[0] = isolatedColor[0] = (blockColors[0] >> 10) & 0x1f;
+            lineColor[1] = isolatedColor[1] = (blockColors[0] >> 5) & 0x1f;
+            lineColor[2] = isolatedColor[2] = blockColors[0] & 0x1f;
+            uint32_t packedSelectors = 0x55555555u;
+            for (int px = 0; px < 16; px++)
+                packedSelectors |= ((signBits >> px) & 1u) << (px * 2 + 1);
+            etc_emit_t(best, lineColor, isolatedColor, packedSelectors, table, opaque);
+            return;
+        }
+        int colors[2][3];
+        for (int sector = 0; sector < 2; sector++)
+            for (int ch = 0; ch < 3; ch++)
+                colors[sector][ch] = (blockColors[sector] >> ((2 - ch) * 5)) & 15;
+        uint32_t lowBits = 0, highBits = 0;
+        if (((table & 1) == 1) != (blockColors[0] > blockColors[1]))
+        {
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int t = colors[0][ch];
+                colors[0][ch] = colors[1][ch];
+                colors[1][ch] = t;
+            }
+            sectorBits ^= 0xffffu;
+        }
+        const int r1 = colors[0][0], g1a = colors[0][1] >> 1, g1b = colors[0][1] & 1, b1a = colors[0][2] >> 3, b1b = colors[0][2] & 7;
+        const int r2 = colors[1][0], g2 = colors[1][1], b2 = colors[1][2];
+        if ((g1a & 4) != 0 && r1 + g1a < 8)
+            highBits |= 1u << (63 - 32);
+        const int fakeDG = b1b >> 1, fakeG = b1a | (g1b << 1);
+        if (fakeG + fakeDG < 4)
+            highBits |= 1u << (50 - 32);
+        else
+            highBits |= 7u << (53 - 32);
+        const int da = (table >> 2) & 1, db = (table >> 1) & 1;
+        highBits |= (uint32_t)r1 << (59 - 32);
+        highBits |= (uint32_t)g1a << (56 - 32);
+        highBits |= (uint32_t)g1b << (52 - 32);
+        highBits |= (uint32_t)b1a << (51 - 32);
+        highBits |= (uint32_t)b1b << (47 - 32);
+        highBits |= (uint32_t)r2 << (43 - 32);
+        highBits |= (uint32_t)g2 << (39 - 32);
+        highBits |= (uint32_t)b2 << (35 - 32);
+        highBits |= (uint32_t)da << (34 - 32);
+        if (opaque)
+            highBits |= 1u << (33 - 32);
+        highBits |= (uint32_t)db;
+        for (int px = 0; px < 16; px++)
+        {
+            const int order = (px & 3) * 4 + (px >> 2);
+            lowBits |= ((signBits >> order) & 1u) << px;
+            lowBits |= ((sectorBits >> order) & 1u) << (16 + px);
+        }
+        best.hi = highBits;
+        best.lo = lowBits;
+    }
+
+    // block pixel of (flip, sector, i): g_flipTables, ETC.cpp:47-57
+    CVTT_HD int etc_flip_pixel(int flip, int sector, int i)
+    {
+        return flip ? (sector * 8 + i) : ((i >> 1) * 4 + sector * 2 + (i & 1));
+    }
+
+    CVTT_HD void etc_emit_etc1(ETCBest &best, int flip, int d, const int colors[2][3], const int *tables, const uint32_t *selectors)
+    {
+        uint32_t highBits = 0, lowBits = 0;
+        if (d == 0)
+        {
+            highBits |= (uint32_t)colors[0][0] << 28;
+            highBits |= (uint32_t)colors[1][0] << 24;
+            highBits |= (uint32_t)colors[0][1] << 20;
+            highBits |= (uint32_t)colors[1][1] << 16;
+            highBits |= (uint32_t)colors[0][2] << 12;
+            highBits |= (uint32_t)colors[1][2] << 8;
+        }
+        else
+        {
+            highBits |= (uint32_t)colors[0][0] << 27;
+            highBits |= (uint32_t)((colors[1][0] - colors[0][0]) & 7) << 24;
+            highBits |= (uint32_t)colors[0][1] << 19;
+            highBits |= (uint32_t)((colors[1][1] - colors[0][1]) & 7) << 16;
+            highBits |= (uint32_t)colors[0][2] << 11;
+            highBits |= (uint32_t)((colors[1][2] - colors[0][2]) & 7) << 8;
+        }
+        highBits |= (uint32_t)tables[0] << 5;
+        highBits |= (uint32_t)tables[1] << 2;
+        highBits |= (uint32_t)d << 1;
+        highBits |= (uint32_t)flip;
+        uint32_t codes = 0;     // 2 bits per block pixel
+        for (int sector = 0; sector < 2; sector++)
+            for (int px = 0; px < 8; px++)
+            {
+                const uint32_t selector = (selectors[sector] >> (2 * px)) & 3u;
+                const uint32_t code = (0x4B >> (2 * selector)) & 3u;          // modifierCodes { 3, 2, 0, 1 }
+                codes |= code << (2 * etc_flip_pixel(flip, sector, px));
+            }
+        for (int sb = 0; sb < 2; sb++)
+            for (int px = 0; px < 16; px++)
+            {
+                const int order = (px & 3) * 4 + (px >> 2);
+                lowBits |= ((codes >> (2 * order + sb)) & 1u) << (px + sb * 16);
+            }
+        best.hi = highBits;
+        best.lo = lowBits;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // EncodePlanar, ETC.cpp:1274-1662 (RGB path)
+    template<bool UNIFORM, int STRIDE>
+    CVTT_HD void etc_planar(const ETCParams &P, const ETCLane<STRIDE> &L, ETCBest &best)
+    {
+        float totalError = 0.0f;
+        int bestCoeffs[3][3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            float fc = 0.0f, fh = 0.0f, fv = 0.0f, fo = 0.0f;
+            for (int px = 0; px < 16; px++)
+            {
+                const float x = (float)(px % 4), y = (float)(px / 4);
+                const float c = (float)etc_px(L.pw[px * STRIDE], ch);
+                fh = fsub(fh, fmul(c, x));
+                fv = fsub(fv, fmul(c, y));
+                fo = fsub(fo, c);
+                fh = fsub(fh, fmul(c, x));
+                fv = fsub(fv, fmul(c, y));
+                fo = fsub(fo, c);
+                fc = fadd(fc, fmul(c, c));
+            }
+            const float gD = fh, lD = fv, qD = fo;
+            const float l1D = fadd(lD, fmul(gD, P.pl_r0to1));
+            const float q1D = fadd(qD, fmul(gD, P.pl_r0to2));
+            const float q2D = fadd(q1D, fmul(l1D, P.pl_r1to2));
+            const float o = fdiv(fsub(0.0f, q2D), P.pl_n2);
+            const float l2D = fadd(l1D, fmul(q2D, P.pl_r2to1));
+            const float g2D = fadd(fadd(gD, fmul(l2D, P.pl_elim2)), fmul(q2D, P.pl_elim1));
+            float h = fdiv(fsub(0.0f, g2D), P.pl_d);
+            float v = fdiv(fsub(0.0f, l2D), P.pl_k1);
+            h = fadd(fmul(h, 4.0f), o);
+            v = fadd(fmul(v, 4.0f), o);
+
+            const float fcoeffsIn[3] = { o, h, v };
+            int ranges[3][2];
+            for (int c = 0; c < 3; c++)
+            {
+                float coeff = sse_max(0.0f, fcoeffsIn[c]);
+                if (ch == 1)
+                    coeff = sse_min(127.0f, fmul(coeff, 127.0f / 255.0f));
+                else
+                    coeff = sse_min(63.0f, fmul(coeff, 63.0f / 255.0f));
+                // RoundAndConvertToU15 under round-down / round-up (the value is in 0..127)
+                ranges[c][0] = (int)floorf(coeff);
+                ranges[c][1] = (int)ceilf(coeff);
+            }
+
+            float bestChannelError = FLT_MAX;
+            for (int io = 0; io < 2; io++)
+                for (int ih = 0; ih < 2; ih++)
+                    for (int iv = 0; iv < 2; iv++)
+                    {
+                        const int cO = ranges[0][io], cH = ranges[1][ih], cV = ranges[2][iv];
+                        // DecodePlanarCoeff, ETC.cpp:1264-1270
+                        const int dO = (ch == 1) ? ((cO << 1) | (cO >> 6)) : ((cO << 2) | (cO >> 4));
+                        const int dH = (ch == 1) ? ((cH << 1) | (cH >> 6)) : ((cH << 2) | (cH >> 4));
+                        const int dV = (ch == 1) ? ((cV << 1) | (cV >> 6)) : ((cV << 2) | (cV >> 4));
+                        const int hMinusO = dH - dO, vMinusO = dV - dO, addend = (dO << 2) + 2;
+                        float error = 0.0f;
+                        for (int px = 0; px < 16; px++)
+                        {
+                            const int interpolated = ((px & 3) * hMinusO + (px >> 2) * vMinusO + addend) >> 2;
+                            const int dec = imin(255, imax(0, interpolated));
+                            const float deltaF = (float)(etc_px(L.pw[px * STRIDE], ch) - dec);
+                            error = fadd(error, fmul(deltaF, deltaF));
+                        }
+                        if (error < bestChannelError)
+                        {
+                            bestChannelError = error;
+                            bestCoeffs[ch][0] = cO;
+                            bestCoeffs[ch][1] = cH;
+                            bestCoeffs[ch][2] = cV;
+                        }
+                    }
+            if (!UNIFORM)
+                bestChannelError = fmul(bestChannelError, P.wSq[ch]);
+            totalError = fadd(totalError, bestChannelError);
+        }
+
+        if (totalError < best.error)
+        {
+            best.error = totalError;
+            const int ro = bestCoeffs[0][0], rh = bestCoeffs[0][1], rv = bestCoeffs[0][2];
+            const int go = bestCoeffs[1][0], gh = bestCoeffs[1][1], gv = bestCoeffs[1][2];
+            const int bo = bestCoeffs[2][0], bh = bestCoeffs[2][1], bv = bestCoeffs[2][2];
+            const int go1 = go >> 6, go2 = go & 63, bo1 = bo >> 5, bo2 = (bo >> 3) & 3, bo3 = bo & 7, rh1 = rh >> 1, rh2 = rh & 1;
+            const int fakeR = ro >> 2, fakeDR = go1 | ((ro & 3) << 1);
+            const int fakeG = go2 >> 2, fakeDG = ((go2 & 3) << 1) | bo1;
+            const int fakeB = bo2, fakeDB = bo3 >> 1;
+            uint32_t highBits = 0, lowBits = 0;
+            if ((fakeDR & 4) != 0 && fakeR + fakeDR < 8)
+                highBits |= 1u << (63 - 32);
+            if ((fakeDG & 4) != 0 && fakeG + fakeDG < 8)
+                highBits |= 1u << (55 - 32);
+            if (fakeB + fakeDB < 4)
+                highBits |= 1u << (42 - 32);
+            else
+                highBits |= 7u << (45 - 32);
+            highBits |= (uint32_t)ro << (57 - 32);
+            highBits |= (uint32_t)go1 << (56 - 32);
+            highBits |= (uint32_t)go2 << (49 - 32);
+            highBits |= (uint32_t)bo1 << (48 - 32);
+            highBits |= (uint32_t)bo2 << (43 - 32);
+            highBits |= (uint32_t)bo3 << (39 - 32);
+            highBits |= (uint32_t)rh1 << (34 - 32);
+            highBits |= 1u << (33 - 32);
+            highBits |= (uint32_t)rh2;
+            lowBits |= (uint32_t)gh << 25;
+            lowBits |= (uint32_t)bh << 19;
+            lowBits |= (uint32_t)rv << 13;
+            lowBits |= (uint32_t)gv << 6;
+            lowBits |= (uint32_t)bv;
+            best.hi = highBits;
+            best.lo = lowBits;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // EncodeTMode, ETC.cpp:396-647.  isolatedMask: bit px set = pixel is in the isolated cluster.
+    template<bool UNIFORM, int STRIDE, class Vote>
+    CVTT_HD void etc_t_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, Vote &vote, uint32_t isolatedMask, ETCBest &best)
+    {
+        int isolatedTotal[3] = { 0, 0, 0 }, lineTotal[3] = { 0, 0, 0 }, numIsolated = 0;
+        for (int px = 0; px < 16; px++)
+        {
+            const F4 p = L.pw[px * STRIDE];
+            const bool iso = (isolatedMask >> px) & 1;
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int v = etc_px(p, ch);
+                lineTotal[ch] += v;
+                if (iso)
+                    isolatedTotal[ch] += v;
+            }
+            numIsolated += iso ? 1 : 0;
+        }
+        for (int ch = 0; ch < 3; ch++)
+            lineTotal[ch] -= isolatedTotal[ch];
+        const int numLine = 16 - numIsolated;
+
+        int isolatedQ[3], isolatedColor[3];
+        {
+            const int divisor = numIsolated * 34, addend = (numIsolated << 4) | numIsolated;
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int numerator = isolatedTotal[ch] + isolatedTotal[ch] + addend;
+                isolatedQ[ch] = (divisor == 0) ? 0 : (numerator / divisor);
+                isolatedColor[ch] = isolatedQ[ch] | (isolatedQ[ch] << 4);
+            }
+        }
+        float isoW[3];
+        etc_weigh<UNIFORM>(P, isolatedColor, isoW);
+
+        bool bestIsThisMode = false;
+        uint32_t bestSelectors = 0;
+        int bestTable = 0, bestLineColor = 0;
+        const int lineDivisor = numLine * 34, lineAddend = (numLine << 4) | numLine;
+
+        for (int table = 0; table < 8; table++)
+        {
+            const int modifier = T.thModifier[table];
+            const int modifierOffset = modifier + modifier;
+
+            // unique line colours of this lane, in order (at most 2 * numLine + 1 <= 33, the reference keeps 31)
+            int numUnique = 0, lastColor = -1;
+            // first pass counts, second pass evaluates: the group maximum of the count is needed before the extra candidate
+            for (int offs = -numLine; offs <= numLine; offs++)
+            {
+                int packed = 0;
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + lineAddend + offs * modifierOffset));
+                    const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
+                    packed |= imin(15, divided) << (ch * 5);
+                }
+                if (numUnique == 0 || packed != lastColor)
+                {
+                    numUnique++;
+                    lastColor = packed;
+                }
+            }
+            const int maxUnique = vote.max(numUnique);
+            const int numCandidates = numUnique + ((numUnique < maxUnique) ? 1 : 0);
+
+            int offs = -numLine;
+            lastColor = -1;
+            for (int ci = 0; ci < numCandidates; ci++)
+            {
+                int packedColor = 0;        // the never-written slot of the reference's candidate array reads as colour 0
+                if (ci < numUnique)
+                {
+                    for (;;)
+                    {
+                        int packed = 0;
+                        for (int ch = 0; ch < 3; ch++)
+                        {
+                            const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + lineAddend + offs * modifierOffset));
+                            const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
+                            packed |= imin(15, divided) << (ch * 5);
+                        }
+                        offs++;
+                        if (packed != lastColor)
+                        {
+                            lastColor = packed;
+                            packedColor = packed;
+                            break;
+                        }
+                    }
+                }
+
+                int lineColors[3][3];
+                float lineW[3][3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const int q = (packedColor >> (ch * 5)) & 15;
+                    const int unq = (q << 4) | q;
+                    lineColors[0][ch] = imin(255, unq + modifier);
+                    lineColors[1][ch] = unq;
+                    lineColors[2][ch] = imax(0, unq - modifier);
+                }
+                for (int i = 0; i < 3; i++)
+                    etc_weigh<UNIFORM>(P, lineColors[i], lineW[i]);
+
+                uint32_t selectors = 0;
+                float error = 0.0f;
+                for (int px = 0; px < 16; px++)
+                {
+                    const F4 p = L.pw[px * STRIDE];
+                    float pixelError = etc_error<UNIFORM>(p, isolatedColor, isoW);
+                    uint32_t pixelBestSelector = 0;
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+                    {
+                        const float e = etc_error<UNIFORM>(p, lineColors[i], lineW[i]);
+                        if (e < pixelError)
+                            pixelBestSelector = (uint32_t)(i + 1);
+                        pixelError = sse_min(e, pixelError);
+                    }
+                    error = fadd(error, pixelError);
+                    selectors |= pixelBestSelector << (px * 2);
+                }
+                if (error < best.error)
+                {
+                    best.error = error;
+                    bestLineColor = packedColor;
+                    bestSelectors = selectors;
+                    bestTable = table;
+                    bestIsThisMode = true;
+                }
+            }
+        }
+
+        if (bestIsThisMode)
+        {
+            int lineColor[3];
+            for (int ch = 0; ch < 3; ch++)
+                lineColor[ch] = (bestLineColor >> (ch * 5)) & 15;
+            etc_emit_t(best, lineColor, isolatedQ, bestSelectors, bestTable, true);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // EncodeHMode, ETC.cpp:649-885.  groupMask: bit px set = pixel belongs to sector 1.
+    template<bool UNIFORM, int STRIDE>
+    CVTT_HD void etc_h_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, uint32_t groupMask, ETCBest &best)
+    {
+        int totals[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } }, counts[2] = { 0, 0 };
+        for (int px = 0; px < 16; px++)
+        {
+            const F4 p = L.pw[px * STRIDE];
+            const bool g = (groupMask >> px) & 1;
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int v = etc_px(p, ch);
+                totals[0][ch] += v;
+                if (g)
+                    totals[1][ch] += v;
+            }
+            counts[1] += g ? 1 : 0;
+        }
+        for (int ch = 0; ch < 3; ch++)
+            totals[0][ch] -= totals[1][ch];
+        counts[0] = 16 - counts[1];
+
+        bool bestIsThisMode = false;
+        uint32_t bestSectorBits = 0, bestSignBits = 0;
+        int bestColors[2] = { 0, 0 }, bestTable = 0;
+
+        for (int table = 0; table < 8; table++)
+        {
+            const int modifier = T.thModifier[table];
+            const int modifierOffset = modifier * 2;
+            int numUnique[2] = { 0, 0 };
+
+            // unique colours per sector, each evaluated once against all 16 pixels (errors of the better of +-modifier)
+            int total = 0;
+            for (int sector = 0; sector < 2; sector++)
+            {
+                const int count = counts[sector];
+                int lastColor = -1;
+                for (int offs = -count; offs <= count; offs++)
+                {
+                    int packed = 0;
+                    for (int ch = 0; ch < 3; ch++)
+                    {
+                        int q = 0;
+                        if (count != 0)
+                            q = imin(15, imax(0, wrap_s16(totals[sector][ch] * 2 + count * 17 + modifierOffset * offs)) / (count * 34));
+                        packed |= q << ((2 - ch) * 5);
+                    }
+                    if (numUnique[sector] != 0 && packed == lastColor)
+                        continue;
+                    lastColor = packed;
+                    numUnique[sector]++;
+
+                    int colors[2][3];
+                    float cw[2][3];
+                    for (int ch = 0; ch < 3; ch++)
+                    {
+                        const int q = (packed >> ((2 - ch) * 5)) & 15;
+                        const int unq = (q << 4) | q;
+                        colors[0][ch] = imin(255, unq + modifier);
+                        colors[1][ch] = imax(0, unq - modifier);
+                    }
+                    etc_weigh<UNIFORM>(P, colors[0], cw[0]);
+                    etc_weigh<UNIFORM>(P, colors[1], cw[1]);
+                    uint32_t signBits = 0;
+                    for (int px = 0; px < 16; px++)
+                    {
+                        const F4 p = L.pw[px * STRIDE];
+                        const float e0 = etc_error<UNIFORM>(p, colors[0], cw[0]), e1 = etc_error<UNIFORM>(p, colors[1], cw[1]);
+                        if (e1 < e0)
+                            signBits |= 1u << px;
+                        S.hErr[(size_t)(total * 16 + px) * S.stride] = sse_min(e0, e1);
+                    }
+                    S.hMeta[(size_t)total * S.stride] = signBits | ((uint32_t)packed << 16);
+                    total++;
+                }
+            }
+
+            // colour pairs in the reference's stepping order (ETC.cpp:800-822); a lane only needs its own n0 * n1 steps
+            const int n0 = numUnique[0], n1 = numUnique[1];
+            const int combos = n0 * n1;
+            int index0 = 0, index1 = 0;
+            for (int combo = 0; combo < combos; combo++)
+            {
+                index0++;
+                const bool overflow = (n0 - 1) < index0;
+                if (overflow)
+                    index0 = 0;
+                index1 = imin(n1 - 1, index1 + (overflow ? 1 : 0));
+                const int ci0 = index0, ci1 = index1 + n0;
+                const uint32_t m0 = S.hMeta[(size_t)ci0 * S.stride], m1 = S.hMeta[(size_t)ci1 * S.stride];
+
+                float totalError = 0.0f;
+                uint32_t sectorBits = 0;
+                for (int px = 0; px < 16; px++)
+                {
+                    const float e0 = S.hErr[(size_t)(ci0 * 16 + px) * S.stride], e1 = S.hErr[(size_t)(ci1 * 16 + px) * S.stride];
+                    totalError = fadd(totalError, sse_min(e0, e1));
+                    if (e1 < e0)
+                        sectorBits |= 1u << px;
+                }
+                if (totalError < best.error)
+                {
+                    best.error = totalError;
+                    bestIsThisMode = true;
+                    bestTable = table;
+                    bestColors[0] = (int)(m0 >> 16);
+                    bestColors[1] = (int)(m1 >> 16);
+                    bestSectorBits = sectorBits;
+                    bestSignBits = ((m1 & sectorBits) | (m0 & ~sectorBits)) & 0xffffu;
+                }
+            }
+        }
+
+        if (bestIsThisMode)
+            etc_emit_h(best, bestColors, bestSectorBits, bestSignBits, bestTable, true);
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // TestHalfBlock, ETC.cpp:94-149
+    template<bool UNIFORM, int STRIDE>
+    CVTT_HD float etc_test_half_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, int flip, int sector, int packedColor, int table, bool differential, uint32_t &outSelectors)
+    {
+        int mod[4][3];
+        float modW[4][3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const int q = (packedColor >> (ch * 5)) & 31;
+            const int unq = differential ? ((q << 3) | (q >> 2)) : ((q << 4) | q);
+            for (int s = 0; s < 4; s++)
+                mod[s][ch] = imin(imax(unq + T.etc1Modifiers[table][s], 0), 255);
+        }
+        for (int s = 0; s < 4; s++)
+            etc_weigh<UNIFORM>(P, mod[s], modW[s]);
+
+        uint32_t selectors = 0;
+        float totalError = 0.0f;
+#pragma unroll
+        for (int px = 0; px < 8; px++)
+        {
+            const F4 p = L.pw[etc_flip_pixel(flip, sector, px) * STRIDE];
+            float bestError = FLT_MAX;
+            uint32_t bestSelector = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+            {
+                const float e = etc_error<UNIFORM>(p, mod[s], modW[s]);
+                if (e < bestError)
+                    bestSelector = (uint32_t)s;
+                bestError = sse_min(e, bestError);
+            }
+            totalError = fadd(totalError, bestError);
+            selectors |= bestSelector << (px * 2);
+        }
+        outSelectors = selectors;
+        return totalError;
+    }
+
+    CVTT_HD bool etc_differential_legal(int a, int b)
+    {
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const int diff = ((b >> (ch * 5)) & 31) - ((a >> (ch * 5)) & 31);
+            if (diff < -4 || diff > 3)
+                return false;
+        }
+        return true;
+    }
+
+    // CompressETC1BlockInternal, ETC.cpp:2624-2882.  MIN_D = 1 is the ETC2 call (differential only), 0 is ETC1.
+    template<bool UNIFORM, int MIN_D, int STRIDE>
+    CVTT_HD void etc_etc1(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, ETCBest &best)
+    {
+        bool bestIsThisMode = false;
+        int bestColors[2] = { 0, 0 }, bestTables[2] = { 0, 0 }, bestFlip = 0, bestD = 0;
+        uint32_t bestSelectors[2] = { 0, 0 };
+
+        for (int flip = 0; flip < 2; flip++)
+        {
+            int cumulative[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+            for (int sector = 0; sector < 2; sector++)
+                for (int px = 0; px < 8; px++)
+                {
+                    const F4 p = L.pw[etc_flip_pixel(flip, sector, px) * STRIDE];
+                    for (int ch = 0; ch < 3; ch++)
+                        cumulative[sector][ch] += etc_px(p, ch);
+                }
+
+            int numAttempts[2] = { 0, 0 };
+            float bestIndError[2] = { FLT_MAX, FLT_MAX };
+            uint32_t bestIndSelectors[2] = { 0, 0 };
+            int bestIndColors[2] = { 0, 0 }, bestIndTable[2] = { 0, 0 };
+
+            for (int d = MIN_D; d < 2; d++)
+            {
+                for (int sector = 0; sector < 2; sector++)
+                {
+                    const int16_t *potentialOffsets = T.potentialOffsets;
+                    for (int table = 0; table < 8; table++)
+                    {
+                        const int numOffsets = *potentialOffsets++;
+                        int lastColor = -1;
+                        for (int oi = 0; oi < numOffsets; oi++)
+                        {
+                            int packed = 0;
+                            for (int ch = 0; ch < 3; ch++)
+                            {
+                                const int cu = imin(2040, imax(0, cumulative[sector][ch] + potentialOffsets[oi]));
+                                const int q = (d == 1) ? (((cu << 5) - cu + (cu >> 3) + 1024) >> 11) : (((cu << 5) - (cu << 1) + (cu >> 3) + 2048) >> 12);
+                                packed |= q << (ch * 5);
+                            }
+                            if (oi != 0 && packed == lastColor)
+                                continue;       // adjacent duplicates are dropped (ETC.cpp:2756-2768)
+                            lastColor = packed;
+
+                            uint32_t selectors;
+                            const float error = etc_test_half_block<UNIFORM, STRIDE>(P, T, L, flip, sector, packed, table, d == 1, selectors);
+                            if (d == 0)
+                            {
+                                if (error < bestIndError[sector])
+                                {
+                                    bestIndError[sector] = error;
+                                    bestIndSelectors[sector] = selectors;
+                                    bestIndColors[sector] = packed;
+                                    bestIndTable[sector] = table;
+                                }
+                            }
+                            else
+                            {
+                                const size_t slot = (size_t)(sector * kETCMaxAttempts + numAttempts[sector]) * S.stride;
+                                S.drsErr[slot] = error;
+                                S.drsMeta[slot] = (uint32_t)packed | ((uint32_t)table << 15);
+                                numAttempts[sector]++;
+                            }
+                        }
+                        potentialOffsets += numOffsets;
+                    }
+                }
+
+                if (d == 0)
+                {
+                    const float total = fadd(bestIndError[0], bestIndError[1]);
+                    if (total < best.error)
+                    {
+                        bestIsThisMode = true;
+                        best.error = total;
+                        bestFlip = flip;
+                        bestD = 0;
+                        for (int sector = 0; sector < 2; sector++)
+                        {
+                            bestColors[sector] = bestIndColors[sector];
+                            bestSelectors[sector] = bestIndSelectors[sector];
+                            bestTables[sector] = bestIndTable[sector];
+                        }
+                    }
+                }
+                else
+                {
+                    // FindBestDifferentialCombination, ETC.cpp:219-362 (canIgnoreSector is false without punch-through)
+                    const float blockBestTotalError = best.error;
+                    float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
+                    uint32_t bestDiffMeta[2] = { 0, 0 };
+                    int kept[2] = { 0, 0 };
+                    for (int sector = 0; sector < 2; sector++)
+                        for (int i = 0; i < numAttempts[sector]; i++)
+                        {
+                            const size_t slot = (size_t)(sector * kETCMaxAttempts + i) * S.stride;
+                            const float error = S.drsErr[slot];
+                            const uint32_t meta = S.drsMeta[slot];
+                            if (error < bestDiffErrors[sector])
+                            {
+                                bestDiffErrors[sector] = error;
+                                bestDiffMeta[sector] = meta;
+                            }
+                            // stable compaction of the attempts the slow path may look at (error < blockBestTotalError)
+                            if (error < blockBestTotalError)
+                            {
+                                const size_t dst = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
+                                S.drsErr[dst] = error;
+                                S.drsMeta[dst] = meta;
+                                kept[sector]++;
+                            }
+                        }
+
+                    int winMeta[2] = { -1, -1 };
+                    float winTotal = 0.0f;
+                    if (fadd(bestDiffErrors[0], bestDiffErrors[1]) < blockBestTotalError)
+                    {
+                        if (etc_differential_legal((int)(bestDiffMeta[0] & 0x7fffu), (int)(bestDiffMeta[1] & 0x7fffu)))
+                        {
+                            winMeta[0] = (int)bestDiffMeta[0];
+                            winMeta[1] = (int)bestDiffMeta[1];
+                            winTotal = fadd(bestDiffErrors[0], bestDiffErrors[1]);
+                        }
+                        else
+                        {
+                            // The reference sorts both lists by (error, index) and scans pairs.  Equivalent without a sort:
+                            // walk sector 0 in that order by repeated "next larger key" selection; for each entry the partner
+                            // is the smallest-key entry of sector 1 whose colour makes a legal differential pair.
+                            float current = blockBestTotalError;
+                            float lastErr = -1.0f;
+                            int lastIdx = -1;
+                            for (;;)
+                            {
+                                int i0 = -1;
+                                float e0 = 0.0f;
+                                uint32_t m0 = 0;
+                                for (int i = 0; i < kept[0]; i++)
+                                {
+                                    const size_t slot = (size_t)i * S.stride;
+                                    const float e = S.drsErr[slot];
+                                    const bool after = (e > lastErr) || (e == lastErr && i > lastIdx);
+                                    if (after && (i0 < 0 || e < e0))
+                                    {
+                                        i0 = i;
+                                        e0 = e;
+                                        m0 = S.drsMeta[slot];
+                                    }
+                                }
+                                if (i0 < 0)
+                                    break;
+                                lastErr = e0;
+                                lastIdx = i0;
+                                if (e0 >= current)
+                                    break;
+                                const float maxError1 = fsub(current, e0);
+                                if (maxError1 < bestDiffErrors[1])
+                                    break;
+                                // the scan of sector 1 stops at the first entry with error >= maxError1; before that the first legal one wins
+                                int j1 = -1;
+                                float e1 = 0.0f;
+                                uint32_t m1 = 0;
+                                for (int j = 0; j < kept[1]; j++)
+                                {
+                                    const size_t slot = (size_t)(kETCMaxAttempts + j) * S.stride;
+                                    const float e = S.drsErr[slot];
+                                    if (e < maxError1 && (j1 < 0 || e < e1))
+                                    {
+                                        const uint32_t m = S.drsMeta[slot];
+                                        if (etc_differential_legal((int)(m0 & 0x7fffu), (int)(m & 0x7fffu)))
+                                        {
+                                            j1 = j;
+                                            e1 = e;
+                                            m1 = m;
+                                        }
+                                    }
+                                }
+                                if (j1 >= 0)
+                                {
+                                    current = fadd(e0, e1);
+                                    winMeta[0] = (int)m0;
+                                    winMeta[1] = (int)m1;
+                                    winTotal = current;
+                                }
+                            }
+                        }
+                    }
+                    if (winMeta[0] >= 0)
+                    {
+                        bestIsThisMode = true;
+                        best.error = winTotal;
+                        bestFlip = flip;
+                        bestD = 1;
+                        for (int sector = 0; sector < 2; sector++)
+                        {
+                            bestColors[sector] = winMeta[sector] & 0x7fff;
+                            bestTables[sector] = (winMeta[sector] >> 15) & 7;
+                            // the selectors are a function of (colour, table); recomputed instead of stored per attempt
+                            etc_test_half_block<UNIFORM, STRIDE>(P, T, L, flip, sector, bestColors[sector], bestTables[sector], true, bestSelectors[sector]);
+                        }
+                    }
+                }
+            }
+        }
+
+        if (bestIsThisMode)
+        {
+            int colors[2][3];
+            for (int sector = 0; sector < 2; sector++)
+                for (int ch = 0; ch < 3; ch++)
+                    colors[sector][ch] = (bestColors[sector] >> (ch * 5)) & 31;
+            etc_emit_etc1(best, bestFlip, bestD, colors, bestTables, bestSelectors);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // CompressETC2Block without punch-through (ETC.cpp:1664-1887): chroma split, then planar, T, T, H, differential
+    template<bool UNIFORM, int STRIDE, class Vote>
+    CVTT_HD void etc2_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, Vote &vote, uint32_t out[2])
+    {
+        ETCBest best;
+        best.error = FLT_MAX;
+        best.hi = best.lo = 0;
+
+        etc_planar<UNIFORM, STRIDE>(P, L, best);
+
+        float chromaDelta[16][2];
+        if (UNIFORM)
+        {
+            int coords[16][2], centroid[2] = { 0, 0 };
+            for (int px = 0; px < 16; px++)
+            {
+                const F4 p = L.pw[px * STRIDE];
+                const int r = etc_px(p, 0), g = etc_px(p, 1), b = etc_px(p, 2);
+                coords[px][0] = r - b;
+                coords[px][1] = r - (g << 1) + b;
+                centroid[0] += coords[px][0];
+                centroid[1] += coords[px][1];
+            }
+            for (int px = 0; px < 16; px++)
+            {
+                chromaDelta[px][0] = (float)((coords[px][0] << 4) - centroid[0]);
+                chromaDelta[px][1] = fmul((float)((coords[px][1] << 4) - centroid[1]), 0.57735026918962576450914878050196f);
+            }
+        }
+        else
+        {
+            float coords[16][2], centroid[2] = { 0.0f, 0.0f };
+            for (int px = 0; px < 16; px++)
+            {
+                const F4 p = L.pw[px * STRIDE];
+                coords[px][0] = fadd(fadd(fmul(p.x, P.chromaAxis0[0]), fmul(p.y, P.chromaAxis0[1])), fmul(p.z, P.chromaAxis0[2]));
+                coords[px][1] = fadd(fadd(fmul(p.x, P.chromaAxis1[0]), fmul(p.y, P.chromaAxis1[1])), fmul(p.z, P.chromaAxis1[2]));
+            }
+            for (int px = 0; px < 16; px++)
+                for (int ch = 0; ch < 2; ch++)
+                    centroid[ch] = fadd(centroid[ch], coords[px][ch]);
+            for (int px = 0; px < 16; px++)
+                for (int ch = 0; ch < 2; ch++)
+                    chromaDelta[px][ch] = fsub(fmul(coords[px][ch], 16.0f), centroid[ch]);
+        }
+
+        float covXX = 0.0f, covYY = 0.0f, covXY = 0.0f;
+        for (int px = 0; px < 16; px++)
+        {
+            const float nx = chromaDelta[px][0], ny = chromaDelta[px][1];
+            covXX = fadd(covXX, fmul(nx, nx));
+            covYY = fadd(covYY, fmul(ny, ny));
+            covXY = fadd(covXY, fmul(nx, ny));
+        }
+        const float halfTrace = fmul(fadd(covXX, covYY), 0.5f);
+        const float det = fsub(fmul(covXX, covYY), fmul(covXY, covXY));
+        const float mm = sqrtf(sse_max(0.0f, fsub(fmul(halfTrace, halfTrace), det)));
+        const float ev = fadd(halfTrace, mm);
+        float dx = fadd(fsub(covYY, ev), covXY);
+        const float dy = fsub(0.0f, fadd(fsub(covXX, ev), covXY));
+        if (dx == 0.0f && dy == 0.0f)
+            dx = 1.0f;
+        uint32_t sectorMask = 0;
+        for (int px = 0; px < 16; px++)
+            if (fadd(fmul(chromaDelta[px][0], dx), fmul(chromaDelta[px][1], dy)) < 0.0f)
+                sectorMask |= 1u << px;
+
+        etc_t_mode<UNIFORM, STRIDE>(P, T, L, vote, sectorMask, best);
+        sectorMask ^= 0xffffu;
+        etc_t_mode<UNIFORM, STRIDE>(P, T, L, vote, sectorMask, best);
+        etc_h_mode<UNIFORM, STRIDE>(P, T, L, S, sectorMask, best);
+        etc_etc1<UNIFORM, 1, STRIDE>(P, T, L, S, best);
+
+        out[0] = best.hi;
+        out[1] = best.lo;
+    }
+
+    // CompressETC1Block, ETC.cpp:2112-2126
+    template<bool UNIFORM, int STRIDE>
+    CVTT_HD void etc1_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, uint32_t out[2])
+    {
+        ETCBest best;
+        best.error = FLT_MAX;
+        best.hi = best.lo = 0;
+        etc_etc1<UNIFORM, 0, STRIDE>(P, T, L, S, best);
+        out[0] = best.hi;
+        out[1] = best.lo;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // CompressETC2AlphaBlockInternal (ETC.cpp:1902-2085): 16 tables x 10 ranges x 2 multipliers, pure integer.
+    // pixels: 0..255 (8-bit alpha) or the shifted 11-bit range of CompressEACBlock.  Output: the 8 bytes as two
+    // big-endian words like the colour emitters.
+    CVTT_HD void etc_alpha_encode_block(const ETCTables &T, const int *pixels, bool is11Bit, bool isSigned, uint32_t out[2])
+    {
+        int minAlpha = is11Bit ? 2047 : 255, maxAlpha = 0;
+        for (int px = 0; px < 16; px++)
+        {
+            minAlpha = imin(minAlpha, pixels[px]);
+            maxAlpha = imax(maxAlpha, pixels[px]);
+        }
+        const int alphaSpan = maxAlpha - minAlpha, alphaSpanMidpointTimes2 = maxAlpha + minAlpha;
+
+        int bestTotalError = 0x7fffffff, bestTableIndex = 0, bestBaseCodeword = 0, bestMultiplier = 0;
+        uint32_t bestIndexes[2] = { 0, 0 };     // 16 x 3 bits in pixel order: pixels 0-9 in [0], 10-15 in [1]
+
+        for (int tableIndex = 0; tableIndex < 16; tableIndex++)
+            for (int r = 0; r < 10; r++)
+            {
+                const int subrange = r % 3, mainRange = r / 3;
+                const int maxOffset = T.alphaModifier[tableIndex][3 - mainRange - (subrange & 1)];
+                const int minOffset = -T.alphaModifier[tableIndex][3 - mainRange - ((subrange >> 1) & 1)] - 1;
+                const int offsetSpan = (maxOffset - minOffset) & 0xffff;
+
+                int minMultiplier = alphaSpan / offsetSpan;
+                if (is11Bit)
+                    minMultiplier = imin(minMultiplier, 112) & 120;
+                else
+                    minMultiplier = imax(imin(minMultiplier, 14), 1);
+
+                for (int multiplierOffset = 0; multiplierOffset < 2; multiplierOffset++)
+                {
+                    int multiplier = minMultiplier;
+                    if (is11Bit)
+                    {
+                        if (multiplierOffset == 1)
+                            multiplier += 8;
+                        else
+                            multiplier = imax(multiplier, 1);
+                    }
+                    else if (multiplierOffset == 1)
+                        multiplier += 1;
+
+                    const int multipliedMinOffset = wrap_s16(multiplier * minOffset);
+                    const int multipliedMaxOffset = wrap_s16(multiplier * maxOffset);
+                    int unclampedBaseAlphaTimes2 = wrap_s16(alphaSpanMidpointTimes2 - multipliedMaxOffset - multipliedMinOffset);
+
+                    int baseAlpha;
+                    if (is11Bit)
+                    {
+                        if (isSigned)
+                            unclampedBaseAlphaTimes2 = wrap_s16(unclampedBaseAlphaTimes2 + 8);
+                        const int minBaseAlphaTimes2 = isSigned ? 16 : 0;
+                        const int clamped = imin(imax(unclampedBaseAlphaTimes2, minBaseAlphaTimes2), 4095);
+                        baseAlpha = (clamped >> 1) & 2040;
+                        if (!isSigned)
+                            baseAlpha += 4;
+                    }
+                    else
+                    {
+                        const int clamped = imin(imax(unclampedBaseAlphaTimes2, 0), 510);
+                        baseAlpha = (clamped + 1) >> 1;
+                    }
+
+                    uint32_t indexes[2] = { 0, 0 };
+                    int totalError = 0;
+                    for (int px = 0; px < 16; px++)
+                    {
+                        // QuantizeETC2Alpha, ETC.cpp:2366-2411
+                        const int offset = wrap_s16(pixels[px] - baseAlpha);
+                        const int aboutReflectorTimes2 = wrap_s16(offset + offset + multiplier);
+                        const int absTimes2 = (aboutReflectorTimes2 < 0 ? -aboutReflectorTimes2 : aboutReflectorTimes2) & 0xffff;
+                        int lookup = (absTimes2 >> 1) / multiplier;
+                        if (lookup >= 13)
+                            lookup = 12;
+                        const int positiveIndex = T.alphaRounding[tableIndex][lookup];
+                        const int positiveOffset = T.alphaModifier[tableIndex][positiveIndex];
+                        const int signBits = aboutReflectorTimes2 >> 15;           // 0 or -1
+                        const int offsetUnmultiplied = wrap_s16(positiveOffset ^ signBits);
+                        const int quantizedOffset = wrap_s16(offsetUnmultiplied * multiplier);
+                        const int offsetValue = wrap_s16(baseAlpha + quantizedOffset);
+                        int q;
+                        if (is11Bit)
+                            q = imin(2047, imax(isSigned ? 1 : 0, offsetValue));
+                        else
+                            q = imin(255, imax(0, offsetValue));
+                        const int index = positiveIndex + 4 - (signBits & 4);
+                        if (px < 10)
+                            indexes[0] |= (uint32_t)index << (3 * px);
+                        else
+                            indexes[1] |= (uint32_t)index << (3 * (px - 10));
+                        const int delta = q - pixels[px];
+                        totalError += is11Bit ? (delta * delta) : ((delta * delta) & 0xffff);
+                    }
+                    if (totalError < bestTotalError)
+                    {
+                        bestTotalError = totalError;
+                        bestTableIndex = tableIndex;
+                        bestBaseCodeword = baseAlpha;
+                        bestMultiplier = multiplier;
+                        bestIndexes[0] = indexes[0];
+                        bestIndexes[1] = indexes[1];
+                    }
+                }
+            }
+
+        if (is11Bit)
+        {
+            bestMultiplier >>= 3;
+            if (isSigned)
+                bestBaseCodeword ^= 0x80;
+        }
+
+        // byte 0: base codeword, byte 1: multiplier << 4 | table, then the sixteen 3-bit indexes, column-major, MSB first
+        uint64_t bits = 0;
+        for (int s = 0; s < 16; s++)
+        {
+            const int px = (s & 3) * 4 + (s >> 2);      // indexes[pixelSelectorOrder[px]] = bestIndexes[px]
+            const uint32_t index = (px < 10) ? ((bestIndexes[0] >> (3 * px)) & 7u) : ((bestIndexes[1] >> (3 * (px - 10))) & 7u);
+            bits = (bits << 3) | index;
+        }
+        const uint32_t b0 = (uint32_t)bestBaseCodeword & 0xffu, b1 = (uint32_t)((bestMultiplier << 4) | bestTableIndex) & 0xffu;
+        out[0] = (b0 << 24) | (b1 << 16) | (uint32_t)((bits >> 32) & 0xffffu);
+        out[1] = (uint32_t)(bits & 0xffffffffu);
+    }
+
+    // the byte order of the block: both words are written most significant byte first
+    CVTT_HD uint32_t etc_bswap(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+}

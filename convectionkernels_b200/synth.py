@@ -155,3 +155,14 @@ def random_blocks_f16(n, seed=0, signed=False):
         b[i, :, :3] = px
         b[i, :, 3] = 1
     return np.ascontiguousarray(b.astype(np.float16).view(np.int16))
+
+
+def random_blocks_s16(n, seed=0, signed=False):
+    """n PixelBlockScalarS16 blocks (int16 [16]) for EncodeETC2Alpha11: full-range noise, quantised steps, narrow ranges and
+    out-of-range values (the encoder clamps to 0..2047 / -1023..1023)."""
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-1100 if signed else -50, 2100, size=(n, 16)).astype(np.int16)
+    b[::3] = (b[::3] // 64) * 8
+    k = len(b[1::5])
+    b[1::5] = b[1::5, :1] + rng.integers(-20, 20, size=(k, 16))
+    return np.ascontiguousarray(b)

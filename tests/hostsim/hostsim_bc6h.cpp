@@ -1,57 +1,17 @@
 // TEST INFRASTRUCTURE ONLY.  CPU build of the BC6H per-thread device code (convectionkernels_b200/csrc/bc6h_core.cuh).
 // The eight lanes of a reference group run as eight host threads; the group votes of the kernel (ballots over an
 // 8-lane segment) become a spin barrier with an OR reduction.  Not part of the product library.
-#include <atomic>
 #include <thread>
 #include <vector>
 #include <xmmintrin.h>
 
 #include "../../convectionkernels_b200/csrc/bc6h_host.h"
+#include "host_vote.h"
 
 using namespace cvttb200;
 
 namespace
 {
-    struct GroupShared
-    {
-        std::atomic<int> count{0};
-        std::atomic<int> sense{0};
-        std::atomic<unsigned> bits[2];
-        GroupShared() { bits[0] = 0; bits[1] = 0; }
-    };
-
-    struct HostVote
-    {
-        GroupShared *g;
-        int localSense = 0;
-        int phase = 0;
-
-        bool any(bool x)
-        {
-            const int slot = phase & 1;
-            phase++;
-            localSense ^= 1;
-            if (x)
-                g->bits[slot].fetch_or(1u);
-            if (g->count.fetch_add(1) == 7)
-            {
-                g->bits[slot ^ 1].store(0u);
-                g->count.store(0);
-                g->sense.store(localSense);
-            }
-            else
-            {
-                int spins = 0;
-                while (g->sense.load() != localSense)
-                    if (++spins > 64)
-                        std::this_thread::yield();
-            }
-            return g->bits[slot].load() != 0;
-        }
-        bool all(bool x) { return !any(!x); }
-        bool warp_any(bool x) { return x; }      // the argument is uniform over the group
-    };
-
     template<bool SIGNED, bool FAST>
     void run_lane(int lane, GroupShared *shared, const BC6HParams *P, const int16_t *blocks, size_t nBlocks, uint8_t *out)
     {

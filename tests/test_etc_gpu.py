@@ -1,0 +1,87 @@
+"""GPU parity tests for ETC1 / ETC2 / EAC (run with -m gpu on the B200 box): the CUDA path through the C ABI against the golden
+vectors and against the unmodified reference on the same host (oracle/_ref).  Bit-exact is the bar."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, first_mismatch
+from convectionkernels_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt_bytes(o):
+    return np.frombuffer(bytes(memoryview(o)), np.uint8)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.init(0)
+
+
+@pytest.mark.parametrize("name", golden_names("etc") + golden_names("eac"))
+def test_golden(name):
+    g = load_golden(name)
+    got = api.encode(str(g["fmt"]), g["blocks"], g["options"])
+    assert (got == g["expected"]).all(), first_mismatch(g["expected"], got)
+
+
+@pytest.mark.parametrize("fmt,flags", [("ETC2_RGBA", None), ("ETC2", api.Flags.Default | 0x200), ("ETC1", None), ("ETC1", api.Flags.Default | 0x200),
+                                       ("ETC2_ALPHA", None)])
+def test_random_blocks_against_reference(reference, fmt, flags):
+    blocks = synth.random_blocks_rgba8(8192 + 24, seed=101)        # ragged last warp
+    o = api.Options()
+    if flags is not None:
+        o.flags = flags
+    want = reference.encode(fmt, blocks, _opt_bytes(o), threads=0)
+    got = api.encode(fmt, blocks, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+@pytest.mark.parametrize("signed", [False, True])
+def test_eac_r11_against_reference(reference, signed):
+    blocks = synth.random_blocks_s16(65536, seed=7, signed=signed)
+    o = api.Options()
+    want = reference.encode("EAC_R11S" if signed else "EAC_R11U", blocks, _opt_bytes(o), threads=0)
+    got = api.EncodeETC2Alpha11(blocks, signed, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_weights_and_image_content_against_reference(reference):
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(512, 512))          # 16384 blocks of the config-4 image
+    o = api.Options()
+    o.redWeight, o.greenWeight, o.blueWeight = 1.0, 0.5, 0.25
+    want = reference.encode("ETC2_RGBA", blocks, _opt_bytes(o), threads=0)
+    got = api.EncodeETC2RGBA(blocks, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_unsupported_variants_fail_loudly():
+    blocks = synth.random_blocks_rgba8(8, seed=1)
+    o = api.Options()
+    with pytest.raises(api.CvttError) as e:
+        api.encode("ETC2_PUNCHTHROUGH", blocks, o)
+    assert e.value.status == -2
+    o.flags |= 0x400
+    with pytest.raises(api.CvttError) as e:
+        api.encode("ETC2", blocks, o)
+    assert e.value.status == -2
+
+
+def test_full_size_properties(reference):
+    """BASELINE.json configs[3] size (4096x4096 RGBA8 -> ETC2 RGBA): determinism, sub-range independence at group granularity, and a
+    sample of groups against the reference."""
+    import torch
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(4096, 4096))
+    o = api.Options()
+    d = torch.from_numpy(blocks).cuda()
+    full = api.EncodeETC2RGBA(d, o).cpu().numpy()
+    again = api.EncodeETC2RGBA(d, o).cpu().numpy()
+    assert (full == again).all()
+    for first, n in ((8 * 1001, 8 * 37), (524288, 4096)):
+        part = api.EncodeETC2RGBA(blocks[first:first + n], o)
+        assert (part == full[first:first + n]).all()
+    rng = np.random.default_rng(4)
+    groups = rng.choice(1048576 // 8, size=2048, replace=False)
+    idx = (groups[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    want = reference.encode("ETC2_RGBA", blocks[idx], _opt_bytes(o), threads=0)
+    assert (full[idx] == want).all(), first_mismatch(want, full[idx])

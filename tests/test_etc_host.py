@@ -1,0 +1,50 @@
+"""CPU tests of the ETC device logic: convectionkernels_b200/csrc/etc_core.cuh compiled for the CPU (tests/hostsim, test-only; eight
+threads per reference group, the kernel's segment maximum becomes a barrier reduction) against the golden vectors recorded from the
+unmodified reference."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, first_mismatch
+
+KIND = {"ETC1": 0, "ETC2": 1, "ETC2_RGBA": 2, "ETC2_ALPHA": 3, "EAC_R11U": 4, "EAC_R11S": 5}
+
+
+@pytest.fixture(scope="module")
+def hostsim_etc():
+    out = os.path.join(ROOT, "tests", "_build", "libcvtt_hostsim_etc.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    csrc = os.path.join(ROOT, "convectionkernels_b200", "csrc")
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-pthread", "-w", "-I", csrc, "-o", out,
+                           os.path.join(ROOT, "tests", "hostsim", "hostsim_etc.cpp"), os.path.join(csrc, "etc_host.cpp")])
+    H = ctypes.CDLL(out)
+    H.hostsim_encode_etc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    return H
+
+
+@pytest.mark.parametrize("name", golden_names("etc") + golden_names("eac"))
+def test_etc_device_logic_on_cpu_matches_golden(hostsim_etc, name):
+    g = load_golden(name)
+    blocks = np.ascontiguousarray(g["blocks"])
+    n = blocks.shape[0]
+    out = np.zeros_like(g["expected"])
+    opt = np.ascontiguousarray(g["options"])
+    rc = hostsim_etc.hostsim_encode_etc(KIND[str(g["fmt"])], blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data)
+    assert rc == 0
+    assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)
+
+
+def test_t_mode_group_coupling(hostsim_etc, reference):
+    """the T-mode candidate list depends on the other blocks of the group (never-written slot = colour 0)"""
+    from convectionkernels_b200 import api, synth
+    base = synth.random_blocks_rgba8(64, seed=23)
+    flat = np.broadcast_to(np.array([200, 30, 30, 255], np.uint8), (1, 16, 4)).copy()
+    blocks = np.concatenate([np.concatenate([flat if k % 2 else base[k:k + 1], base[8 * (k % 8):8 * (k % 8) + 7]]) for k in range(16)])
+    opt = np.frombuffer(bytes(memoryview(api.Options())), np.uint8)
+    want = reference.encode("ETC2", blocks, opt)
+    out = np.zeros_like(want)
+    assert hostsim_etc.hostsim_encode_etc(1, blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data) == 0
+    assert (out == want).all(), first_mismatch(want, out)

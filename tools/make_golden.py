@@ -65,3 +65,14 @@ save("bc6hs_random_fast_uniform", "BC6HS", hs, options(flags=0x348))
 save("bc6hu_random_rounds22", "BC6HU", hu, options(refine_bc6h=2, seeds=2))
 save("bc6hs_random_rounds13_weights", "BC6HS", hs, options(refine_bc6h=1, seeds=3, weights=(1.0, 0.5, 2.0, 1.0)))
 save("bc6hu_ramp", "BC6HU", ramp, options())
+
+# config 4 content: ETC2 RGBA and the other ETC / EAC entry points (no reciprocal instruction on these paths)
+save("etc2rgba_random", "ETC2_RGBA", rb, options())
+save("etc2rgba_mixed", "ETC2_RGBA", mixed, options())
+save("etc2_random_uniform", "ETC2", rb, options(flags=0x308))
+save("etc2_gradient", "ETC2", grad, options())
+save("etc1_random", "ETC1", rb, options())
+save("etc1_mixed_uniform", "ETC1", mixed[:256], options(flags=0x308))
+save("etc2alpha_mixed", "ETC2_ALPHA", mixed, options())
+save("eacr11u_random", "EAC_R11U", synth.random_blocks_s16(256, seed=41), options())
+save("eacr11s_random", "EAC_R11S", synth.random_blocks_s16(256, seed=42, signed=True), options())
