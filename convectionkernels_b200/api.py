@@ -259,3 +259,38 @@ def EncodeETC2Alpha11(pBlocks, isSigned, options, out=None):
     """cvtt::Kernels::EncodeETC2Alpha11, reference ConvectionKernels.h:259 / ConvectionKernels_API.cpp:257-268.  pBlocks:
     PixelBlockScalarS16 (int16 [n][16])"""
     return encode("EAC_R11S" if isSigned else "EAC_R11U", pBlocks, options, None, out)
+
+
+def EncodeBC1(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC1, reference ConvectionKernels.h:243 / ConvectionKernels_API.cpp:86-99"""
+    return encode("BC1", pBlocks, options, None, out)
+
+
+def EncodeBC2(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC2, reference ConvectionKernels.h:244 / ConvectionKernels_API.cpp:101-115"""
+    return encode("BC2", pBlocks, options, None, out)
+
+
+def EncodeBC3(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC3, reference ConvectionKernels.h:245 / ConvectionKernels_API.cpp:117-131"""
+    return encode("BC3", pBlocks, options, None, out)
+
+
+def EncodeBC4U(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC4U, reference ConvectionKernels.h:246 / ConvectionKernels_API.cpp:133-146"""
+    return encode("BC4U", pBlocks, options, None, out)
+
+
+def EncodeBC4S(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC4S (PixelBlockS8 input), reference ConvectionKernels.h:247 / ConvectionKernels_API.cpp:148-164"""
+    return encode("BC4S", pBlocks, options, None, out)
+
+
+def EncodeBC5U(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC5U, reference ConvectionKernels.h:248 / ConvectionKernels_API.cpp:166-180"""
+    return encode("BC5U", pBlocks, options, None, out)
+
+
+def EncodeBC5S(pBlocks, options, out=None):
+    """cvtt::Kernels::EncodeBC5S (PixelBlockS8 input), reference ConvectionKernels.h:249 / ConvectionKernels_API.cpp:182-199"""
+    return encode("BC5S", pBlocks, options, None, out)

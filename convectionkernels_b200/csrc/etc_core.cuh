@@ -76,8 +76,6 @@ namespace cvttb200
     };
 
     CVTT_HD int etc_px(const F4 &p, int ch) { return (int)((as_uint(p.w) >> (8 * ch)) & 0xffu); }
-    CVTT_HD int imin(int a, int b) { return a < b ? a : b; }
-    CVTT_HD int imax(int a, int b) { return a > b ? a : b; }
 
     // ComputeErrorUniform (ETC.cpp:59-71) / ComputeErrorWeighted (:73-80).  cw = (float)colour * weight per channel.
     template<bool UNIFORM>

@@ -15,7 +15,7 @@ os.makedirs(OUT, exist_ok=True)
 rcp = R.rcp_table()
 
 
-def options(flags=None, refine=None, weights=None, refine_bc6h=None, seeds=None):
+def options(flags=None, refine=None, weights=None, refine_bc6h=None, seeds=None, refine_s3tc=None, refine_iic=None):
     o = R.default_options().copy()
     if flags is not None:
         o[0:4] = np.frombuffer(struct.pack("<I", flags), np.uint8)
@@ -76,3 +76,16 @@ save("etc1_mixed_uniform", "ETC1", mixed[:256], options(flags=0x308))
 save("etc2alpha_mixed", "ETC2_ALPHA", mixed, options())
 save("eacr11u_random", "EAC_R11U", synth.random_blocks_s16(256, seed=41), options())
 save("eacr11s_random", "EAC_R11S", synth.random_blocks_s16(256, seed=42, signed=True), options())
+
+# BC1-BC5 (config 1 content and the other S3TC entry points)
+rba = rb.copy()
+rba[::2, :, 3] = np.random.default_rng(5).integers(0, 256, size=rba[::2, :, 3].shape)
+save("bc1_random_alpha", "BC1", rba, options())
+save("bc1_random_noparanoid_refine3", "BC1", rba, options(flags=0x008, refine_s3tc=3))
+save("bc2_random", "BC2", rba, options())
+save("bc3_mixed", "BC3", mixed[:256], options())
+save("bc3_random_uniform", "BC3", rba, options(flags=0x308))
+save("bc4u_random", "BC4U", rba, options())
+save("bc4s_random", "BC4S", rba, options())
+save("bc5u_random_seeds2", "BC5U", rba, options(seeds=2, refine_iic=3))
+save("bc5s_random", "BC5S", rba, options())
