@@ -27,12 +27,46 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-WORKLOAD = "EncodeBC7 plan=FromQuality(100) Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU"
 SIDE = 4096
 BLOCKS = (SIDE // 4) * (SIDE // 4)
-METRIC = "Mblocks/s (4x4) BC7 q100"
-ALGO_BYTES_PER_BLOCK = 64 + 16
 CPU_SAMPLE_BLOCKS = 262144               # first 1024 rows of the texture
+
+# The headline (default) is BASELINE.json configs[1], BC7.  --format selects one of the other single-GPU configurations
+# (configs[2] BC6HU, configs[3] ETC2_RGBA) or any other implemented format; the JSON contract is the same.
+# name -> (workload text, metric, input kind, bytes read per block, bytes written per block, dominant kernel)
+FORMAT_CONFIGS = {
+    "BC7": ("EncodeBC7 plan=FromQuality(100) Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) BC7 q100", "rgba8", 64, 16, "bc7_encode_kernel<true>"),
+    "BC6HU": ("EncodeBC6HU Options=default (slow indexing) 4096x4096 synthetic F16 HDR ramp (1048576 blocks) per GPU", "Mblocks/s (4x4) BC6HU", "f16", 128, 16, "bc6h_encode_kernel<false,false>"),
+    "BC6HS": ("EncodeBC6HS Options=default 4096x4096 synthetic signed F16 HDR ramp per GPU", "Mblocks/s (4x4) BC6HS", "f16s", 128, 16, "bc6h_encode_kernel<true,false>"),
+    "ETC2_RGBA": ("EncodeETC2RGBA Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) ETC2 RGBA", "rgba8", 64, 16, "etc_encode_kernel<2,false>"),
+    "ETC2": ("EncodeETC2 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC2 RGB", "rgba8", 64, 8, "etc_encode_kernel<1,false>"),
+    "ETC1": ("EncodeETC1 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC1", "rgba8", 64, 8, "etc_encode_kernel<0,false>"),
+    "ETC2_ALPHA": ("EncodeETC2Alpha 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) EAC alpha", "rgba8", 64, 8, "eac_encode_kernel<0>"),
+    "BC1": ("EncodeBC1 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC1", "rgba8", 64, 8, "s3tc_encode_kernel<BC1>"),
+    "BC2": ("EncodeBC2 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC2", "rgba8", 64, 16, "s3tc_encode_kernel<BC2>"),
+    "BC3": ("EncodeBC3 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC3", "rgba8", 64, 16, "s3tc_encode_kernel<BC3>"),
+    "BC4U": ("EncodeBC4U Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC4U", "rgba8", 64, 8, "s3tc_encode_kernel<BC4U>"),
+    "BC5U": ("EncodeBC5U Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC5U", "rgba8", 64, 16, "s3tc_encode_kernel<BC5U>"),
+}
+FORMAT = "BC7"
+WORKLOAD, METRIC, INPUT_KIND, IN_BYTES, OUT_BYTES, KERNEL_NAME = FORMAT_CONFIGS[FORMAT]
+ALGO_BYTES_PER_BLOCK = IN_BYTES + OUT_BYTES
+
+
+def select_format(name):
+    global FORMAT, WORKLOAD, METRIC, INPUT_KIND, IN_BYTES, OUT_BYTES, KERNEL_NAME, ALGO_BYTES_PER_BLOCK
+    FORMAT = name
+    WORKLOAD, METRIC, INPUT_KIND, IN_BYTES, OUT_BYTES, KERNEL_NAME = FORMAT_CONFIGS[name]
+    ALGO_BYTES_PER_BLOCK = IN_BYTES + OUT_BYTES
+
+
+def synthetic_blocks(seed_offset=0):
+    from convectionkernels_b200 import synth
+    if INPUT_KIND == "f16":
+        return synth.image_to_blocks(synth.hdr_ramp_f16(SIDE, SIDE, seed=99 + seed_offset))
+    if INPUT_KIND == "f16s":
+        return synth.image_to_blocks(synth.hdr_ramp_f16(SIDE, SIDE, seed=99 + seed_offset, signed=True))
+    return synth.image_to_blocks(synth.mixed_rgba8(SIDE, SIDE, seed=1234 + seed_offset))
 
 
 def measured_peak():
@@ -46,7 +80,8 @@ def measured_peak():
 def profile_constants():
     """dram traffic per launch and issue-slot utilisation from the committed ncu capture (profiles/), if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "bc7_kernel_ncu_summary.json")) as f:
+        name = "bc7_kernel_ncu_summary.json" if FORMAT == "BC7" else FORMAT.lower() + "_kernel_ncu_summary.json"
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             return json.load(f)
     except Exception:
         return {}
@@ -96,17 +131,16 @@ def reference_arm(args):
     if rank != 0:
         return
     from oracle.loader import Reference
-    from convectionkernels_b200 import synth
     R = Reference()
     threads = R.hardware_threads()
-    sample_blocks = 131072
-    blocks = synth.image_to_blocks(synth.mixed_rgba8(SIDE, SIDE))[:sample_blocks]
-    opt, plan = R.default_options(), R.plan_from_quality(100)
+    sample_blocks = 131072 if FORMAT in ("BC7", "BC6HU", "BC6HS") else 524288
+    blocks = synthetic_blocks()[:sample_blocks]
+    opt, plan = R.default_options(), (R.plan_from_quality(100) if FORMAT == "BC7" else None)
     for _ in range(args.warmup):
-        R.encode("BC7", blocks[:16384], opt, plan, threads=0)
+        R.encode(FORMAT, blocks[:16384], opt, plan, threads=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        R.encode("BC7", blocks, opt, plan, threads=0)
+        R.encode(FORMAT, blocks, opt, plan, threads=0)
     dt = time.perf_counter() - t0
     v = sample_blocks * args.steps / dt / 1e6
     print(json.dumps({
@@ -125,8 +159,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--format", default="BC7", choices=sorted(FORMAT_CONFIGS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    select_format(args.format)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -149,21 +185,23 @@ def main():
     api.init(local_rank)
 
     # synthetic input: each rank owns one whole texture (weak scaling); pinned host copy for the e2e leg
-    blocks_np = synth.image_to_blocks(synth.mixed_rgba8(SIDE, SIDE, seed=1234 + rank))
+    blocks_np = synthetic_blocks(rank)
     host_in = torch.from_numpy(blocks_np.reshape(-1)).pin_memory()
-    host_out = torch.empty(BLOCKS * 16, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty(BLOCKS * OUT_BYTES, dtype=torch.uint8).pin_memory()
     d_in = host_in.to(dev)
-    d_out = torch.empty((BLOCKS, 16), dtype=torch.uint8, device=dev)
+    d_out = torch.empty((BLOCKS, OUT_BYTES), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     opt = api.Options()
-    plan = api.BC7EncodingPlan()
-    api.ConfigureBC7EncodingPlanFromQuality(plan, 100)
+    plan = None
+    if FORMAT == "BC7":
+        plan = api.BC7EncodingPlan()
+        api.ConfigureBC7EncodingPlanFromQuality(plan, 100)
     total_blocks = BLOCKS * world
 
     def step():
-        api.encode("BC7", d_in, opt, plan, out=d_out)
+        api.encode(FORMAT, d_in, opt, plan, out=d_out)
         if distributed:
-            return sharding.gather_encoded(d_out, total_blocks, 16, dst=0)
+            return sharding.gather_encoded(d_out, total_blocks, OUT_BYTES, dst=0)
         return d_out
 
     def barrier():
@@ -189,10 +227,10 @@ def main():
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_start.record()
         k0.record()
-        api.encode("BC7", d_in, opt, plan, out=d_out)
+        api.encode(FORMAT, d_in, opt, plan, out=d_out)
         k1.record()
         if distributed:
-            sharding.gather_encoded(d_out, total_blocks, 16, dst=0)
+            sharding.gather_encoded(d_out, total_blocks, OUT_BYTES, dst=0)
         e_end.record()
         torch.cuda.synchronize()
         step_ms_total += e_start.elapsed_time(e_end)
@@ -210,13 +248,13 @@ def main():
     kernel_ms = float(np.mean(kernel_events))
 
     # ---- end-to-end leg: public call with host buffers, copies inside the timed region ----------------------
-    host_out_np = host_out.numpy().reshape(BLOCKS, 16)
+    host_out_np = host_out.numpy().reshape(BLOCKS, OUT_BYTES)
     host_in_np = host_in.numpy()
-    api.encode("BC7", host_in_np, opt, plan, out=host_out_np)
+    api.encode(FORMAT, host_in_np, opt, plan, out=host_out_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        api.encode("BC7", host_in_np, opt, plan, out=host_out_np)       # returns when host_out is complete
+        api.encode(FORMAT, host_in_np, opt, plan, out=host_out_np)       # returns when host_out is complete
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -231,9 +269,9 @@ def main():
         prof = profile_constants()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
-                    "kernel": "bc7_encode_kernel<true>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BLOCK * BLOCKS,
-                    "note": "compute-bound path (~5e6 instructions per 80 bytes); see issue_slot_frac_ncu and DESIGN.md",
-                    "issue_slot_frac_ncu": prof.get("issue_slot_frac")}
+                    "kernel": KERNEL_NAME, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BLOCK * BLOCKS,
+                    "note": "compute-bound path (millions of instructions per block against <= 144 bytes); the binding unit is the FP32 pipe / issue slots, see fma_pipe_frac_ncu, issue_slot_frac_ncu and DESIGN.md",
+                    "issue_slot_frac_ncu": prof.get("issue_slot_frac"), "fma_pipe_frac_ncu": prof.get("fma_pipe_frac")}
 
         # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same texture
         cpu = None
@@ -242,10 +280,10 @@ def main():
             R = Reference()
             threads = R.hardware_threads()
             sample = blocks_np[:CPU_SAMPLE_BLOCKS]
-            ob, pb = np.frombuffer(bytes(memoryview(opt)), np.uint8), np.frombuffer(plan.tobytes(), np.uint8)
-            R.encode("BC7", sample[:8192], ob, pb, threads=0)
+            ob, pb = np.frombuffer(bytes(memoryview(opt)), np.uint8), (np.frombuffer(plan.tobytes(), np.uint8) if plan is not None else None)
+            R.encode(FORMAT, sample[:8192], ob, pb, threads=0)
             t0 = time.perf_counter()
-            ref_out = R.encode("BC7", sample, ob, pb, threads=0)
+            ref_out = R.encode(FORMAT, sample, ob, pb, threads=0)
             dt = time.perf_counter() - t0
             cpu = {"value": CPU_SAMPLE_BLOCKS / dt / 1e6, "unit": "Mblocks/s", "cores": threads, "kind": "reference",
                    "sample": "first %d blocks (1024 rows) of the texture, %d threads, %.1f s" % (CPU_SAMPLE_BLOCKS, threads, dt),
@@ -258,9 +296,9 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "blocks_per_gpu": BLOCKS, "parallelism": "block-range shard x%d, NCCL gather of encoded ranges" % world if distributed else "single GPU",
-                       "l2": "256 MiB flush write between timed iterations", "plan": "ConfigureBC7EncodingPlanFromQuality(100)", "flags": "Default (BC7_FastIndexing|S3TC_Paranoid)"},
+                       "l2": "256 MiB flush write between timed iterations", "plan": "ConfigureBC7EncodingPlanFromQuality(100)" if FORMAT == "BC7" else None, "flags": "Default (BC7_FastIndexing|S3TC_Paranoid)", "format": FORMAT},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "Mblocks/s", "h2d_bytes_per_step": BLOCKS * 64, "d2h_bytes_per_step": BLOCKS * 16,
+            "e2e": {"value": e2e_value, "unit": "Mblocks/s", "h2d_bytes_per_step": BLOCKS * IN_BYTES, "d2h_bytes_per_step": BLOCKS * OUT_BYTES,
                     "host_equals_device_result": same},
             "gpu_launches": int(launches),
             "roofline": roofline,

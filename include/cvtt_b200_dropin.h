@@ -4,8 +4,9 @@
 // A caller written against the reference replaces
 //     #include "ConvectionKernels.h"        + link ConvectionKernels.lib
 // by  #include "cvtt_b200_dropin.h"         + link -lcvtt_b200
-// and keeps calling cvtt::Kernels::EncodeBC7(pBC, pBlocks, options, plan) with 8 blocks per call.  For throughput,
-// call cvtt::Kernels::B200::Encode* with a whole image's blocks instead (same result, one launch).
+// and keeps calling cvtt::Kernels::EncodeBC7 / EncodeBC1..5 / EncodeBC6H* / EncodeETC* with 8 blocks per call.  For
+// throughput, call cvtt::Kernels::B200::Encode with a whole image's blocks instead (same result, one launch).  The decoders
+// (DecodeBC7 / DecodeBC6H*) are CPU code in the reference and are not part of this library.
 //
 // Types derive from the C PODs, so their layout is the reference's by construction (checked by static_assert below).
 // Error behaviour: the reference's functions return void and only assert; this shim prints cvttb200_last_error() and
@@ -58,8 +59,27 @@ namespace cvtt
 
     static_assert(sizeof(Options) == 44 && sizeof(BC7EncodingPlan) == 808 && sizeof(BC7FineTuningParams) == 285, "layout must match the reference");
 
+    // The reference's ETC compression data is CPU scratch memory (ConvectionKernels_ETC.h:36-78).  The device equivalent is
+    // allocated by the library per call, so these objects only keep the reference's allocation protocol alive: Alloc* calls
+    // allocFunc(context, size) once and returns the pointer, Release* hands it back to freeFunc(context, ptr, size).
+    class ETC2CompressionData
+    {
+    public:
+        void *m_context;
+        Options m_options;
+    };
+
+    class ETC1CompressionData
+    {
+    public:
+        void *m_context;
+    };
+
     namespace Kernels
     {
+        typedef void *allocFunc_t(void *context, size_t size);
+        typedef void freeFunc_t(void *context, void *ptr, size_t size);
+
         namespace B200
         {
             inline void Check(int status, const char *what)
@@ -71,16 +91,72 @@ namespace cvtt
                 }
             }
 
-            // whole-image entry points: numBlocks is any multiple of NumParallelBlocks; pointers may be host or device memory
+            // whole-image entry point: numBlocks is any multiple of NumParallelBlocks; pointers may be host or device memory.
+            // format is a cvttb200_format; plan is only read for CVTTB200_BC7.
+            inline void Encode(int format, uint8_t *pBC, const void *pBlocks, size_t numBlocks, const Options &options, const BC7EncodingPlan *encodingPlan = NULL, void *cudaStream = NULL)
+            {
+                Check(cvttb200_encode(format, pBlocks, numBlocks, pBC, &options, encodingPlan, cudaStream), "Encode");
+            }
+
             inline void EncodeBC7(uint8_t *pBC, const PixelBlockU8 *pBlocks, size_t numBlocks, const Options &options, const BC7EncodingPlan &encodingPlan, void *cudaStream = NULL)
             {
                 Check(cvttb200_encode(CVTTB200_BC7, pBlocks, numBlocks, pBC, &options, &encodingPlan, cudaStream), "EncodeBC7");
             }
         }
 
+        // The reference's entry points (ConvectionKernels.h:242-259): NumParallelBlocks blocks in, NumParallelBlocks blocks out.
+        inline void EncodeBC1(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC1, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC2(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC2, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC3(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC3, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC4U(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC4U, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC4S(uint8_t *pBC, const PixelBlockS8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC4S, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC5U(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC5U, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC5S(uint8_t *pBC, const PixelBlockS8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC5S, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC6HU(uint8_t *pBC, const PixelBlockF16 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC6HU, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeBC6HS(uint8_t *pBC, const PixelBlockF16 *pBlocks, const Options &options) { B200::Encode(CVTTB200_BC6HS, pBC, pBlocks, NumParallelBlocks, options); }
         inline void EncodeBC7(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, const BC7EncodingPlan &encodingPlan)
         {
             B200::EncodeBC7(pBC, pBlocks, NumParallelBlocks, options, encodingPlan);
+        }
+        inline void EncodeETC1(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC1CompressionData *) { B200::Encode(CVTTB200_ETC1, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2RGBA(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2_RGBA, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2PunchthroughAlpha(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2_PUNCHTHROUGH, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2Alpha(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_ETC2_ALPHA, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2Alpha11(uint8_t *pBC, const PixelBlockScalarS16 *pBlocks, bool isSigned, const Options &options)
+        {
+            B200::Encode(isSigned ? CVTTB200_EAC_R11S : CVTTB200_EAC_R11U, pBC, pBlocks, NumParallelBlocks, options);
+        }
+
+        inline ETC2CompressionData *AllocETC2Data(allocFunc_t allocFunc, void *context, const Options &options)
+        {
+            void *buffer = allocFunc(context, sizeof(ETC2CompressionData));
+            if (!buffer)
+                return NULL;
+            ETC2CompressionData *data = static_cast<ETC2CompressionData *>(buffer);
+            data->m_context = context;
+            data->m_options = options;
+            return data;
+        }
+
+        inline void ReleaseETC2Data(ETC2CompressionData *compressionData, freeFunc_t freeFunc)
+        {
+            freeFunc(compressionData->m_context, compressionData, sizeof(ETC2CompressionData));
+        }
+
+        inline ETC1CompressionData *AllocETC1Data(allocFunc_t allocFunc, void *context)
+        {
+            void *buffer = allocFunc(context, sizeof(ETC1CompressionData));
+            if (!buffer)
+                return NULL;
+            ETC1CompressionData *data = static_cast<ETC1CompressionData *>(buffer);
+            data->m_context = context;
+            return data;
+        }
+
+        inline void ReleaseETC1Data(ETC1CompressionData *compressionData, freeFunc_t freeFunc)
+        {
+            freeFunc(compressionData->m_context, compressionData, sizeof(ETC1CompressionData));
         }
 
         inline void ConfigureBC7EncodingPlanFromQuality(BC7EncodingPlan &encodingPlan, int quality)

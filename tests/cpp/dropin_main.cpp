@@ -39,6 +39,35 @@ int main(int argc, char **argv)
         fprintf(stderr, "8-block calls and whole-image call disagree\n");
         return 2;
     }
+    // the other reference entry points, 8 blocks per call vs one whole-image call
+    {
+        static void *(*allocShim)(void *, size_t) = [](void *, size_t size) -> void * { return malloc(size); };
+        static void (*freeShim)(void *, void *, size_t) = [](void *, void *ptr, size_t) { free(ptr); };
+        cvtt::ETC2CompressionData *etc2 = cvtt::Kernels::AllocETC2Data(*allocShim, NULL, options);
+        std::vector<uint8_t> a(blocks.size() * 16), b(blocks.size() * 16);
+        for (size_t i = 0; i < blocks.size(); i += cvtt::NumParallelBlocks)
+            cvtt::Kernels::EncodeETC2RGBA(&a[i * 16], &blocks[i], options, etc2);
+        cvtt::Kernels::B200::Encode(CVTTB200_ETC2_RGBA, b.data(), blocks.data(), blocks.size(), options);
+        cvtt::Kernels::ReleaseETC2Data(etc2, *freeShim);
+        if (a != b)
+        {
+            fprintf(stderr, "ETC2 RGBA: 8-block calls and whole-image call disagree\n");
+            return 3;
+        }
+        for (size_t i = 0; i < blocks.size(); i += cvtt::NumParallelBlocks)
+            cvtt::Kernels::EncodeBC3(&a[i * 16], &blocks[i], options);
+        cvtt::Kernels::B200::Encode(CVTTB200_BC3, b.data(), blocks.data(), blocks.size(), options);
+        if (a != b)
+        {
+            fprintf(stderr, "BC3: 8-block calls and whole-image call disagree\n");
+            return 4;
+        }
+        uint64_t h2 = 1469598103934665603ull;
+        for (size_t i = 0; i < b.size(); i++)
+            h2 = (h2 ^ b[i]) * 1099511628211ull;
+        printf("BC3 fnv64 %016llx\n", (unsigned long long)h2);
+    }
+
     uint64_t hash = 1469598103934665603ull;
     for (size_t i = 0; i < whole.size(); i++)
         hash = (hash ^ whole[i]) * 1099511628211ull;

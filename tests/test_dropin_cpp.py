@@ -51,3 +51,7 @@ def test_dropin_matches_oracle(oracle):
     opt = np.frombuffer(bytes(memoryview(api.Options())), np.uint8)
     want = oracle.encode_bc7(blocks, opt, oracle.plan_from_quality(60))
     assert "%d blocks, fnv64 %016x" % (len(blocks), _fnv64(want)) in r.stdout, r.stdout
+    from oracle import loader
+    if os.path.exists(loader.REF_SO):
+        ref = loader.Reference().encode("BC3", blocks, opt)
+        assert "BC3 fnv64 %016x" % _fnv64(ref) in r.stdout, r.stdout

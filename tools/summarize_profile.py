@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Turns gpurun_out/<name>.ncu-rep (+ launches.csv) into the tracked summaries under profiles/.
-usage: summarize_profile.py <tag> <rep> <blocks_in_captured_launch> [launches.csv]"""
+usage: summarize_profile.py <tag> <rep> <blocks_in_captured_launch> [launches.csv|-] [summary_name]"""
 import csv, io, json, os, subprocess, sys
 
 tag, rep, blocks = sys.argv[1], sys.argv[2], int(sys.argv[3])
-launches = sys.argv[4] if len(sys.argv) > 4 else None
+launches = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None
+summary_name = sys.argv[5] if len(sys.argv) > 5 else "bc7"      # profiles/<summary_name>_kernel_ncu_summary.json, read by bench.py
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 os.makedirs(OUT, exist_ok=True)
@@ -59,7 +60,7 @@ summary = {
     "registers_per_thread": int(float(m["launch__registers_per_thread"][0])),
     "warp_instructions_per_block": float(m["smsp__inst_executed.sum"][0].replace(",", "")) / (blocks / 32.0) if "smsp__inst_executed.sum" in m else None,
 }
-with open(os.path.join(OUT, "bc7_kernel_ncu_summary.json"), "w") as f:
+with open(os.path.join(OUT, summary_name + "_kernel_ncu_summary.json"), "w") as f:
     json.dump(summary, f, indent=1)
 print(json.dumps(summary, indent=1))
 
