@@ -511,7 +511,7 @@ namespace cvttb200
                             // SelectIndexHDRSlow (IndexSelectorHDR.h:125-139)
                             const float pl[3] = { fmul(lp.x, P.w[0]), fmul(lp.y, P.w[1]), fmul(lp.z, P.w[2]) };
                             int index = 0;
-                            float bestError = 0.0f;
+                            float bestError = 0.0f, l0 = reconLin[0][0], l1 = reconLin[0][1], l2 = reconLin[0][2];
 #pragma unroll
                             for (int i = 0; i < RANGE; i++)
                             {
@@ -521,14 +521,17 @@ namespace cvttb200
                                     bestError = error;
                                 else
                                 {
-                                    if (error < bestError)
-                                        index = i;
+                                    const bool better = error < bestError;
+                                    index = better ? i : index;
+                                    l0 = better ? reconLin[i][0] : l0;      // selects, so the tables stay in registers
+                                    l1 = better ? reconLin[i][1] : l1;
+                                    l2 = better ? reconLin[i][2] : l2;
                                     bestError = sse_min(bestError, error);
                                 }
                             }
-                            linOut[0] = reconLin[index][0];
-                            linOut[1] = reconLin[index][1];
-                            linOut[2] = reconLin[index][2];
+                            linOut[0] = l0;
+                            linOut[1] = l1;
+                            linOut[2] = l2;
                             return index;
                         }
                     };
@@ -552,10 +555,11 @@ namespace cvttb200
                     metaEP[metaRound][subset][1] = qp[1];
                     metaEP[metaRound][subset][2] = qp[2];
                     // indexes[fixupIndex] = index (the array is shared by both subsets of the round)
+                    uint32_t roundIdx[2] = { 0, 0 }, roundMask[2] = { 0, 0 };
                     {
                         const int sh = 4 * (fixupIndex & 7);
-                        uint32_t &wd = metaIdx[metaRound][fixupIndex >> 3];
-                        wd = (wd & ~(15u << sh)) | ((uint32_t)fixIndexStored << sh);
+                        roundIdx[fixupIndex >> 3] = (uint32_t)fixIndexStored << sh;
+                        roundMask[fixupIndex >> 3] = 15u << sh;
                     }
 
                     // a round that repeats an earlier round's endpoints on all eight lanes is dropped (BC67.cpp:2853-2877)
@@ -567,6 +571,8 @@ namespace cvttb200
                         if (vote.all(anySame))
                         {
                             roundValid &= ~(1u << (metaRound * 2 + subset));
+                            for (int h = 0; h < 2; h++)
+                                metaIdx[metaRound][h] = (metaIdx[metaRound][h] & ~roundMask[h]) | roundIdx[h];
                             continue;
                         }
                     }
@@ -588,8 +594,16 @@ namespace cvttb200
                             raw = selectIndex(px, rl);
                             index = invert ? (RANGE - 1 - raw) : raw;
                             const int sh = 4 * (px & 7);
-                            uint32_t &wd = metaIdx[metaRound][px >> 3];
-                            wd = (wd & ~(15u << sh)) | ((uint32_t)index << sh);
+                            if (px < 8)
+                            {
+                                roundIdx[0] |= (uint32_t)index << sh;
+                                roundMask[0] |= 15u << sh;
+                            }
+                            else
+                            {
+                                roundIdx[1] |= (uint32_t)index << sh;
+                                roundMask[1] |= 15u << sh;
+                            }
                         }
 
                         const F4 lp = L.lin[px * STRIDE];
@@ -637,6 +651,8 @@ namespace cvttb200
                         }
                     }
                     metaErr[metaRound][subset] = subsetError;
+                    for (int h = 0; h < 2; h++)
+                        metaIdx[metaRound][h] = (metaIdx[metaRound][h] & ~roundMask[h]) | roundIdx[h];
                 }
             }
         }

@@ -257,8 +257,9 @@ namespace
 
 namespace
 {
-    constexpr int kETCThreads = 128;
-    constexpr int kETCCtasPerSM = 4;
+    constexpr int kETCThreads = 512;      // 16 warps = 64 reference groups per CTA, one CTA per SM, phases in lock-step
+    constexpr int kETCCtasPerSM = 1;
+    constexpr size_t kETCSmemBytes = (size_t)kETCThreads * 16 * sizeof(F4);
 
     __constant__ ETCTables c_etcTables;
 
@@ -283,10 +284,10 @@ namespace
     __global__ void __launch_bounds__(kETCThreads, kETCCtasPerSM)
     etc_encode_kernel(const __grid_constant__ ETCParams P, const uint4 *__restrict__ in, uint32_t *__restrict__ out, uint32_t nBlocks, ETCScratch scratch)
     {
-        __shared__ F4 sPw[16 * kETCThreads];
+        extern __shared__ __align__(16) unsigned char smem[];
+        F4 *sPw = reinterpret_cast<F4 *>(smem);
         const uint32_t tid = threadIdx.x;
         const uint32_t gthread = blockIdx.x * kETCThreads + tid;
-        const uint32_t totalThreads = gridDim.x * kETCThreads;
 
         ETCScratch S = scratch;
         S.drsErr += gthread;
@@ -298,9 +299,10 @@ namespace
         L.pw = sPw + tid;
         SegmentMax vote;
 
-        for (uint32_t base = (gthread & ~31u); base < nBlocks; base += totalThreads)
+        // CTA-uniform trip count: every thread of the CTA takes part in the phase barriers of the encode functions
+        for (uint32_t tileBase = blockIdx.x * kETCThreads; tileBase < nBlocks; tileBase += gridDim.x * kETCThreads)
         {
-            const uint32_t block = base + (tid & 31);
+            const uint32_t block = tileBase + tid;
             const bool active = block < nBlocks;
             int alpha[16];
 #pragma unroll
@@ -551,6 +553,12 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
         CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
@@ -673,18 +681,17 @@ namespace
     int launch_etc_color(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const ETCParams &P, bool uniform, cudaStream_t stream)
     {
         // resident threads: the whole device, or fewer for small inputs
-        const size_t warpsNeeded = (nBlocks + 31) / 32;
         const size_t maxCtas = (size_t)ctx.numSMs * kETCCtasPerSM;
-        const unsigned grid = (unsigned)std::min(maxCtas, (warpsNeeded + kETCThreads / 32 - 1) / (kETCThreads / 32));
+        const unsigned grid = (unsigned)std::min(maxCtas, (nBlocks + kETCThreads - 1) / kETCThreads);
         const size_t threads = (size_t)grid * kETCThreads;
         void *dScratch = nullptr;
         CVTT_CUDA(cudaMallocAsync(&dScratch, etc_scratch_bytes(threads), stream));
         ETCScratch S;
         etc_scratch_layout(S, dScratch, threads);
         if (uniform)
-            etc_encode_kernel<KIND, true><<<grid, kETCThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+            etc_encode_kernel<KIND, true><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
         else
-            etc_encode_kernel<KIND, false><<<grid, kETCThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+            etc_encode_kernel<KIND, false><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
         g_launches++;
         CVTT_CUDA(cudaGetLastError());
         CVTT_CUDA(cudaFreeAsync(dScratch, stream));

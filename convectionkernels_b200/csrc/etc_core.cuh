@@ -406,6 +406,7 @@ namespace cvttb200
 
         for (int table = 0; table < 8; table++)
         {
+            cta_sync();     // keeps the warps of the CTA in the same code region (instruction cache), see DESIGN.md
             const int modifier = T.thModifier[table];
             const int modifierOffset = modifier + modifier;
 
@@ -536,6 +537,7 @@ namespace cvttb200
 
         for (int table = 0; table < 8; table++)
         {
+            cta_sync();
             const int modifier = T.thModifier[table];
             const int modifierOffset = modifier * 2;
             int numUnique[2] = { 0, 0 };
@@ -708,6 +710,7 @@ namespace cvttb200
                     const int16_t *potentialOffsets = T.potentialOffsets;
                     for (int table = 0; table < 8; table++)
                     {
+                        cta_sync();
                         const int numOffsets = *potentialOffsets++;
                         int lastColor = -1;
                         for (int oi = 0; oi < numOffsets; oi++)
@@ -766,6 +769,7 @@ namespace cvttb200
                 }
                 else
                 {
+                    cta_sync();
                     // FindBestDifferentialCombination, ETC.cpp:219-362 (canIgnoreSector is false without punch-through)
                     const float blockBestTotalError = best.error;
                     float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
@@ -902,6 +906,7 @@ namespace cvttb200
         best.error = FLT_MAX;
         best.hi = best.lo = 0;
 
+        cta_sync();
         etc_planar<UNIFORM, STRIDE>(P, L, best);
 
         float chromaDelta[16][2];
