@@ -87,6 +87,7 @@ namespace cvttb200
         bool anyBlockHasAlpha;    // group vote, BC67.cpp:1069
         bool allowRGBModes;       // group vote, BC67.cpp:1072
         bool blockHasNonMaxAlpha; // this block
+        bool blockHasNonZeroAlpha, isPunchThrough;   // this block: max alpha > 0; every alpha is 0 or 255 (BC67.cpp:1056-1067)
         // warp-level "does any lane need this path" (pure work skipping, never changes a lane's result)
         bool warpAnyRGB, warpAnyPCA4, warpAnyExpand, warpAnyMode7;
     };
@@ -99,6 +100,7 @@ namespace cvttb200
         uint32_t ep[3][2];    // per subset, per endpoint: r | g << 8 | b << 16 | a << 24
         uint32_t idx[2];      // 16 x 4 bits, pixel order
         uint32_t idx2[2];
+        uint32_t sc[3];       // per subset: 0, or 0x80000000 | index when the subset's winner is a single-colour candidate
     };
 
     CVTT_HD float quant_one(const QuantConst &q, float c, int p)
@@ -462,7 +464,7 @@ namespace cvttb200
     // refine rounds of one pair of trial chains starting from the tweaked endpoints u0/u1
     template<int MODE, bool FAST, int STRIDE>
     CVTT_HD void bc7_trial_pair(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const float *sumV, float staticAlphaError,
-        const f2 *u0, const f2 *u1, int p0x, int p0y, int p1x, int p1y, int seqX, int seqY, BC7PairBest<BC7ModeT<MODE>::NCH> &best)
+        const f2 *u0, const f2 *u1, int p0x, int p0y, int p1x, int p1y, int seqX, int seqY, bool invalidX, bool invalidY, BC7PairBest<BC7ModeT<MODE>::NCH> &best)
     {
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
@@ -536,7 +538,8 @@ namespace cvttb200
 
             {
                 const int sx = seqX + refine, sy = seqY + refine;
-                if (shapeError.x < best.err.x || (shapeError.x == best.err.x && sx < best.seqX))
+                // Flags::BC7_RespectPunchThrough masks the commits of parity combinations that would move alpha off 0 / 255 (BC67.cpp:1406-1414)
+                if (!invalidX && (shapeError.x < best.err.x || (shapeError.x == best.err.x && sx < best.seqX)))
                 {
                     best.err.x = shapeError.x;
                     best.seqX = sx;
@@ -547,7 +550,7 @@ namespace cvttb200
                         best.e1[ch].x = q1b[ch].x;
                     }
                 }
-                if (shapeError.y < best.err.y || (shapeError.y == best.err.y && sy < best.seqY))
+                if (!invalidY && (shapeError.y < best.err.y || (shapeError.y == best.err.y && sy < best.seqY)))
                 {
                     best.err.y = shapeError.y;
                     best.seqY = sy;
@@ -589,7 +592,7 @@ namespace cvttb200
 
     template<int MODE, bool FAST, int STRIDE>
     CVTT_HD void bc7_shape_trials(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
-        const float *sumV, float staticAlphaError, BC7ShapeBest &out)
+        const float *sumV, float staticAlphaError, uint32_t punchInvalid, BC7ShapeBest &out)
     {
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
@@ -623,7 +626,8 @@ namespace cvttb200
                     // lanes: pIter = 2 pp and 2 pp + 1, i.e. first parity bit 0 and 1
                     const int p1 = M::SHAREDP ? 0 : pp;
                     const int seqX = ((pp * 2) * 4 + tweak) << 16, seqY = ((pp * 2 + 1) * 4 + tweak) << 16;
-                    bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 1, M::SHAREDP ? 0 : p1, M::SHAREDP ? 1 : p1, seqX, seqY, best);
+                    bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 1, M::SHAREDP ? 0 : p1, M::SHAREDP ? 1 : p1, seqX, seqY,
+                                                       ((punchInvalid >> (pp * 2)) & 1) != 0, ((punchInvalid >> (pp * 2 + 1)) & 1) != 0, best);
                 }
             }
         }
@@ -643,7 +647,7 @@ namespace cvttb200
                     u0[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf0, offs[ch]), base[ch]), 0.0f, 255.0f));
                     u1[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf1, offs[ch]), base[ch]), 0.0f, 255.0f));
                 }
-                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 0, 0, 0, tweak << 16, pairFull ? (tweakY << 16) : 0x7ff00000, best);
+                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 0, 0, 0, tweak << 16, pairFull ? (tweakY << 16) : 0x7ff00000, false, false, best);
             }
         }
 
@@ -658,6 +662,56 @@ namespace cvttb200
         }
         out.e0 = r0;
         out.e1 = r1;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // TrySingleColorRGBAMultiTable (BC67.cpp:940-1040) for one (mode, shape), evaluated after the shape's trials when
+    // Flags::BC7_TrySingleColor is set (BC67.cpp:1436-1570).
+    //
+    // What the reference actually computes: its table loop accepts a candidate under
+    //     better = ParallelMath::AndNot(pti, better)           (BC67.cpp:998)
+    // and AndNot(a, b) is a & ~b (ParallelMath.h:901-906), i.e. "punch-through-invalid and NOT closer to the average".
+    // Without punch-through invalidation pti is false, and with it the first comparison against FLT_MAX is always
+    // "better", so no table entry is ever accepted: the single-colour tables (ConvectionKernels_BC7_SingleColor.h) are dead
+    // data and the candidate that reaches the error test is always the initial one -- both endpoints (0, 0, 0[, 255]),
+    // reconstructed colour (0, 0, 0[, 255]), index 0 for every pixel of the shape.  Bit-exactness means reproducing that:
+    // the flag adds an "all black at index 0" candidate per (mode, shape).  (The average the reference computes over
+    // pixels[0..n-1] instead of the shape's pixels, :1444-1446, therefore has no observable effect either.)
+    // Returns true when the candidate replaces the shape's best; scIndex receives the index every pixel of the shape takes.
+    template<int MODE, int STRIDE>
+    CVTT_HD bool bc7_try_single_color(const BC7Params &P, const BC7Lane<STRIDE> &L, int n, float staticAlphaError, BC7ShapeBest &best, uint32_t &scIndex)
+    {
+        typedef BC7ModeT<MODE> M;
+        enum { NCH = M::NCH };
+        const int reconstructed[4] = { 0, 0, 0, 255 };
+        int agg[4] = { 0, 0, 0, 0 };
+        for (int i = 0; i < n; i++)
+        {
+            const F4 p = L.gv[i * STRIDE];
+            const int pv[4] = { (int)(as_uint(p.x) & 0xffu), (int)(as_uint(p.y) & 0xffu), (int)(as_uint(p.z) & 0xffu), (int)(as_uint(p.w) & 0xffu) };
+            for (int ch = 0; ch < NCH; ch++)
+                agg[ch] += (reconstructed[ch] - pv[ch]) * (reconstructed[ch] - pv[ch]);
+        }
+        // AggregatedError<4>::Finalize over all four accumulators (the unused one is zero), then the static alpha error
+        float error;
+        if (P.flags & kFlag_Uniform)
+            error = (float)(agg[0] + agg[1] + agg[2] + agg[3]);
+        else
+        {
+            error = fmul((float)agg[0], P.wSq[0]);
+            for (int ch = 1; ch < 4; ch++)
+                error = fadd(error, fmul((float)agg[ch], P.wSq[ch]));
+        }
+        error = fadd(error, staticAlphaError);
+
+        if (error < best.err)
+        {
+            best.err = error;
+            best.e0 = best.e1 = (NCH == 4) ? 0xff000000u : 0u;
+            scIndex = 0x80000000u;
+            return true;
+        }
+        return false;
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -936,6 +990,7 @@ namespace cvttb200
             const float c0[4] = { bRGB0[0], bRGB0[1], bRGB0[2], bA0 }, c1[4] = { bRGB1[0], bRGB1[1], bRGB1[2], bA1 };
             work.ep[0][0] = pack_ep_bytes(c0, 4);
             work.ep[0][1] = pack_ep_bytes(c1, 4);
+            work.sc[0] = work.sc[1] = work.sc[2] = 0;
         }
     }
 
@@ -1261,9 +1316,15 @@ namespace cvttb200
         for (int s = 0; s < 3; s++)
             work.ep[s][0] = work.ep[s][1] = 0;
         work.idx[0] = work.idx[1] = work.idx2[0] = work.idx2[1] = 0;
+        work.sc[0] = work.sc[1] = work.sc[2] = 0;
 
-        // per-(mode, shape) results, indexed by the slot numbers the host assigned: error, endpoint 0, endpoint 1
-        uint32_t res[kBC7MaxSlots][3];
+        // per-(mode, shape) results, indexed by the slot numbers the host assigned: error, endpoint 0, endpoint 1, single-colour marker
+        uint32_t res[kBC7MaxSlots][4];
+
+        const bool trySingleColor = (P.flags & kFlag_BC7_TrySingleColor) != 0;
+        // Flags::BC7_RespectPunchThrough is rejected by the host (see launch_bc7): the reference's masking at BC67.cpp:1411 has
+        // the same inverted AndNot, which makes commits order dependent; the hook for a per-parity mask is kept.
+        const uint32_t punchInvalid67 = 0;
 
         const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;                   // BC67.cpp:1121
         const bool allowMode7 = lf.anyBlockHasAlpha || (P.mode7RGBPartitionEnabled != 0); // BC67.cpp:1078
@@ -1336,29 +1397,53 @@ namespace cvttb200
                     const uint32_t rw = pc[2 + r];
                     const int mode = rw & 0xf, seeds = (rw >> 4) & 0xf, slot = (rw >> 8) & 0xff;
                     BC7ShapeBest best;
+                    uint32_t scIndex = 0;
                     if (mode < 4)
                     {
                         if (!lf.warpAnyRGB)
                             continue;
                         switch (mode)
                         {
-                        case 0: bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
-                        case 1: bc7_shape_trials<1, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
-                        case 2: bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
-                        default: bc7_shape_trials<3, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best); break;
+                        case 0:
+                            bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            if (trySingleColor)
+                                bc7_try_single_color<0, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
+                            break;
+                        case 1:
+                            bc7_shape_trials<1, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            if (trySingleColor)
+                                bc7_try_single_color<1, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
+                            break;
+                        case 2:
+                            bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            if (trySingleColor)
+                                bc7_try_single_color<2, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
+                            break;
+                        default:
+                            bc7_shape_trials<3, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            if (trySingleColor)
+                                bc7_try_single_color<3, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
+                            break;
                         }
                     }
                     else if (mode == 6)
-                        bc7_shape_trials<6, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
+                    {
+                        bc7_shape_trials<6, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, punchInvalid67, best);
+                        if (trySingleColor)
+                            bc7_try_single_color<6, STRIDE>(P, L, n, 0.0f, best, scIndex);
+                    }
                     else
                     {
                         if (!lf.warpAnyMode7)
                             continue;
-                        bc7_shape_trials<7, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
+                        bc7_shape_trials<7, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, punchInvalid67, best);
+                        if (trySingleColor)
+                            bc7_try_single_color<7, STRIDE>(P, L, n, 0.0f, best, scIndex);
                     }
                     res[slot][0] = as_uint(best.err);
                     res[slot][1] = best.e0;
                     res[slot][2] = best.e1;
+                    res[slot][3] = scIndex;
                 }
                 pc += 2 + nRuns;
             }
@@ -1396,6 +1481,7 @@ namespace cvttb200
                     {
                         work.ep[s][0] = res[slots[s]][1];
                         work.ep[s][1] = res[slots[s]][2];
+                        work.sc[s] = res[slots[s]][3];
                     }
                 }
             }
@@ -1482,7 +1568,9 @@ namespace cvttb200
                     {
                         const int px = ctz32(m);
                         const F4 p = bc7_expand_pixel(L.raw[px * STRIDE]);
-                        idx[px >> 3] |= bc7_select_index<FAST>(S, p) << (4 * (px & 7));
+                        // a single-colour winner gives every pixel of the subset the table's index (BC67.cpp:1035-1036)
+                        const uint32_t index = work.sc[s] ? (work.sc[s] & 15u) : bc7_select_index<FAST>(S, p);
+                        idx[px >> 3] |= index << (4 * (px & 7));
                     }
                 }
             }

@@ -149,7 +149,8 @@ namespace
         L.gv = sGv + tid;
         L.gw = sGw + tid;
 
-        uint32_t minAlpha = 255;
+        uint32_t minAlpha = 255, maxAlpha = 0;
+        bool isPunchThrough = true;
         if (active)
         {
             const uint4 *src = in + (size_t)block * 4;
@@ -158,6 +159,11 @@ namespace
             {
                 const uint4 v = __ldg(src + q);
                 minAlpha = min(minAlpha, min(min(v.x >> 24, v.y >> 24), min(v.z >> 24, v.w >> 24)));
+                maxAlpha = max(maxAlpha, max(max(v.x >> 24, v.y >> 24), max(v.z >> 24, v.w >> 24)));
+                const uint32_t a[4] = { v.x >> 24, v.y >> 24, v.z >> 24, v.w >> 24 };
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    isPunchThrough = isPunchThrough && (a[k] == 0 || a[k] == 255);
                 sRaw[(q * 4 + 0) * kBC7Threads + tid] = v.x;
                 sRaw[(q * 4 + 1) * kBC7Threads + tid] = v.y;
                 sRaw[(q * 4 + 2) * kBC7Threads + tid] = v.z;
@@ -180,6 +186,8 @@ namespace
         lf.anyBlockHasAlpha = (hasAlphaBallot & segMask) != 0;
         lf.allowRGBModes = (allowRGBBallot & segMask) != 0;
         lf.blockHasNonMaxAlpha = minAlpha < 255;
+        lf.blockHasNonZeroAlpha = maxAlpha > 0;
+        lf.isPunchThrough = isPunchThrough;
         const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;
         const bool mode7 = lf.anyBlockHasAlpha || P.mode7RGBPartitionEnabled != 0;
         lf.warpAnyRGB = __any_sync(0xffffffffu, active && lf.allowRGBModes);
@@ -731,8 +739,8 @@ namespace
 
     int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, cudaStream_t stream)
     {
-        if (options.flags & (kFlag_BC7_TrySingleColor | kFlag_BC7_RespectPunchThrough))
-            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::BC7_TrySingleColor / BC7_RespectPunchThrough are not implemented yet");
+        if (options.flags & kFlag_BC7_RespectPunchThrough)
+            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::BC7_RespectPunchThrough is not implemented (the reference masks its commits with inverted operands, BC67.cpp:1411)");
         if (nBlocks > 0xffffff00u)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
 

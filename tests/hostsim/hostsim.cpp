@@ -30,12 +30,20 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
     {
         const size_t lanes = std::min<size_t>(32, nBlocks - warpBase);
         BC7LaneFlags lf[32];
-        int minAlpha[32];
+        int minAlpha[32], maxAlpha[32];
+        bool punch[32];
         for (size_t l = 0; l < lanes; l++)
         {
             minAlpha[l] = 255;
+            maxAlpha[l] = 0;
+            punch[l] = true;
             for (int px = 0; px < 16; px++)
-                minAlpha[l] = std::min<int>(minAlpha[l], blocks[(warpBase + l) * 64 + px * 4 + 3]);
+            {
+                const int a = blocks[(warpBase + l) * 64 + px * 4 + 3];
+                minAlpha[l] = std::min<int>(minAlpha[l], a);
+                maxAlpha[l] = std::max<int>(maxAlpha[l], a);
+                punch[l] = punch[l] && (a == 0 || a == 255);
+            }
         }
         bool wRGB = false, wPCA4 = false, wM7 = false;
         for (size_t l = 0; l < lanes; l++)
@@ -50,6 +58,8 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
             lf[l].anyBlockHasAlpha = anyAlpha;
             lf[l].allowRGBModes = allowRGB;
             lf[l].blockHasNonMaxAlpha = minAlpha[l] < 255;
+            lf[l].blockHasNonZeroAlpha = maxAlpha[l] > 0;
+            lf[l].isPunchThrough = punch[l];
             wRGB |= allowRGB;
             wPCA4 |= anyAlpha || !allowRGB;
             wM7 |= anyAlpha || plan->mode7RGBPartitionEnabled != 0;

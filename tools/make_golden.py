@@ -50,6 +50,7 @@ save("bc7_random_better", "BC7", rb, options(flags=0x180), q100)                
 save("bc7_random_uniform", "BC7", rb, options(flags=0x208), q100)
 save("bc7_random_refine3_weights", "BC7", rb, options(refine=3, weights=(1.0, 0.5, 2.0, 0.25)), q100)
 save("bc7_random_refine1", "BC7", rb, options(refine=1), q100)
+save("bc7_random_trysinglecolor", "BC7", rb, options(flags=0x118), q100)          # BC7_TrySingleColor | S3TC_Paranoid, exact indexing
 save("bc7_gradient_q100", "BC7", grad, options(), q100)
 save("bc7_mixed_q100", "BC7", mixed, options(), q100)
 # config 1 (plumbing, CPU only): EncodeBC1 on the 256x256 gradient
