@@ -421,13 +421,14 @@ namespace
         __shared__ F4 sPx[16 * kS3TCThreads];
         const uint32_t tid = threadIdx.x;
         const uint32_t block = blockIdx.x * kS3TCThreads + tid;
-        if (block >= nBlocks)
-            return;
+        const bool active = block < nBlocks;      // whole warps stay alive: the exhaustive search uses a segment maximum
         constexpr bool isSigned = (FMT == CVTTB200_BC4S || FMT == CVTTB200_BC5S);
 #pragma unroll
         for (int q = 0; q < 4; q++)
         {
-            const uint4 v = __ldg(in + (size_t)block * 4 + q);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (active)
+                v = __ldg(in + (size_t)block * 4 + q);
             const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -449,17 +450,18 @@ namespace
         L.px = sPx + tid;
 
         uint32_t w[4] = { 0, 0, 0, 0 };
+        SegmentMax vote;
         if (FMT == CVTTB200_BC1)
-            s3tc_pack_rgb<kS3TCThreads>(P, L, true, w);
+            s3tc_pack_rgb<kS3TCThreads>(P, L, true, vote, w);
         else if (FMT == CVTTB200_BC2)
         {
             s3tc_pack_explicit_alpha<kS3TCThreads>(L, 3, w);
-            s3tc_pack_rgb<kS3TCThreads>(P, L, false, w + 2);
+            s3tc_pack_rgb<kS3TCThreads>(P, L, false, vote, w + 2);
         }
         else if (FMT == CVTTB200_BC3)
         {
             s3tc_pack_interpolated_alpha<kS3TCThreads>(P, L, 3, false, w);
-            s3tc_pack_rgb<kS3TCThreads>(P, L, false, w + 2);
+            s3tc_pack_rgb<kS3TCThreads>(P, L, false, vote, w + 2);
         }
         else if (FMT == CVTTB200_BC4U || FMT == CVTTB200_BC4S)
             s3tc_pack_interpolated_alpha<kS3TCThreads>(P, L, 0, isSigned, w);
@@ -469,6 +471,8 @@ namespace
             s3tc_pack_interpolated_alpha<kS3TCThreads>(P, L, 1, isSigned, w + 2);
         }
 
+        if (!active)
+            return;
         if (FMT == CVTTB200_BC1 || FMT == CVTTB200_BC4U || FMT == CVTTB200_BC4S)
             reinterpret_cast<uint2 *>(out)[block] = make_uint2(w[0], w[1]);
         else
@@ -661,8 +665,6 @@ namespace
 
     int launch_s3tc(int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, cudaStream_t stream)
     {
-        if (options.flags & kFlag_S3TC_Exhaustive)
-            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::S3TC_Exhaustive is not implemented yet");
         if (nBlocks > 0xffffff00u)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
         S3TCParams P;
@@ -723,7 +725,7 @@ namespace
             CVTT_CUDA(cudaGetLastError());
             return CVTTB200_OK;
         }
-        if (options.flags & (kFlag_ETC_UseFakeBT709 | kFlag_ETC_FakeBT709Accurate))
+        if (options.flags & kFlag_ETC_UseFakeBT709)
             return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::ETC_UseFakeBT709 is not implemented yet");
         ETCParams P;
         etc_fill_params(P, options);

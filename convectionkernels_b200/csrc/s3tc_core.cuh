@@ -9,8 +9,9 @@
 //   IndexSelector<N>::Init / SelectIndexLDR / ReconstructLDRPrecise  ConvectionKernels_IndexSelector.h:27-131
 //   EndpointRefiner<N>                    ConvectionKernels_EndpointRefiner.h:38-152
 //
-// Flags::S3TC_Exhaustive is rejected by the host (CVTTB200_ERR_UNSUPPORTED).  Every AnySet / AllSet of the
-// non-exhaustive path only skips work whose result cannot change a lane, so lanes are independent.
+// Every AnySet / AllSet of the default path only skips work whose result cannot change a lane, so lanes are
+// independent there.  The exhaustive search (Flags::S3TC_Exhaustive) has one coupling: TestCounts stops feeding its refiner once
+// the position inside a cluster reaches the largest pixel count of the reference call (S3TC.cpp:279-283), expressed by Vote::max.
 #pragma once
 
 #include "cvtt_common.cuh"
@@ -166,9 +167,145 @@ namespace cvttb200
         }
     }
 
-    // PackRGB, non-exhaustive (S3TC.cpp:717-1051).  out: the 8 bytes as two little-endian words.
+#ifndef CVTT_SC_QUALIFIER
+#if defined(__CUDACC__)
+#define CVTT_SC_QUALIFIER static __device__ const
+#else
+#define CVTT_SC_QUALIFIER static const
+#endif
+#endif
+#if defined(__CUDACC__) || defined(CVTT_HOSTSIM)
+#include "s3tc_sc_tables.inc"
+#define CVTT_HAVE_S3TC_SC_TABLES 1
+#endif
+
+    // no cross-lane coupling: the vote used by callers that never take the exhaustive path
+    struct NoVote
+    {
+        CVTT_HD int max(int v) const { return v; }
+    };
+
+    // TestSingleColor (S3TC.cpp:83-188), Flags::S3TC_Exhaustive only
     template<int STRIDE>
-    CVTT_HD void s3tc_pack_rgb(const S3TCParams &P, const S3TCLane<STRIDE> &L, bool alphaTest, uint32_t out[2])
+    CVTT_HD void s3tc_test_single_color(const S3TCParams &P, const S3TCLane<STRIDE> &L, int range, S3TCBestRGB &best)
+    {
+#if defined(CVTT_HAVE_S3TC_SC_TABLES) && (defined(__CUDA_ARCH__) || defined(CVTT_HOSTSIM))
+        int totals[3] = { 0, 0, 0 };
+        for (int px = 0; px < 16; px++)
+        {
+            const F4 p = L.px[px * STRIDE];
+            totals[0] += (int)p.x;
+            totals[1] += (int)p.y;
+            totals[2] += (int)p.z;
+        }
+        const bool paranoidMetric = (P.flags & kFlag_S3TC_Paranoid) != 0;
+        int eps[2][3], interpolated[3];
+        float factors[3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const int average = (totals[ch] + 8) >> 4;
+            const unsigned char *entry = kS3TCSCTables[paranoidMetric ? 1 : 0][range == 3 ? 1 : 0][ch == 1 ? 1 : 0] + 4 * average;
+            eps[0][ch] = entry[0];
+            eps[1][ch] = entry[1];
+            interpolated[ch] = entry[2];
+            factors[ch] = fmul(fabsf((float)(int)entry[3]), 0.03f);      // ParanoidFactorForSpan
+        }
+        float error = 0.0f;
+        for (int px = 0; px < 16; px++)
+        {
+            const F4 p = L.px[px * STRIDE];
+            const int pv[3] = { (int)p.x, (int)p.y, (int)p.z };
+            for (int ch = 0; ch < 3; ch++)
+            {
+                if (paranoidMetric)
+                {
+                    const float absDiff = fadd(fabsf((float)(interpolated[ch] - pv[ch])), factors[ch]);
+                    error = fadd(error, fmul(fmul(absDiff, absDiff), P.wSq[ch]));
+                }
+                else
+                    error = fadd(error, fmul((float)wrap_u16((interpolated[ch] - pv[ch]) * (interpolated[ch] - pv[ch])), P.wSq[ch]));
+            }
+        }
+        if (error < best.error)
+        {
+            best.error = error;
+            for (int e = 0; e < 2; e++)
+                for (int ch = 0; ch < 3; ch++)
+                    best.ep[e][ch] = eps[e][ch];
+            best.idx = 0x55555555u;       // every index is 1
+            best.range = range;
+        }
+#endif
+    }
+
+    // TestCounts (S3TC.cpp:260-301): least-squares endpoints for "the counts[i] next sorted pixels take index i", then TestEndpoints.
+    // sortedOrder: 16 x 4 bits, entry e = block pixel of the e-th sorted input (only the first numElements are pixels, the rest
+    // of the reference's array is zero); groupMaxElements: the largest numElements of the reference call (see the escape, :279-283).
+    template<int STRIDE>
+    CVTT_HD void s3tc_test_counts(const S3TCParams &P, const S3TCLane<STRIDE> &L, const int *counts, int nCounts, int numElements, int groupMaxElements,
+        uint64_t sortedOrder, S3TCBestRGB &best)
+    {
+        const float rcpMaxIndex = 1.0f / (float)(nCounts - 1);
+        float tv[3] = { 0.0f, 0.0f, 0.0f }, sv[3] = { 0.0f, 0.0f, 0.0f }, tt = 0.0f, ts = 0.0f;
+        int contributed = 0, e = 0;
+        bool escape = false;
+        for (int i = 0; i < nCounts && !escape; i++)
+            for (int n = 0; n < counts[i]; n++)
+            {
+                if (n >= groupMaxElements)
+                {
+                    escape = true;
+                    break;
+                }
+                if (n < numElements)
+                {
+                    float v[3] = { 0.0f, 0.0f, 0.0f };
+                    if (e < numElements)
+                    {
+                        const F4 p = L.px[(int)((sortedOrder >> (4 * e)) & 15u) * STRIDE];
+                        v[0] = fmul(p.x, P.w[0]);
+                        v[1] = fmul(p.y, P.w[1]);
+                        v[2] = fmul(p.z, P.w[2]);
+                    }
+                    const float t = fmul((float)i, rcpMaxIndex);
+                    for (int ch = 0; ch < 3; ch++)
+                    {
+                        tv[ch] = fadd(tv[ch], fmul(t, v[ch]));
+                        sv[ch] = fadd(sv[ch], v[ch]);
+                    }
+                    tt = fadd(tt, fmul(t, t));
+                    ts = fadd(ts, t);
+                    contributed++;
+                }
+                e++;
+            }
+
+        // EndpointRefiner::GetRefinedEndpointsLDR (EndpointRefiner.h:99-152)
+        float wN = (float)contributed;
+        safe_denominator(wN);
+        const float wRcp = P.rcpN[(int)wN];
+        float adenom = fmul(fsub(fmul(tt, wN), fmul(ts, ts)), wRcp);
+        const bool adenomZero = (adenom == 0.0f);
+        if (adenomZero)
+            adenom = 1.0f;
+        int ec[2][3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sv[ch]), wRcp)), adenom);
+            const float b = fmul(fsub(sv[ch], fmul(a, ts)), wRcp);
+            float p1 = b, p2 = fadd(a, b);
+            if (adenomZero)
+                p1 = p2 = fmul(sv[ch], wRcp);
+            ec[0][ch] = s3_round(clamp_for_round(fmul(p1, P.rcpW[ch]), 0.0f, 255.0f));
+            ec[1][ch] = s3_round(clamp_for_round(fmul(p2, P.rcpW[ch]), 0.0f, 255.0f));
+        }
+        s3tc_test_endpoints<STRIDE>(P, L, ec, nCounts, false, best);
+    }
+
+    // PackRGB (S3TC.cpp:717-1051).  out: the 8 bytes as two little-endian words.  vote.max is the maximum over the 8 blocks of the
+    // reference call, needed by the exhaustive search only.
+    template<int STRIDE, class Vote>
+    CVTT_HD void s3tc_pack_rgb(const S3TCParams &P, const S3TCLane<STRIDE> &L, bool alphaTest, Vote &vote, uint32_t out[2])
     {
         // alpha test: alpha becomes 0 / 255, transparent pixels get weight 0 in the endpoint fit (S3TC.cpp:744-773)
         uint32_t transparentMask = 0;
@@ -261,6 +398,95 @@ namespace cvttb200
         for (int e = 0; e < 2; e++)
             best.ep[e][0] = best.ep[e][1] = best.ep[e][2] = 0;
 
+        if (P.flags & kFlag_S3TC_Exhaustive)
+        {
+            // sort the pixels along the fitted axis: 11-bit index << 4 | pixel number, transparent pixels get -16 + px (S3TC.cpp:805-842)
+            int sortBins[16];
+            {
+                int sortEP[2][3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    // UnfinishedEndpoints::FinishLDR(0, 11): tweak 0 has the factors (-0.0, 1.0)
+                    sortEP[0][ch] = s3_round(clamp_for_round(fadd(base[ch], fmul(offs[ch], -0.0f)), 0.0f, 255.0f));
+                    sortEP[1][ch] = s3_round(clamp_for_round(fadd(base[ch], fmul(offs[ch], 1.0f)), 0.0f, 255.0f));
+                }
+                float origin[3], dW[3], axis[3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    origin[ch] = (float)sortEP[0][ch];
+                    dW[ch] = fmul(fsub((float)sortEP[1][ch], origin[ch]), P.w[ch]);
+                }
+                float lenSq = fmul(dW[0], dW[0]);
+                lenSq = fadd(lenSq, fmul(dW[1], dW[1]));
+                lenSq = fadd(lenSq, fmul(dW[2], dW[2]));
+                safe_denominator(lenSq);
+                const float mdl = fdiv(2047.0f, lenSq);
+                for (int ch = 0; ch < 3; ch++)
+                    axis[ch] = fmul(fmul(dW[ch], P.w[ch]), mdl);
+                for (int px = 0; px < 16; px++)
+                {
+                    const F4 p = L.px[px * STRIDE];
+                    float dist = fmul(fsub(p.x, origin[0]), axis[0]);
+                    dist = fadd(dist, fmul(fsub(p.y, origin[1]), axis[1]));
+                    dist = fadd(dist, fmul(fsub(p.z, origin[2]), axis[2]));
+                    int bin = s3_round(clamp_for_round(dist, 0.0f, 2047.0f)) << 4;
+                    if ((transparentMask >> px) & 1)
+                        bin = -16;
+                    sortBins[px] = bin + px;
+                }
+            }
+            for (int sortEnd = 1; sortEnd < 16; sortEnd++)
+                for (int sortLoc = sortEnd; sortLoc > 0; sortLoc--)
+                {
+                    const int a = sortBins[sortLoc], b = sortBins[sortLoc - 1];
+                    sortBins[sortLoc] = a > b ? a : b;
+                    sortBins[sortLoc - 1] = a > b ? b : a;
+                }
+            int firstElement = 0;
+            for (int e = 0; e < 16; e++)
+                if (sortBins[e] < 0)
+                    firstElement = e + 1;
+            const int numElements = 16 - firstElement;
+            uint64_t sortedOrder = 0;       // sortedInputs[15 - e] = pixels[sortBins[e] & 15]
+            for (int e = firstElement; e < 16; e++)
+                sortedOrder |= (uint64_t)(sortBins[e] & 15) << (4 * (15 - e));
+            const int groupMaxElements = vote.max(numElements);
+
+            for (int n0 = 0; n0 <= 15; n0++)
+            {
+                const int remainingFor1 = (16 - n0 == 16) ? 15 : 16 - n0;
+                for (int n1 = 0; n1 <= remainingFor1; n1++)
+                {
+                    const int remainingFor2 = (16 - n1 - n0 == 16) ? 15 : 16 - n1 - n0;
+                    for (int n2 = 0; n2 <= remainingFor2; n2++)
+                    {
+                        const int n3 = 16 - n2 - n1 - n0;
+                        if (n3 == 16)
+                            continue;
+                        const int counts[4] = { n0, n1, n2, n3 };
+                        s3tc_test_counts<STRIDE>(P, L, counts, 4, numElements, groupMaxElements, sortedOrder, best);
+                    }
+                }
+            }
+            s3tc_test_single_color<STRIDE>(P, L, 4, best);
+            if (alphaTest)
+            {
+                for (int n0 = 0; n0 <= 15; n0++)
+                {
+                    const int remainingFor1 = (16 - n0 == 16) ? 15 : 16 - n0;
+                    for (int n1 = 0; n1 <= remainingFor1; n1++)
+                    {
+                        const int n2 = 16 - n1 - n0;
+                        if (n2 == 16)
+                            continue;
+                        const int counts[4] = { n0, n1, n2, 0 };
+                        s3tc_test_counts<STRIDE>(P, L, counts, 3, numElements, groupMaxElements, sortedOrder, best);
+                    }
+                }
+                s3tc_test_single_color<STRIDE>(P, L, 3, best);
+            }
+        }
+        else
         for (int range = alphaTest ? 3 : 4; range <= 4; range++)
         {
             int tweakRounds = (range == 3) ? 3 : 4;               // BCCommon::TweakRoundsForRange

@@ -55,6 +55,16 @@ def test_weights_and_image_content_against_reference(reference):
     assert (got == want).all(), first_mismatch(want, got)
 
 
+def test_ultra_preset_is_accepted(reference):
+    """Flags::Ultra carries ETC_FakeBT709Accurate without ETC_UseFakeBT709: the bit has no effect on its own"""
+    blocks = synth.random_blocks_rgba8(1024, seed=3)
+    o = api.Options()
+    o.flags = api.Flags.Ultra
+    want = reference.encode("ETC2_RGBA", blocks, _opt_bytes(o), threads=0)
+    got = api.EncodeETC2RGBA(blocks, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
 def test_unsupported_variants_fail_loudly():
     blocks = synth.random_blocks_rgba8(8, seed=1)
     o = api.Options()

@@ -55,9 +55,14 @@ def test_config1_gradient_bc1(reference):
     assert (got == want).all(), first_mismatch(want, got)
 
 
-def test_exhaustive_flag_fails_loudly():
-    o = api.Options()
-    o.flags |= 0x80
-    with pytest.raises(api.CvttError) as e:
-        api.EncodeBC1(synth.random_blocks_rgba8(8, seed=1), o)
-    assert e.value.status == -2
+@pytest.mark.parametrize("fmt", ["BC1", "BC2", "BC3"])
+def test_exhaustive_against_reference(reference, fmt):
+    """Flags::Better / Ultra: S3TC_Exhaustive (cluster-fit enumeration, single-colour tables, per-call maximum of the pixel counts)"""
+    blocks = synth.random_blocks_rgba8(2048 + 8, seed=56)
+    blocks[::2, :, 3] = np.random.default_rng(3).integers(0, 256, size=blocks[::2, :, 3].shape)
+    for flags in (api.Flags.Better, api.Flags.Ultra, 0x288):
+        o = api.Options()
+        o.flags = flags
+        want = reference.encode(fmt, blocks, _opt_bytes(o), threads=0)
+        got = api.encode(fmt, blocks, o)
+        assert (got == want).all(), first_mismatch(want, got)

@@ -17,7 +17,7 @@ def hostsim_s3tc():
     out = os.path.join(ROOT, "tests", "_build", "libcvtt_hostsim_s3tc.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     csrc = os.path.join(ROOT, "convectionkernels_b200", "csrc")
-    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-w", "-I", csrc, "-o", out,
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-pthread", "-w", "-DCVTT_HOSTSIM", "-I", csrc, "-o", out,
                            os.path.join(ROOT, "tests", "hostsim", "hostsim_s3tc.cpp"), os.path.join(csrc, "s3tc_host.cpp")])
     H = ctypes.CDLL(out)
     H.hostsim_encode_s3tc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]

@@ -90,3 +90,5 @@ save("bc4u_random", "BC4U", rba, options())
 save("bc4s_random", "BC4S", rba, options())
 save("bc5u_random_seeds2", "BC5U", rba, options(seeds=2, refine_iic=3))
 save("bc5s_random", "BC5S", rba, options())
+save("bc1_random_alpha_exhaustive", "BC1", rba[:128], options(flags=0x188))
+save("bc3_random_exhaustive_uniform", "BC3", rba[:128], options(flags=0x288))
