@@ -106,12 +106,31 @@ namespace cvttb200
         return wrap_s16(scaled | (negative ? 0x8000 : 0));
     }
 
+    // QuantizeSingleEndpointElementSigned / Unsigned (BC67.cpp:2425-2446).  The reference evaluates elem * 32 / 31 (signed) or
+    // elem * 64 / 31 (unsigned) in fp32 under MXCSR round-up and converts with round-up again (RoundAndConvertToU15 / U16,
+    // ParallelMath.h:923-945).  For the admissible inputs (0..31743) that is exactly ceil(N / 31) with N = elem * 32 or
+    // elem * 64: N < 2^21, so a non-integer quotient is at least 1/31 below the next integer while the two upward roundings
+    // add less than 2^-7.  tests/test_bc6h_host.py checks all 31744 inputs against the fp32 formulation
+    // (bc6h_quantize_element_reference), which is what the reference executes.
     template<bool SIGNED>
     CVTT_HD int bc6h_quantize_element(int elem, int precision)
     {
         if (SIGNED)
         {
-            // QuantizeSingleEndpointElementSigned, BC67.cpp:2425-2440
+            const bool negative = elem < 0;
+            const int absElem = negative ? -elem : elem;
+            const int q = ((absElem * 32 + 30) / 31) >> (16 - precision);
+            return negative ? -q : q;
+        }
+        else
+            return ((elem * 64 + 30) / 31) >> (16 - precision);
+    }
+
+    template<bool SIGNED>
+    CVTT_HD int bc6h_quantize_element_reference(int elem, int precision)
+    {
+        if (SIGNED)
+        {
             const bool negative = elem < 0;
             const int absElem = negative ? -elem : elem;
             const float f = fdiv_ru(fmul_ru((float)absElem, 32.0f), 31.0f);
@@ -120,7 +139,6 @@ namespace cvttb200
         }
         else
         {
-            // QuantizeSingleEndpointElementUnsigned, BC67.cpp:2442-2446 (RoundAndConvertToU16, ParallelMath.h:923-933)
             const float f = sse_min(fdiv_ru(fmul_ru((float)elem, 64.0f), 31.0f), 65535.0f);
             const int expanded = wrap_u16(packs_s16(f2i_ru(fadd_ru(f, -32768.0f)))) ^ 0x8000;
             return expanded >> (16 - precision);
@@ -219,14 +237,14 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // EndpointSelector<3, 8> (ConvectionKernels_EndpointSelector.h:13-150) over the pixels of `mask`, ascending
-    // pixel order, unit pixel weights; pw[px * STRIDE] holds the pre-weighted pixel in .xyz.
-    template<int STRIDE>
-    CVTT_HD void endpoint_selector3_masked(const F4 *pw, uint32_t mask, int n, const float *wv, float *base, float *offs)
+    // pixel order, unit pixel weights; L.pw_at(px) is the pre-weighted pixel.
+    template<class Lane>
+    CVTT_HD void endpoint_selector3_masked(const Lane &L, uint32_t mask, int n, const float *wv, float *base, float *offs)
     {
         float centroid[3] = { 0.0f, 0.0f, 0.0f }, cov[6] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
         for (uint32_t m = mask; m; m &= m - 1)
         {
-            const F4 p = pw[ctz32(m) * STRIDE];
+            const F4 p = L.pw_at(ctz32(m));
             centroid[0] = fadd(centroid[0], p.x);
             centroid[1] = fadd(centroid[1], p.y);
             centroid[2] = fadd(centroid[2], p.z);
@@ -238,7 +256,7 @@ namespace cvttb200
         }
         for (uint32_t m = mask; m; m &= m - 1)
         {
-            const F4 p = pw[ctz32(m) * STRIDE];
+            const F4 p = L.pw_at(ctz32(m));
             const float d[3] = { fsub(p.x, centroid[0]), fsub(p.y, centroid[1]), fsub(p.z, centroid[2]) };
             int index = 0;
 #pragma unroll
@@ -279,7 +297,7 @@ namespace cvttb200
         float minDist = FLT_MAX, maxDist = -FLT_MAX;
         for (uint32_t m = mask; m; m &= m - 1)
         {
-            const F4 p = pw[ctz32(m) * STRIDE];
+            const F4 p = L.pw_at(ctz32(m));
             float dist = fadd(0.0f, fmul(dir[0], fsub(p.x, centroid[0])));
             dist = fadd(dist, fmul(dir[1], fsub(p.y, centroid[1])));
             dist = fadd(dist, fmul(dir[2], fsub(p.z, centroid[2])));
@@ -296,19 +314,54 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // Per-lane pixel storage, element px at [px * STRIDE]:
-    //   lin[px].xyz = TwosCLHalfToFloat(pixel)            lin[px].w = bits: pixel ch0 | pixel ch1 << 16
-    //   pw[px].xyz  = (float)pixel * channelWeight         pw[px].w  = bits: pixel ch2
-    template<int STRIDE>
+    // Per-lane pixel storage: planes of 32-bit words, element i of a plane at [i * STRIDE] (conflict-free in shared memory).
+    //   lin[px * 3 + ch] = TwosCLHalfToFloat(pixel)           (the value the errors compare against)
+    //   pw[px * 3 + ch]  = (float)pixel * channelWeight       (EndpointSelector / EndpointRefiner input)
+    //   pix[px * 2 + k]  = pixel ch0 | ch1 << 16, pixel ch2   (only read, and only allocated, with BC6H_FastIndexing)
+    template<int STRIDE, bool WITH_PIX>
     struct BC6HLane
     {
-        F4 *lin;
-        F4 *pw;
+        float *lin;
+        float *pw;
+        uint32_t *pix;
+
+        CVTT_HD F4 lin_at(int px) const
+        {
+            F4 r;
+            r.x = lin[(px * 3 + 0) * STRIDE];
+            r.y = lin[(px * 3 + 1) * STRIDE];
+            r.z = lin[(px * 3 + 2) * STRIDE];
+            r.w = WITH_PIX ? as_float(pix[(px * 2 + 0) * STRIDE]) : 0.0f;
+            return r;
+        }
+        CVTT_HD F4 pw_at(int px) const
+        {
+            F4 r;
+            r.x = pw[(px * 3 + 0) * STRIDE];
+            r.y = pw[(px * 3 + 1) * STRIDE];
+            r.z = pw[(px * 3 + 2) * STRIDE];
+            r.w = WITH_PIX ? as_float(pix[(px * 2 + 1) * STRIDE]) : 0.0f;
+            return r;
+        }
+        CVTT_HD void store(int px, const F4 &l, const F4 &q) const
+        {
+            lin[(px * 3 + 0) * STRIDE] = l.x;
+            lin[(px * 3 + 1) * STRIDE] = l.y;
+            lin[(px * 3 + 2) * STRIDE] = l.z;
+            pw[(px * 3 + 0) * STRIDE] = q.x;
+            pw[(px * 3 + 1) * STRIDE] = q.y;
+            pw[(px * 3 + 2) * STRIDE] = q.z;
+            if (WITH_PIX)
+            {
+                pix[(px * 2 + 0) * STRIDE] = as_uint(l.w);
+                pix[(px * 2 + 1) * STRIDE] = as_uint(q.w);
+            }
+        }
     };
 
     // Loads one PixelBlockF16 (int16 [16][4], alpha ignored) and converts it as BC6HComputer::Pack does (BC67.cpp:2691-2715)
-    template<bool SIGNED, int STRIDE>
-    CVTT_HD void bc6h_load_pixel(const BC6HParams &P, const BC6HLane<STRIDE> &L, int px, int r, int g, int b)
+    template<bool SIGNED, class Lane>
+    CVTT_HD void bc6h_load_pixel(const BC6HParams &P, const Lane &L, int px, int r, int g, int b)
     {
         int c[3] = { r, g, b };
         F4 lin, pw;
@@ -333,8 +386,7 @@ namespace cvttb200
         lin.w = as_float(((uint32_t)c[0] & 0xffffu) | ((uint32_t)c[1] << 16));
         pw.x = pf[0]; pw.y = pf[1]; pw.z = pf[2];
         pw.w = as_float((uint32_t)c[2] & 0xffffu);
-        L.lin[px * STRIDE] = lin;
-        L.pw[px * STRIDE] = pw;
+        L.store(px, lin, pw);
     }
 
     struct BC6HBest
@@ -355,7 +407,7 @@ namespace cvttb200
     // ---------------------------------------------------------------------------------------------------------
     // All trials of one (precision, partition): fills the meta arrays, then the commit scan (BC67.cpp:2790-2988).
     template<bool SIGNED, bool FAST, int RANGE, int STRIDE, class Vote>
-    CVTT_HD void bc6h_partition(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, bool partitioned, int aPrec, int p,
+    CVTT_HD void bc6h_partition(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE, FAST> &L, Vote &vote, bool partitioned, int aPrec, int p,
         const float *ufepBase /* [2][3] */, const float *ufepOffs /* [2][3] */, BC6HBest &best)
     {
         enum { kMaxTweak = 4, kMaxRefine = 3, kMeta = 12 };
@@ -384,7 +436,7 @@ namespace cvttb200
             float sumV[3] = { 0.0f, 0.0f, 0.0f };
             for (uint32_t m = mask; m; m &= m - 1)
             {
-                const F4 q = L.pw[ctz32(m) * STRIDE];
+                const F4 q = L.pw_at(ctz32(m));
                 sumV[0] = fadd(sumV[0], q.x);
                 sumV[1] = fadd(sumV[1], q.y);
                 sumV[2] = fadd(sumV[2], q.z);
@@ -495,10 +547,10 @@ namespace cvttb200
                     // index selection; returns the uninverted interpolator number
                     auto selectIndex = [&](int px, float *linOut) -> int
                     {
-                        const F4 lp = L.lin[px * STRIDE];
+                        const F4 lp = L.lin_at(px);
                         if (FAST)
                         {
-                            const F4 pq = L.pw[px * STRIDE];
+                            const F4 pq = L.pw_at(px);
                             const uint32_t w0 = as_uint(lp.w), w1 = as_uint(pq.w);
                             const float c0 = (float)wrap_s16((int)(w0 & 0xffffu)), c1 = (float)wrap_s16((int)(w0 >> 16)), c2 = (float)wrap_s16((int)(w1 & 0xffffu));
                             float dist = fmul(fsub(c0, origin[0]), axis[0]);
@@ -606,12 +658,12 @@ namespace cvttb200
                             }
                         }
 
-                        const F4 lp = L.lin[px * STRIDE];
+                        const F4 lp = L.lin_at(px);
                         float error = 0.0f;
                         if (FAST)
                         {
                             // ReconstructHDR* + ComputeErrorHDRFast (BCCommon.h:45-61, SqDiffSInt16 ParallelMath.h:996-1010)
-                            const F4 pq = L.pw[px * STRIDE];
+                            const F4 pq = L.pw_at(px);
                             const uint32_t w0 = as_uint(lp.w), w1 = as_uint(pq.w);
                             const int orig[3] = { wrap_s16((int)(w0 & 0xffffu)), wrap_s16((int)(w0 >> 16)), wrap_s16((int)(w1 & 0xffffu)) };
                             const int weight = wrap_u16(weightRecip * raw + 256) >> 9;
@@ -640,7 +692,7 @@ namespace cvttb200
                         if (refineNext)
                         {
                             // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92)
-                            const F4 pq = L.pw[px * STRIDE];
+                            const F4 pq = L.pw_at(px);
                             const float t = fmul((float)index, 1.0f / maxV);
                             tv[0] = fadd(tv[0], fmul(t, pq.x));
                             tv[1] = fadd(tv[1], fmul(t, pq.y));
@@ -740,7 +792,7 @@ namespace cvttb200
     // ---------------------------------------------------------------------------------------------------------
     // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).
     template<bool SIGNED, bool FAST, int STRIDE, class Vote>
-    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, uint32_t out[4])
+    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE, FAST> &L, Vote &vote, uint32_t out[4])
     {
         BC6HBest best;
         best.error = FLT_MAX;
@@ -760,9 +812,9 @@ namespace cvttb200
                 int n = 0;
                 for (uint32_t m = mask; m; m &= m - 1)
                     n++;
-                endpoint_selector3_masked<STRIDE>(L.pw, mask, n, P.w, ufepBase[p] + subset * 3, ufepOffs[p] + subset * 3);
+                endpoint_selector3_masked(L, mask, n, P.w, ufepBase[p] + subset * 3, ufepOffs[p] + subset * 3);
             }
-        endpoint_selector3_masked<STRIDE>(L.pw, 0xffffu, 16, P.w, ufepBase[32], ufepOffs[32]);
+        endpoint_selector3_masked(L, 0xffffu, 16, P.w, ufepBase[32], ufepOffs[32]);
         for (int ch = 0; ch < 3; ch++)
             ufepBase[32][3 + ch] = ufepOffs[32][3 + ch] = 0.0f;
 

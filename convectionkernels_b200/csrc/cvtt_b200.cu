@@ -209,7 +209,8 @@ namespace
 namespace
 {
     constexpr int kBC6HThreads = 128;
-    constexpr size_t kBC6HSmemBytes = (size_t)kBC6HThreads * 16 * 2 * sizeof(F4);
+    // per thread: 48 + 48 floats, plus 32 words of raw pixels for the fast-indexing kernels
+    constexpr size_t kBC6HSmemBytesSlow = (size_t)kBC6HThreads * 96 * 4, kBC6HSmemBytesFast = (size_t)kBC6HThreads * 128 * 4;
 
     __constant__ BC6HTables c_bc6hTables;
 
@@ -224,30 +225,32 @@ namespace
     };
 
     // One thread per block, warp = 4 reference groups.  Input: PixelBlockF16 = int16 [16][4] (128 B, alpha ignored), read
-    // with eight 128-bit loads per thread; converted once into two [pixel][thread] fp32x4 arrays in shared memory.
+    // with eight 128-bit loads per thread; converted once into [word][thread] planes in shared memory (384 B per thread, so
+    // that four CTAs = 16 warps fit an SM).
     template<bool SIGNED, bool FAST>
-    __global__ void __launch_bounds__(kBC6HThreads, 3)
+    __global__ void __launch_bounds__(kBC6HThreads, 4)
     bc6h_encode_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
     {
         extern __shared__ __align__(16) unsigned char smem[];
-        F4 *sLin = reinterpret_cast<F4 *>(smem);
-        F4 *sPw = sLin + 16 * kBC6HThreads;
+        float *sLin = reinterpret_cast<float *>(smem);
+        float *sPw = sLin + 48 * kBC6HThreads;
 
         const uint32_t tid = threadIdx.x;
         const uint32_t block = blockIdx.x * kBC6HThreads + tid;
         const bool active = block < nBlocks;
 
-        BC6HLane<kBC6HThreads> L;
+        BC6HLane<kBC6HThreads, FAST> L;
         L.lin = sLin + tid;
         L.pw = sPw + tid;
+        L.pix = reinterpret_cast<uint32_t *>(sPw + 48 * kBC6HThreads) + tid;
 #pragma unroll
         for (int q = 0; q < 8; q++)
         {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (active)
                 v = __ldg(in + (size_t)block * 8 + q);
-            bc6h_load_pixel<SIGNED, kBC6HThreads>(P, L, 2 * q, (int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu));
-            bc6h_load_pixel<SIGNED, kBC6HThreads>(P, L, 2 * q + 1, (int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu));
+            bc6h_load_pixel<SIGNED>(P, L, 2 * q, (int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu));
+            bc6h_load_pixel<SIGNED>(P, L, 2 * q + 1, (int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu));
         }
         __syncwarp();
 
@@ -571,10 +574,10 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesFast));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
+        CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesFast));
         CVTT_CUDA(cudaDeviceSynchronize());
         CVTT_CUDA(cudaSetDevice(prev));
 
@@ -650,13 +653,13 @@ namespace
         uint4 *out = (uint4 *)dOut;
         if (isSigned)
         {
-            if (fast) bc6h_encode_kernel<true, true><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
-            else bc6h_encode_kernel<true, false><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+            if (fast) bc6h_encode_kernel<true, true><<<grid, kBC6HThreads, kBC6HSmemBytesFast, stream>>>(P, in, out, (uint32_t)nBlocks);
+            else bc6h_encode_kernel<true, false><<<grid, kBC6HThreads, kBC6HSmemBytesSlow, stream>>>(P, in, out, (uint32_t)nBlocks);
         }
         else
         {
-            if (fast) bc6h_encode_kernel<false, true><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
-            else bc6h_encode_kernel<false, false><<<grid, kBC6HThreads, kBC6HSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks);
+            if (fast) bc6h_encode_kernel<false, true><<<grid, kBC6HThreads, kBC6HSmemBytesFast, stream>>>(P, in, out, (uint32_t)nBlocks);
+            else bc6h_encode_kernel<false, false><<<grid, kBC6HThreads, kBC6HSmemBytesSlow, stream>>>(P, in, out, (uint32_t)nBlocks);
         }
         g_launches++;
         CVTT_CUDA(cudaGetLastError());

@@ -21,12 +21,14 @@ namespace
         for (size_t base = 0; base < nBlocks; base += 8)
         {
             const int16_t *src = blocks + (base + lane) * 64;
-            F4 lin[16], pw[16];
-            BC6HLane<1> L;
+            float lin[48], pw[48];
+            uint32_t pix[32];
+            BC6HLane<1, FAST> L;
             L.lin = lin;
             L.pw = pw;
+            L.pix = pix;
             for (int px = 0; px < 16; px++)
-                bc6h_load_pixel<SIGNED, 1>(*P, L, px, src[px * 4 + 0], src[px * 4 + 1], src[px * 4 + 2]);
+                bc6h_load_pixel<SIGNED>(*P, L, px, src[px * 4 + 0], src[px * 4 + 1], src[px * 4 + 2]);
             uint32_t o[4];
             bc6h_encode_block<SIGNED, FAST, 1>(*P, T, L, vote, o);
             memcpy(out + (base + lane) * 16, o, 16);
@@ -56,4 +58,20 @@ extern "C" int hostsim_encode_bc6h(const int16_t *blocks, size_t nBlocks, uint8_
     for (auto &t : threads)
         t.join();
     return 0;
+}
+
+// number of inputs (0..31743, every precision the modes use) for which the integer form of the endpoint quantiser differs from
+// the fp32 directed-rounding form the reference executes
+extern "C" int hostsim_bc6h_quantizer_mismatches(void)
+{
+    int bad = 0;
+    const int precisions[] = { 6, 7, 8, 9, 10, 11, 12, 16 };
+    for (int e = 0; e <= 31743; e++)
+        for (int p : precisions)
+        {
+            bad += bc6h_quantize_element<false>(e, p) != bc6h_quantize_element_reference<false>(e, p);
+            bad += bc6h_quantize_element<true>(e, p) != bc6h_quantize_element_reference<true>(e, p);
+            bad += bc6h_quantize_element<true>(-e, p) != bc6h_quantize_element_reference<true>(-e, p);
+        }
+    return bad;
 }

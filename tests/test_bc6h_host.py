@@ -35,3 +35,8 @@ def test_bc6h_device_logic_on_cpu_matches_golden(hostsim_bc6h, name):
     rc = hostsim_bc6h.hostsim_encode_bc6h(blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data)
     assert rc == 0
     assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)
+
+
+def test_integer_quantiser_equals_directed_rounding_fp32(hostsim_bc6h):
+    """the kernel's ceil(N / 31) against the reference's fp32 multiply / divide / convert under MXCSR round-up, all inputs"""
+    assert hostsim_bc6h.hostsim_bc6h_quantizer_mismatches() == 0
