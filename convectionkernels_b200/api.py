@@ -294,3 +294,43 @@ def EncodeBC5U(pBlocks, options, out=None):
 def EncodeBC5S(pBlocks, options, out=None):
     """cvtt::Kernels::EncodeBC5S (PixelBlockS8 input), reference ConvectionKernels.h:249 / ConvectionKernels_API.cpp:182-199"""
     return encode("BC5S", pBlocks, options, None, out)
+
+
+def tiled_block_count(width, height):
+    L = _lib()
+    L.cvttb200_tiled_block_count.restype = ctypes.c_size_t
+    return int(L.cvttb200_tiled_block_count(int(width), int(height)))
+
+
+def tile_image(image, out=None):
+    """image: torch CUDA tensor (H, W, 4) uint8 (RGBA8) or (H, W, 4) int16 / float16 (RGBA16F).  Returns the block array the
+    encoders take, (n, 16, 4) of the same dtype, n = tiled_block_count(W, H) (etc2packer order, edges clamped)."""
+    import torch
+    assert image.is_cuda and image.dim() == 3 and image.shape[2] == 4
+    image = image.contiguous()
+    h, w = int(image.shape[0]), int(image.shape[1])
+    pixel_bytes = 4 * image.element_size()
+    n = tiled_block_count(w, h)
+    if out is None:
+        out = torch.empty((n, 16, 4), dtype=image.dtype, device=image.device)
+    L = _lib()
+    L.cvttb200_tile_image.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    with torch.cuda.device(image.device):
+        _check(L.cvttb200_tile_image(pixel_bytes, image.data_ptr(), w, h, w * pixel_bytes, out.data_ptr(), torch.cuda.current_stream(image.device).cuda_stream))
+    return out
+
+
+def untile_blocks(encoded, width, height):
+    """encoded: torch CUDA uint8 tensor (tiled_block_count, blockBytes).  Returns (ceil(H/4) * ceil(W/4), blockBytes) without the
+    padding blocks."""
+    import torch
+    assert encoded.is_cuda and encoded.dim() == 2
+    encoded = encoded.contiguous()
+    bb = int(encoded.shape[1])
+    n = ((height + 3) // 4) * ((width + 3) // 4)
+    out = torch.empty((n, bb), dtype=torch.uint8, device=encoded.device)
+    L = _lib()
+    L.cvttb200_untile_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    with torch.cuda.device(encoded.device):
+        _check(L.cvttb200_untile_blocks(encoded.data_ptr(), int(width), int(height), bb, out.data_ptr(), torch.cuda.current_stream(encoded.device).cuda_stream))
+    return out

@@ -483,6 +483,67 @@ namespace
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Image <-> block array (the step before / after the encode path; the reference's sample does it on the CPU,
+// etc2packer/etc2packer.cpp:215-248 and :277-284).  Pure data movement: this is the HBM-bound part of the pipeline.
+
+namespace
+{
+    // One thread per block row (4 pixels).  PIXEL_BYTES = 4 (RGBA8 -> PixelBlockU8) or 8 (RGBA16F -> PixelBlockF16).  Blocks are
+    // laid out like the sample packer does: rows of ceil(width / 32) groups of 8 blocks; coordinates past the edge are clamped,
+    // so the padding blocks of the last group of a row repeat the last column (they take part in the group semantics of the
+    // encoders).  Thread t of a warp handles row (t & 3) of block (t >> 2): the warp's stores are one contiguous 512 B (1 KB)
+    // run of the block array, its loads are four 128 B (256 B) row segments -- whole 32-byte sectors on both sides.
+    template<int PIXEL_BYTES>
+    __global__ void __launch_bounds__(256)
+    tile_image_kernel(const unsigned char *__restrict__ image, int width, int height, size_t pitch, int blocksPerRow, uint32_t nBlocks, uint4 *__restrict__ blocks, int vectorOK)
+    {
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t b = (uint32_t)(i >> 2);
+        const int r = (int)(i & 3);
+        if (b >= nBlocks)
+            return;
+        const int by = (int)(b / (uint32_t)blocksPerRow), bx = (int)(b % (uint32_t)blocksPerRow);
+        const int x0 = bx * 4, y = min(by * 4 + r, height - 1);
+        constexpr int kRowVec = PIXEL_BYTES / 4;      // uint4 per block row
+        uint4 *dst = blocks + ((size_t)b * 4 + r) * kRowVec;
+        const unsigned char *rowPtr = image + (size_t)y * pitch;
+        if (vectorOK && x0 + 4 <= width)
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rowPtr + (size_t)x0 * PIXEL_BYTES);
+#pragma unroll
+            for (int k = 0; k < kRowVec; k++)
+                dst[k] = __ldg(src + k);
+        }
+        else
+        {
+            uint32_t row[4 * (PIXEL_BYTES / 4)];
+            for (int c = 0; c < 4; c++)
+            {
+                const int x = min(x0 + c, width - 1);
+                const uint32_t *px = reinterpret_cast<const uint32_t *>(rowPtr + (size_t)x * PIXEL_BYTES);
+                for (int k = 0; k < PIXEL_BYTES / 4; k++)
+                    row[c * (PIXEL_BYTES / 4) + k] = px[k];
+            }
+            for (int k = 0; k < kRowVec; k++)
+                dst[k] = make_uint4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
+        }
+    }
+
+    // Drops the padding blocks: encoded rows of blocksPerRow blocks -> rows of ceil(width / 4) blocks (the payload order of the
+    // sample's KTX writer).  One thread per 8 output bytes.
+    __global__ void __launch_bounds__(256)
+    untile_blocks_kernel(const uint2 *__restrict__ encoded, int blocksPerRow, int realBlocksPerRow, int wordsPerBlock, uint64_t nWords, uint2 *__restrict__ out)
+    {
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= nWords)
+            return;
+        const uint64_t block = i / (uint64_t)wordsPerBlock, word = i % (uint64_t)wordsPerBlock;
+        const uint64_t row = block / (uint64_t)realBlocksPerRow, col = block % (uint64_t)realBlocksPerRow;
+        out[i] = __ldg(encoded + (row * (uint64_t)blocksPerRow + col) * (uint64_t)wordsPerBlock + word);
+    }
+}
+
 // =========================================================================================================
 // Host state
 
@@ -848,6 +909,63 @@ int cvttb200_get_rcp_table(float *rcp17)
 }
 
 const char *cvttb200_last_error(void) { return t_lastError.c_str(); }
+
+size_t cvttb200_tiled_block_count(int width, int height)
+{
+    if (width <= 0 || height <= 0)
+        return 0;
+    return (size_t)((height + 3) / 4) * (size_t)((width + 31) / 32) * 8;
+}
+
+int cvttb200_tile_image(int pixelBytes, const void *image, int width, int height, size_t rowPitchBytes, void *blocks, void *streamPtr)
+{
+    if (!image || !blocks || width <= 0 || height <= 0 || (pixelBytes != 4 && pixelBytes != 8) || rowPitchBytes < (size_t)width * (size_t)pixelBytes)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "bad image description");
+    if (!is_device_pointer(image) || !is_device_pointer(blocks))
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_tile_image works on device memory");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int device = 0;
+    {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "cudaGetDevice");
+    }
+    DeviceContext *ctx = nullptr;
+    int rc = get_context(device, &ctx);
+    if (rc != CVTTB200_OK)
+        return rc;
+    const int blocksPerRow = ((width + 31) / 32) * 8;
+    const size_t nBlocks = cvttb200_tiled_block_count(width, height);
+    if (nBlocks > 0xffffff00u)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "image too large for one call");
+    const int vectorOK = ((uintptr_t)image % 16 == 0) && (rowPitchBytes % 16 == 0);
+    const unsigned grid = (unsigned)((nBlocks * 4 + 255) / 256);
+    cudaStream_t stream = (cudaStream_t)streamPtr;
+    if (pixelBytes == 4)
+        tile_image_kernel<4><<<grid, 256, 0, stream>>>((const unsigned char *)image, width, height, rowPitchBytes, blocksPerRow, (uint32_t)nBlocks, (uint4 *)blocks, vectorOK);
+    else
+        tile_image_kernel<8><<<grid, 256, 0, stream>>>((const unsigned char *)image, width, height, rowPitchBytes, blocksPerRow, (uint32_t)nBlocks, (uint4 *)blocks, vectorOK);
+    g_launches++;
+    CVTT_CUDA(cudaGetLastError());
+    return CVTTB200_OK;
+}
+
+int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t blockBytes, void *out, void *streamPtr)
+{
+    if (!encoded || !out || width <= 0 || height <= 0 || (blockBytes != 8 && blockBytes != 16))
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "bad arguments");
+    if (!is_device_pointer(encoded) || !is_device_pointer(out))
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_untile_blocks works on device memory");
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int blocksPerRow = ((width + 31) / 32) * 8, realBlocksPerRow = (width + 3) / 4;
+    const int wordsPerBlock = (int)(blockBytes / 8);
+    const uint64_t nWords = (uint64_t)((height + 3) / 4) * (uint64_t)realBlocksPerRow * (uint64_t)wordsPerBlock;
+    const unsigned grid = (unsigned)((nWords + 255) / 256);
+    untile_blocks_kernel<<<grid, 256, 0, (cudaStream_t)streamPtr>>>((const uint2 *)encoded, blocksPerRow, realBlocksPerRow, wordsPerBlock, nWords, (uint2 *)out);
+    g_launches++;
+    CVTT_CUDA(cudaGetLastError());
+    return CVTTB200_OK;
+}
 
 int cvttb200_selftest(uint64_t samples, uint64_t seed, uint64_t *mismatches)
 {

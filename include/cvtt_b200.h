@@ -154,6 +154,22 @@ void cvttb200_bc7_fine_tuning_default(cvttb200_bc7_fine_tuning *params);
 size_t cvttb200_input_block_bytes(int format);
 size_t cvttb200_output_block_bytes(int format);
 
+/* ---- image <-> block array (device memory; the loops of the reference's sample packer, etc2packer/etc2packer.cpp:215-248
+ *      and :277-284, which callers otherwise run on the CPU) ------------------------------------------------------------- */
+
+/* Number of blocks cvttb200_tile_image produces: ceil(height / 4) rows of ceil(width / 32) groups of 8 blocks. */
+size_t cvttb200_tiled_block_count(int width, int height);
+
+/* Cuts a linear image (pixelBytes = 4: RGBA8 -> PixelBlockU8, 8: RGBA16F -> PixelBlockF16; rows rowPitchBytes apart) into the
+ * block array the encoders take: row-major 4x4 blocks, 8 horizontally consecutive blocks per reference call, coordinates past
+ * the right / bottom edge clamped to the last column / row (so the padding blocks of a row's last group repeat the edge, exactly
+ * like the sample packer).  `image` and `blocks` are device pointers; the work is enqueued on `stream`. */
+int cvttb200_tile_image(int pixelBytes, const void *image, int width, int height, size_t rowPitchBytes, void *blocks, void *stream);
+
+/* Inverse bookkeeping for encoded data: drops the padding blocks of every row (rows of ceil(width / 32) * 8 encoded blocks ->
+ * rows of ceil(width / 4) blocks, the order a KTX / DDS payload uses).  blockBytes is 8 or 16.  Device pointers. */
+int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t blockBytes, void *out, void *stream);
+
 /* ---- the hot path ---------------------------------------------------------------------------------------- */
 
 /* Encodes nBlocks (a multiple of 8) blocks.  `blocks` and `out` may each be host memory (pageable or pinned) or
