@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libcvtt_b200.so")
 
 SOURCES = ["cvtt_b200.cu", "bc7_host.cpp", "bc6h_host.cpp", "etc_host.cpp", "s3tc_host.cpp"]
-HEADERS = ["cvtt_common.cuh", "bc7_core.cuh", "bc7_host.h", "bc7_tables.inc", "bc6h_core.cuh", "bc6h_host.h", "bc6h_tables.inc", "etc_core.cuh", "etc_host.h", "etc_tables.inc", "s3tc_core.cuh", "s3tc_host.h", os.path.join("..", "..", "include", "cvtt_b200.h")]
+HEADERS = ["cvtt_common.cuh", "bc7_core.cuh", "bc7_host.h", "bc7_tables.inc", "bc6h_core.cuh", "bc6h_host.h", "bc6h_tables.inc", "etc_core.cuh", "etc_host.h", "etc_tables.inc", "etc_bt709_table.inc", "s3tc_sc_tables.inc", "s3tc_core.cuh", "s3tc_host.h", os.path.join("..", "..", "include", "cvtt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -291,7 +291,7 @@ namespace
     // Persistent kernel: the grid is sized to the device (SMs x resident CTAs), every warp walks 32-block slices of the
     // input.  One thread per block; the per-thread scratch of the differential / H-mode searches (the reference's
     // ETC2CompressionData) is a slice of one global allocation, laid out [entry][thread].
-    template<int KIND, bool UNIFORM>
+    template<int KIND, bool UNIFORM, bool BT709>
     __global__ void __launch_bounds__(kETCThreads, kETCCtasPerSM)
     etc_encode_kernel(const __grid_constant__ ETCParams P, const uint4 *__restrict__ in, uint32_t *__restrict__ out, uint32_t nBlocks, ETCScratch scratch)
     {
@@ -328,9 +328,21 @@ namespace
                 {
                     F4 p;
                     const float r = (float)(w[k] & 0xffu), g = (float)((w[k] >> 8) & 0xffu), b = (float)((w[k] >> 16) & 0xffu);
-                    p.x = UNIFORM ? r : r * P.w[0];
-                    p.y = UNIFORM ? g : g * P.w[1];
-                    p.z = UNIFORM ? b : b * P.w[2];
+                    if (BT709)
+                    {
+                        // ExtractBlocks with Flags::ETC_UseFakeBT709: the "pre-weighted" pixel is its fake-BT.709 YUV (ETC.cpp:2142-2143)
+                        float yuv[3];
+                        etc_to_bt709(r, g, b, yuv);
+                        p.x = yuv[0];
+                        p.y = yuv[1];
+                        p.z = yuv[2];
+                    }
+                    else
+                    {
+                        p.x = UNIFORM ? r : r * P.w[0];
+                        p.y = UNIFORM ? g : g * P.w[1];
+                        p.z = UNIFORM ? b : b * P.w[2];
+                    }
                     p.w = __uint_as_float(w[k]);
                     sPw[(q * 4 + k) * kETCThreads + tid] = p;
                     alpha[q * 4 + k] = (int)(w[k] >> 24);
@@ -340,9 +352,9 @@ namespace
 
             uint32_t color[2];
             if (KIND == kETCKindETC1)
-                etc1_encode_block<UNIFORM, kETCThreads>(P, c_etcTables, L, S, color);
+                etc1_encode_block<UNIFORM, BT709, kETCThreads>(P, c_etcTables, L, S, color);
             else
-                etc2_encode_block<UNIFORM, kETCThreads>(P, c_etcTables, L, S, vote, color);
+                etc2_encode_block<UNIFORM, BT709, kETCThreads>(P, c_etcTables, L, S, vote, color);
 
             if (KIND == kETCKindETC2RGBA)
             {
@@ -622,6 +634,17 @@ namespace
         int prev = 0;
         CVTT_CUDA(cudaGetDevice(&prev));
         CVTT_CUDA(cudaSetDevice(device));
+        {
+            // scratch of the BC7 / ETC launches comes from the stream-ordered pool; keep it cached between calls instead of
+            // returning it to the driver at every synchronisation
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            {
+                uint64_t threshold = ~(uint64_t)0;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+            }
+            cudaGetLastError();
+        }
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc7PackTables, &bc7_pack_tables(), sizeof(BC7PackTables)));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
@@ -629,12 +652,18 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
         CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesFast));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
@@ -752,7 +781,7 @@ namespace
     }
 
     template<int KIND>
-    int launch_etc_color(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const ETCParams &P, bool uniform, cudaStream_t stream)
+    int launch_etc_color(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const ETCParams &P, bool uniform, bool bt709, cudaStream_t stream)
     {
         // resident threads: the whole device, or fewer for small inputs
         const size_t maxCtas = (size_t)ctx.numSMs * kETCCtasPerSM;
@@ -762,10 +791,19 @@ namespace
         CVTT_CUDA(cudaMallocAsync(&dScratch, etc_scratch_bytes(threads), stream));
         ETCScratch S;
         etc_scratch_layout(S, dScratch, threads);
-        if (uniform)
-            etc_encode_kernel<KIND, true><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+        const uint4 *in = (const uint4 *)dIn;
+        uint32_t *out = (uint32_t *)dOut;
+        if (bt709)
+        {
+            if (uniform)
+                etc_encode_kernel<KIND, true, true><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks, S);
+            else
+                etc_encode_kernel<KIND, false, true><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks, S);
+        }
+        else if (uniform)
+            etc_encode_kernel<KIND, true, false><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks, S);
         else
-            etc_encode_kernel<KIND, false><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, (const uint4 *)dIn, (uint32_t *)dOut, (uint32_t)nBlocks, S);
+            etc_encode_kernel<KIND, false, false><<<grid, kETCThreads, kETCSmemBytes, stream>>>(P, in, out, (uint32_t)nBlocks, S);
         g_launches++;
         CVTT_CUDA(cudaGetLastError());
         CVTT_CUDA(cudaFreeAsync(dScratch, stream));
@@ -789,16 +827,14 @@ namespace
             CVTT_CUDA(cudaGetLastError());
             return CVTTB200_OK;
         }
-        if (options.flags & kFlag_ETC_UseFakeBT709)
-            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::ETC_UseFakeBT709 is not implemented yet");
         ETCParams P;
         etc_fill_params(P, options);
-        const bool uniform = (options.flags & kFlag_Uniform) != 0;
+        const bool uniform = (options.flags & kFlag_Uniform) != 0, bt709 = (options.flags & kFlag_ETC_UseFakeBT709) != 0;
         switch (format)
         {
-        case CVTTB200_ETC1: return launch_etc_color<kETCKindETC1>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
-        case CVTTB200_ETC2: return launch_etc_color<kETCKindETC2>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
-        case CVTTB200_ETC2_RGBA: return launch_etc_color<kETCKindETC2RGBA>(ctx, dIn, nBlocks, dOut, P, uniform, stream);
+        case CVTTB200_ETC1: return launch_etc_color<kETCKindETC1>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
+        case CVTTB200_ETC2: return launch_etc_color<kETCKindETC2>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
+        case CVTTB200_ETC2_RGBA: return launch_etc_color<kETCKindETC2RGBA>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
         default: return fail(CVTTB200_ERR_UNSUPPORTED, "ETC2 punch-through alpha is not implemented yet");
         }
     }

@@ -77,11 +77,37 @@ namespace cvttb200
 
     CVTT_HD int etc_px(const F4 &p, int ch) { return (int)((as_uint(p.w) >> (8 * ch)) & 0xffu); }
 
-    // ComputeErrorUniform (ETC.cpp:59-71) / ComputeErrorWeighted (:73-80).  cw = (float)colour * weight per channel.
-    template<bool UNIFORM>
+#ifndef CVTT_SC_QUALIFIER
+#if defined(__CUDACC__)
+#define CVTT_SC_QUALIFIER static __device__ const
+#else
+#define CVTT_SC_QUALIFIER static const
+#endif
+#endif
+#if defined(__CUDACC__) || defined(CVTT_HOSTSIM)
+#include "etc_bt709_table.inc"
+#define CVTT_HAVE_BT709_TABLE 1
+#endif
+
+    // ConvertToFakeBT709, ETC.cpp:2344-2353
+    CVTT_HD void etc_to_bt709(float r, float g, float b, float *yuv)
+    {
+        yuv[0] = fadd(fadd(fmul(r, 0.368233989135369f), fmul(g, 1.23876274963149f)), fmul(b, 0.125054068802017f));
+        yuv[1] = fsub(fsub(fmul(r, 0.5f), fmul(g, 0.4541529f)), fmul(b, 0.04584709f));
+        yuv[2] = fadd(fsub(fmul(r, -0.081014709086133f), fmul(g, 0.272538676238785f)), fmul(b, 0.353553390593274f));
+    }
+
+    // ComputeErrorUniform (ETC.cpp:59-71) / ComputeErrorWeighted (:73-80) / ComputeErrorFakeBT709 (:82-92).
+    // cw = what etc_weigh made of the candidate colour: (float)colour * weight, or its fake-BT.709 YUV.
+    template<bool UNIFORM, bool BT709>
     CVTT_HD float etc_error(const F4 &p, const int *c, const float *cw)
     {
-        if (UNIFORM)
+        if (BT709)
+        {
+            const float dy = fsub(cw[0], p.x), du = fsub(cw[1], p.y), dv = fsub(cw[2], p.z);
+            return fadd(fadd(fmul(dy, dy), fmul(du, du)), fmul(dv, dv));
+        }
+        else if (UNIFORM)
         {
             const float d0 = (float)(etc_px(p, 0) - c[0]), d1 = (float)(etc_px(p, 1) - c[1]), d2 = (float)(etc_px(p, 2) - c[2]);
             return fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fmul(d2, d2));
@@ -93,12 +119,108 @@ namespace cvttb200
         }
     }
 
-    template<bool UNIFORM>
+    template<bool UNIFORM, bool BT709>
     CVTT_HD void etc_weigh(const ETCParams &P, const int *c, float *cw)
     {
-        if (!UNIFORM)
+        if (BT709)
+            etc_to_bt709((float)c[0], (float)c[1], (float)c[2], cw);
+        else if (!UNIFORM)
             for (int ch = 0; ch < 3; ch++)
                 cw[ch] = fmul((float)c[ch], P.w[ch]);
+    }
+
+    // ResolveTHFakeBT709Rounding (ETC.cpp:2301-2342) and the shared tail of ResolveHalfBlockFakeBT709RoundingAccurate
+    // (:2197-2237): pick the octant of (low, high) unquantised values whose YUV is closest to the target's.  The reference's
+    // error expression adds delta[1] twice instead of squaring it; reproduced.
+    CVTT_HD int etc_bt709_best_octant(const float *low, const float *high, const float *targetYUV)
+    {
+        float bestError = FLT_MAX;
+        int bestOctant = 0;
+        for (int octant = 0; octant < 8; octant++)
+        {
+            float yuv[3];
+            etc_to_bt709((octant & 1) ? high[0] : low[0], (octant & 2) ? high[1] : low[1], (octant & 4) ? high[2] : low[2], yuv);
+            const float d0 = fsub(yuv[0], targetYUV[0]), d1 = fsub(yuv[1], targetYUV[1]), d2 = fsub(yuv[2], targetYUV[2]);
+            const float error = fadd(fadd(fadd(fmul(d0, d0), d1), d1), fmul(d2, d2));
+            if (error < bestError)
+                bestOctant = octant;
+            bestError = sse_min(error, bestError);
+        }
+        return bestOctant;
+    }
+
+    CVTT_HD void etc_resolve_th_bt709(int *quantized, const int *targets, int granularity)
+    {
+        float low[3], high[3], targetYUV[3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const int unq = (quantized[ch] << 4) | quantized[ch];
+            const int unqNext = imin(255, unq + 17);
+            low[ch] = (float)wrap_u16(wrap_u16(unq * granularity) << 1);
+            high[ch] = (float)wrap_u16(wrap_u16(unqNext * granularity) << 1);
+        }
+        etc_to_bt709((float)targets[0], (float)targets[1], (float)targets[2], targetYUV);
+        const int octant = etc_bt709_best_octant(low, high, targetYUV);
+        for (int ch = 0; ch < 3; ch++)
+            quantized[ch] += (octant >> ch) & 1;
+    }
+
+    // ResolveHalfBlockFakeBT709RoundingAccurate / Fast (ETC.cpp:2157-2299): cu = the clamped cumulative colour of the half block
+    CVTT_HD void etc_resolve_half_block_bt709(int *quantized, const int *cu, bool differential, bool accurate)
+    {
+        if (accurate)
+        {
+            float low[3], high[3], targetYUV[3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int c = cu[ch];
+                quantized[ch] = differential ? (wrap_u16((c << 5) - c + (c >> 3)) >> 11) : (wrap_u16((c << 5) - (c << 1) + (c >> 3)) >> 12);
+                int unq, unqNext;
+                if (differential)
+                {
+                    unq = (quantized[ch] << 3) | (quantized[ch] >> 2);
+                    const int qn = imin(31, quantized[ch] + 1);
+                    unqNext = (qn << 3) | (qn >> 2);
+                }
+                else
+                {
+                    unq = (quantized[ch] << 4) | quantized[ch];
+                    unqNext = imin(255, unq + 17);
+                }
+                low[ch] = (float)(unq << 3);
+                high[ch] = (float)(unqNext << 3);
+            }
+            etc_to_bt709((float)cu[0], (float)cu[1], (float)cu[2], targetYUV);
+            const int octant = etc_bt709_best_octant(low, high, targetYUV);
+            for (int ch = 0; ch < 3; ch++)
+                quantized[ch] += (octant >> ch) & 1;
+        }
+        else
+        {
+#if defined(CVTT_HAVE_BT709_TABLE) && (defined(__CUDA_ARCH__) || defined(CVTT_HOSTSIM))
+            int fill[3];
+            for (int ch = 0; ch < 3; ch++)
+                fill[ch] = cu[ch] + (cu[ch] >> 8);
+            int lookup, base[3], upper;
+            if (differential)
+            {
+                lookup = ((fill[0] << 6) & 0xf00) | ((fill[1] << 4) & 0x0f0) | ((fill[2] >> 2) & 0x00f);
+                for (int ch = 0; ch < 3; ch++)
+                    base[ch] = fill[ch] >> 6;
+                upper = 31;
+            }
+            else
+            {
+                lookup = ((fill[0] << 5) & 0xf00) | ((fill[1] << 1) & 0x0f0) | ((fill[2] >> 3) & 0x00f);
+                for (int ch = 0; ch < 3; ch++)
+                    base[ch] = fill[ch] >> 7;
+                upper = 15;
+            }
+            const int octant = kETCFakeBT709Rounding16[lookup];
+            for (int ch = 0; ch < 3; ch++)
+                quantized[ch] = imin(base[ch] + ((octant >> ch) & 1), upper);
+#endif
+        }
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -247,18 +369,20 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // EncodePlanar, ETC.cpp:1274-1662 (RGB path)
-    template<bool UNIFORM, int STRIDE>
+    template<bool UNIFORM, bool BT709, int STRIDE>
     CVTT_HD void etc_planar(const ETCParams &P, const ETCLane<STRIDE> &L, ETCBest &best)
     {
         float totalError = 0.0f;
         int bestCoeffs[3][3];
+        float oAll[3], hAll[3], vAll[3];
         for (int ch = 0; ch < 3; ch++)
         {
             float fc = 0.0f, fh = 0.0f, fv = 0.0f, fo = 0.0f;
             for (int px = 0; px < 16; px++)
             {
                 const float x = (float)(px % 4), y = (float)(px / 4);
-                const float c = (float)etc_px(L.pw[px * STRIDE], ch);
+                const F4 pp = L.pw[px * STRIDE];
+                const float c = BT709 ? (ch == 0 ? pp.x : (ch == 1 ? pp.y : pp.z)) : (float)etc_px(pp, ch);
                 fh = fsub(fh, fmul(c, x));
                 fv = fsub(fv, fmul(c, y));
                 fo = fsub(fo, c);
@@ -276,8 +400,58 @@ namespace cvttb200
             const float g2D = fadd(fadd(gD, fmul(l2D, P.pl_elim2)), fmul(q2D, P.pl_elim1));
             float h = fdiv(fsub(0.0f, g2D), P.pl_d);
             float v = fdiv(fsub(0.0f, l2D), P.pl_k1);
-            h = fadd(fmul(h, 4.0f), o);
-            v = fadd(fmul(v, 4.0f), o);
+            oAll[ch] = o;
+            hAll[ch] = fadd(fmul(h, 4.0f), o);
+            vAll[ch] = fadd(fmul(v, 4.0f), o);
+        }
+
+        if (BT709)
+        {
+            // the fit was done in fake-BT.709 YUV; back to RGB, round to nearest, measure in YUV (ETC.cpp:1395-1455)
+            float rgbO[3], rgbH[3], rgbV[3];
+            const float *src[3] = { oAll, hAll, vAll };
+            float *dstp[3] = { rgbO, rgbH, rgbV };
+            for (int k = 0; k < 3; k++)
+            {
+                // ConvertFromFakeBT709, ETC.cpp:2355-2364
+                const float yy = fmul(src[k][0], 0.57735026466774571071f), u = src[k][1], vv = src[k][2];
+                dstp[k][0] = fadd(yy, fmul(u, 1.5748000207960953486f));
+                dstp[k][1] = fsub(fsub(yy, fmul(u, 0.46812425854364753669f)), fmul(vv, 0.26491652528157560861f));
+                dstp[k][2] = fadd(yy, fmul(vv, 2.6242146882856944069f));
+            }
+            int rec[16][3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const float fcoeffsIn[3] = { rgbO[ch], rgbH[ch], rgbV[ch] };
+                for (int c = 0; c < 3; c++)
+                {
+                    float coeff = sse_max(0.0f, fcoeffsIn[c]);
+                    if (ch == 1)
+                        coeff = sse_min(127.0f, fmul(coeff, 127.0f / 255.0f));
+                    else
+                        coeff = sse_min(63.0f, fmul(coeff, 63.0f / 255.0f));
+                    bestCoeffs[ch][c] = (int)rne(coeff);
+                }
+                const int cO = bestCoeffs[ch][0], cH = bestCoeffs[ch][1], cV = bestCoeffs[ch][2];
+                const int dO = (ch == 1) ? ((cO << 1) | (cO >> 6)) : ((cO << 2) | (cO >> 4));
+                const int dH = (ch == 1) ? ((cH << 1) | (cH >> 6)) : ((cH << 2) | (cH >> 4));
+                const int dV = (ch == 1) ? ((cV << 1) | (cV >> 6)) : ((cV << 2) | (cV >> 4));
+                const int hMinusO = dH - dO, vMinusO = dV - dO, addend = (dO << 2) + 2;
+                for (int px = 0; px < 16; px++)
+                    rec[px][ch] = imin(255, imax(0, ((px & 3) * hMinusO + (px >> 2) * vMinusO + addend) >> 2));
+            }
+            totalError = 0.0f;
+            for (int px = 0; px < 16; px++)
+            {
+                float yuv[3];
+                etc_weigh<UNIFORM, true>(P, rec[px], yuv);
+                totalError = fadd(totalError, etc_error<UNIFORM, true>(L.pw[px * STRIDE], rec[px], yuv));
+            }
+        }
+        else
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const float o = oAll[ch], h = hAll[ch], v = vAll[ch];
 
             const float fcoeffsIn[3] = { o, h, v };
             int ranges[3][2];
@@ -365,7 +539,7 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // EncodeTMode, ETC.cpp:396-647.  isolatedMask: bit px set = pixel is in the isolated cluster.
-    template<bool UNIFORM, int STRIDE, class Vote>
+    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
     CVTT_HD void etc_t_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, Vote &vote, uint32_t isolatedMask, ETCBest &best)
     {
         int isolatedTotal[3] = { 0, 0, 0 }, lineTotal[3] = { 0, 0, 0 }, numIsolated = 0;
@@ -385,24 +559,45 @@ namespace cvttb200
         for (int ch = 0; ch < 3; ch++)
             lineTotal[ch] -= isolatedTotal[ch];
         const int numLine = 16 - numIsolated;
+        const int lineDivisorV = numLine * 34, lineAddendV = (numLine << 4) | numLine;
 
         int isolatedQ[3], isolatedColor[3];
         {
             const int divisor = numIsolated * 34, addend = (numIsolated << 4) | numIsolated;
+            int targets[3];
             for (int ch = 0; ch < 3; ch++)
             {
-                const int numerator = isolatedTotal[ch] + isolatedTotal[ch] + addend;
+                const int numerator = isolatedTotal[ch] + isolatedTotal[ch] + (BT709 ? 0 : addend);
                 isolatedQ[ch] = (divisor == 0) ? 0 : (numerator / divisor);
-                isolatedColor[ch] = isolatedQ[ch] | (isolatedQ[ch] << 4);
+                targets[ch] = numerator;
             }
+            if (BT709)
+                etc_resolve_th_bt709(isolatedQ, targets, numIsolated);
+            for (int ch = 0; ch < 3; ch++)
+                isolatedColor[ch] = wrap_u16(isolatedQ[ch] | (isolatedQ[ch] << 4));
         }
         float isoW[3];
-        etc_weigh<UNIFORM>(P, isolatedColor, isoW);
+        etc_weigh<UNIFORM, BT709>(P, isolatedColor, isoW);
+
+        // packed line colour for one offset step (ETC.cpp:507-548)
+        auto lineColorAt = [&](int offs, int modifierOffset) -> int
+        {
+            int q[3], targets[3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + (BT709 ? 0 : lineAddendV) + offs * modifierOffset));
+                const int divided = (lineDivisorV == 0) ? 0 : (numerator / lineDivisorV);
+                q[ch] = imin(15, divided);
+                targets[ch] = numerator;
+            }
+            if (BT709)
+                etc_resolve_th_bt709(q, targets, numLine);
+            return q[0] | (q[1] << 5) | (q[2] << 10);
+        };
 
         bool bestIsThisMode = false;
         uint32_t bestSelectors = 0;
         int bestTable = 0, bestLineColor = 0;
-        const int lineDivisor = numLine * 34, lineAddend = (numLine << 4) | numLine;
 
         for (int table = 0; table < 8; table++)
         {
@@ -415,13 +610,7 @@ namespace cvttb200
             // first pass counts, second pass evaluates: the group maximum of the count is needed before the extra candidate
             for (int offs = -numLine; offs <= numLine; offs++)
             {
-                int packed = 0;
-                for (int ch = 0; ch < 3; ch++)
-                {
-                    const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + lineAddend + offs * modifierOffset));
-                    const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
-                    packed |= imin(15, divided) << (ch * 5);
-                }
+                const int packed = lineColorAt(offs, modifierOffset);
                 if (numUnique == 0 || packed != lastColor)
                 {
                     numUnique++;
@@ -440,13 +629,7 @@ namespace cvttb200
                 {
                     for (;;)
                     {
-                        int packed = 0;
-                        for (int ch = 0; ch < 3; ch++)
-                        {
-                            const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + lineAddend + offs * modifierOffset));
-                            const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
-                            packed |= imin(15, divided) << (ch * 5);
-                        }
+                        const int packed = lineColorAt(offs, modifierOffset);
                         offs++;
                         if (packed != lastColor)
                         {
@@ -468,19 +651,19 @@ namespace cvttb200
                     lineColors[2][ch] = imax(0, unq - modifier);
                 }
                 for (int i = 0; i < 3; i++)
-                    etc_weigh<UNIFORM>(P, lineColors[i], lineW[i]);
+                    etc_weigh<UNIFORM, false>(P, lineColors[i], lineW[i]);      // the line colours are never measured in YUV (ETC.cpp:603)
 
                 uint32_t selectors = 0;
                 float error = 0.0f;
                 for (int px = 0; px < 16; px++)
                 {
                     const F4 p = L.pw[px * STRIDE];
-                    float pixelError = etc_error<UNIFORM>(p, isolatedColor, isoW);
+                    float pixelError = etc_error<UNIFORM, BT709>(p, isolatedColor, isoW);
                     uint32_t pixelBestSelector = 0;
 #pragma unroll
                     for (int i = 0; i < 3; i++)
                     {
-                        const float e = etc_error<UNIFORM>(p, lineColors[i], lineW[i]);
+                        const float e = etc_error<UNIFORM, false>(p, lineColors[i], lineW[i]);
                         if (e < pixelError)
                             pixelBestSelector = (uint32_t)(i + 1);
                         pixelError = sse_min(e, pixelError);
@@ -510,7 +693,7 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // EncodeHMode, ETC.cpp:649-885.  groupMask: bit px set = pixel belongs to sector 1.
-    template<bool UNIFORM, int STRIDE>
+    template<bool UNIFORM, bool BT709, int STRIDE>
     CVTT_HD void etc_h_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, uint32_t groupMask, ETCBest &best)
     {
         int totals[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } }, counts[2] = { 0, 0 };
@@ -572,13 +755,13 @@ namespace cvttb200
                         colors[0][ch] = imin(255, unq + modifier);
                         colors[1][ch] = imax(0, unq - modifier);
                     }
-                    etc_weigh<UNIFORM>(P, colors[0], cw[0]);
-                    etc_weigh<UNIFORM>(P, colors[1], cw[1]);
+                    etc_weigh<UNIFORM, BT709>(P, colors[0], cw[0]);
+                    etc_weigh<UNIFORM, BT709>(P, colors[1], cw[1]);
                     uint32_t signBits = 0;
                     for (int px = 0; px < 16; px++)
                     {
                         const F4 p = L.pw[px * STRIDE];
-                        const float e0 = etc_error<UNIFORM>(p, colors[0], cw[0]), e1 = etc_error<UNIFORM>(p, colors[1], cw[1]);
+                        const float e0 = etc_error<UNIFORM, BT709>(p, colors[0], cw[0]), e1 = etc_error<UNIFORM, BT709>(p, colors[1], cw[1]);
                         if (e1 < e0)
                             signBits |= 1u << px;
                         S.hErr[(size_t)(total * 16 + px) * S.stride] = sse_min(e0, e1);
@@ -630,7 +813,7 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // TestHalfBlock, ETC.cpp:94-149
-    template<bool UNIFORM, int STRIDE>
+    template<bool UNIFORM, bool BT709, int STRIDE>
     CVTT_HD float etc_test_half_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, int flip, int sector, int packedColor, int table, bool differential, uint32_t &outSelectors)
     {
         int mod[4][3];
@@ -643,7 +826,7 @@ namespace cvttb200
                 mod[s][ch] = imin(imax(unq + T.etc1Modifiers[table][s], 0), 255);
         }
         for (int s = 0; s < 4; s++)
-            etc_weigh<UNIFORM>(P, mod[s], modW[s]);
+            etc_weigh<UNIFORM, BT709>(P, mod[s], modW[s]);
 
         uint32_t selectors = 0;
         float totalError = 0.0f;
@@ -656,7 +839,7 @@ namespace cvttb200
 #pragma unroll
             for (int s = 0; s < 4; s++)
             {
-                const float e = etc_error<UNIFORM>(p, mod[s], modW[s]);
+                const float e = etc_error<UNIFORM, BT709>(p, mod[s], modW[s]);
                 if (e < bestError)
                     bestSelector = (uint32_t)s;
                 bestError = sse_min(e, bestError);
@@ -680,7 +863,7 @@ namespace cvttb200
     }
 
     // CompressETC1BlockInternal, ETC.cpp:2624-2882.  MIN_D = 1 is the ETC2 call (differential only), 0 is ETC1.
-    template<bool UNIFORM, int MIN_D, int STRIDE>
+    template<bool UNIFORM, bool BT709, int MIN_D, int STRIDE>
     CVTT_HD void etc_etc1(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, ETCBest &best)
     {
         bool bestIsThisMode = false;
@@ -716,6 +899,15 @@ namespace cvttb200
                         for (int oi = 0; oi < numOffsets; oi++)
                         {
                             int packed = 0;
+                            if (BT709)
+                            {
+                                int cu[3], q[3];
+                                for (int ch = 0; ch < 3; ch++)
+                                    cu[ch] = imin(2040, imax(0, cumulative[sector][ch] + potentialOffsets[oi]));
+                                etc_resolve_half_block_bt709(q, cu, d == 1, (P.flags & kFlag_ETC_FakeBT709Accurate) != 0);
+                                packed = q[0] | (q[1] << 5) | (q[2] << 10);
+                            }
+                            else
                             for (int ch = 0; ch < 3; ch++)
                             {
                                 const int cu = imin(2040, imax(0, cumulative[sector][ch] + potentialOffsets[oi]));
@@ -727,7 +919,7 @@ namespace cvttb200
                             lastColor = packed;
 
                             uint32_t selectors;
-                            const float error = etc_test_half_block<UNIFORM, STRIDE>(P, T, L, flip, sector, packed, table, d == 1, selectors);
+                            const float error = etc_test_half_block<UNIFORM, BT709, STRIDE>(P, T, L, flip, sector, packed, table, d == 1, selectors);
                             if (d == 0)
                             {
                                 if (error < bestIndError[sector])
@@ -880,7 +1072,7 @@ namespace cvttb200
                             bestColors[sector] = winMeta[sector] & 0x7fff;
                             bestTables[sector] = (winMeta[sector] >> 15) & 7;
                             // the selectors are a function of (colour, table); recomputed instead of stored per attempt
-                            etc_test_half_block<UNIFORM, STRIDE>(P, T, L, flip, sector, bestColors[sector], bestTables[sector], true, bestSelectors[sector]);
+                            etc_test_half_block<UNIFORM, BT709, STRIDE>(P, T, L, flip, sector, bestColors[sector], bestTables[sector], true, bestSelectors[sector]);
                         }
                     }
                 }
@@ -899,7 +1091,7 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // CompressETC2Block without punch-through (ETC.cpp:1664-1887): chroma split, then planar, T, T, H, differential
-    template<bool UNIFORM, int STRIDE, class Vote>
+    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
     CVTT_HD void etc2_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, Vote &vote, uint32_t out[2])
     {
         ETCBest best;
@@ -907,7 +1099,7 @@ namespace cvttb200
         best.hi = best.lo = 0;
 
         cta_sync();
-        etc_planar<UNIFORM, STRIDE>(P, L, best);
+        etc_planar<UNIFORM, BT709, STRIDE>(P, L, best);
 
         float chromaDelta[16][2];
         if (UNIFORM)
@@ -966,24 +1158,24 @@ namespace cvttb200
             if (fadd(fmul(chromaDelta[px][0], dx), fmul(chromaDelta[px][1], dy)) < 0.0f)
                 sectorMask |= 1u << px;
 
-        etc_t_mode<UNIFORM, STRIDE>(P, T, L, vote, sectorMask, best);
+        etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
         sectorMask ^= 0xffffu;
-        etc_t_mode<UNIFORM, STRIDE>(P, T, L, vote, sectorMask, best);
-        etc_h_mode<UNIFORM, STRIDE>(P, T, L, S, sectorMask, best);
-        etc_etc1<UNIFORM, 1, STRIDE>(P, T, L, S, best);
+        etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
+        etc_h_mode<UNIFORM, BT709, STRIDE>(P, T, L, S, sectorMask, best);
+        etc_etc1<UNIFORM, BT709, 1, STRIDE>(P, T, L, S, best);
 
         out[0] = best.hi;
         out[1] = best.lo;
     }
 
     // CompressETC1Block, ETC.cpp:2112-2126
-    template<bool UNIFORM, int STRIDE>
+    template<bool UNIFORM, bool BT709, int STRIDE>
     CVTT_HD void etc1_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, uint32_t out[2])
     {
         ETCBest best;
         best.error = FLT_MAX;
         best.hi = best.lo = 0;
-        etc_etc1<UNIFORM, 0, STRIDE>(P, T, L, S, best);
+        etc_etc1<UNIFORM, BT709, 0, STRIDE>(P, T, L, S, best);
         out[0] = best.hi;
         out[1] = best.lo;
     }

@@ -16,7 +16,7 @@ namespace
         HostVote vote;
         vote.g = shared;
         const ETCTables &T = etc_tables();
-        const bool uniform = (P->flags & kFlag_Uniform) != 0;
+        const bool uniform = (P->flags & kFlag_Uniform) != 0, bt709 = (P->flags & kFlag_ETC_UseFakeBT709) != 0;
         std::vector<char> scratchMem(etc_scratch_bytes(1));
         ETCScratch S;
         etc_scratch_layout(S, scratchMem.data(), 1);
@@ -32,9 +32,18 @@ namespace
                 for (int px = 0; px < 16; px++)
                 {
                     const uint8_t *s = src + px * 4;
-                    pw[px].x = uniform ? (float)s[0] : (float)s[0] * P->w[0];
-                    pw[px].y = uniform ? (float)s[1] : (float)s[1] * P->w[1];
-                    pw[px].z = uniform ? (float)s[2] : (float)s[2] * P->w[2];
+                    if (bt709)
+                    {
+                        float yuv[3];
+                        etc_to_bt709((float)s[0], (float)s[1], (float)s[2], yuv);
+                        pw[px].x = yuv[0]; pw[px].y = yuv[1]; pw[px].z = yuv[2];
+                    }
+                    else
+                    {
+                        pw[px].x = uniform ? (float)s[0] : (float)s[0] * P->w[0];
+                        pw[px].y = uniform ? (float)s[1] : (float)s[1] * P->w[1];
+                        pw[px].z = uniform ? (float)s[2] : (float)s[2] * P->w[2];
+                    }
                     pw[px].w = as_float((uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24));
                     a[px] = s[3];
                 }
@@ -42,11 +51,19 @@ namespace
                 L.pw = pw;
                 if (kind == 0)
                 {
-                    if (uniform) etc1_encode_block<true, 1>(*P, T, L, S, color); else etc1_encode_block<false, 1>(*P, T, L, S, color);
+                    if (bt709)
+                    {
+                        if (uniform) etc1_encode_block<true, true, 1>(*P, T, L, S, color); else etc1_encode_block<false, true, 1>(*P, T, L, S, color);
+                    }
+                    else if (uniform) etc1_encode_block<true, false, 1>(*P, T, L, S, color); else etc1_encode_block<false, false, 1>(*P, T, L, S, color);
                 }
                 else if (kind == 1 || kind == 2)
                 {
-                    if (uniform) etc2_encode_block<true, 1>(*P, T, L, S, vote, color); else etc2_encode_block<false, 1>(*P, T, L, S, vote, color);
+                    if (bt709)
+                    {
+                        if (uniform) etc2_encode_block<true, true, 1>(*P, T, L, S, vote, color); else etc2_encode_block<false, true, 1>(*P, T, L, S, vote, color);
+                    }
+                    else if (uniform) etc2_encode_block<true, false, 1>(*P, T, L, S, vote, color); else etc2_encode_block<false, false, 1>(*P, T, L, S, vote, color);
                 }
                 if (kind == 2 || kind == 3)
                     etc_alpha_encode_block(T, a, false, false, alpha);

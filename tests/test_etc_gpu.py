@@ -65,15 +65,23 @@ def test_ultra_preset_is_accepted(reference):
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("fmt", ["ETC1", "ETC2", "ETC2_RGBA"])
+@pytest.mark.parametrize("flags", [0x508, 0xD08, 0x708])
+def test_fake_bt709_against_reference(reference, fmt, flags):
+    """Flags::ETC_UseFakeBT709 (fast / accurate rounding, with Uniform)"""
+    blocks = synth.random_blocks_rgba8(4096 + 8, seed=102)
+    o = api.Options()
+    o.flags = flags
+    want = reference.encode(fmt, blocks, _opt_bytes(o), threads=0)
+    got = api.encode(fmt, blocks, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
 def test_unsupported_variants_fail_loudly():
     blocks = synth.random_blocks_rgba8(8, seed=1)
     o = api.Options()
     with pytest.raises(api.CvttError) as e:
         api.encode("ETC2_PUNCHTHROUGH", blocks, o)
-    assert e.value.status == -2
-    o.flags |= 0x400
-    with pytest.raises(api.CvttError) as e:
-        api.encode("ETC2", blocks, o)
     assert e.value.status == -2
 
 

@@ -92,3 +92,5 @@ save("bc5u_random_seeds2", "BC5U", rba, options(seeds=2, refine_iic=3))
 save("bc5s_random", "BC5S", rba, options())
 save("bc1_random_alpha_exhaustive", "BC1", rba[:128], options(flags=0x188))
 save("bc3_random_exhaustive_uniform", "BC3", rba[:128], options(flags=0x288))
+save("etc2rgba_random_bt709", "ETC2_RGBA", rb, options(flags=0x508))
+save("etc1_random_bt709_accurate_uniform", "ETC1", rb, options(flags=0xF08))
