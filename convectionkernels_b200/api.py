@@ -250,6 +250,12 @@ def EncodeETC2RGBA(pBlocks, options, compressionData=None, out=None):
     return encode("ETC2_RGBA", pBlocks, options, None, out)
 
 
+def EncodeETC2PunchthroughAlpha(pBlocks, options, compressionData=None, out=None):
+    """cvtt::Kernels::EncodeETC2PunchthroughAlpha, reference ConvectionKernels.h:255 / ConvectionKernels_API.cpp:231-244: pixels whose
+    alpha is below options.threshold become the transparent index"""
+    return encode("ETC2_PUNCHTHROUGH", pBlocks, options, None, out)
+
+
 def EncodeETC2Alpha(pBlocks, options, out=None):
     """cvtt::Kernels::EncodeETC2Alpha, reference ConvectionKernels.h:258 / ConvectionKernels_API.cpp:245-255"""
     return encode("ETC2_ALPHA", pBlocks, options, None, out)

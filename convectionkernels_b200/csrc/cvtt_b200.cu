@@ -286,7 +286,7 @@ namespace
         }
     };
 
-    enum { kETCKindETC1 = 0, kETCKindETC2 = 1, kETCKindETC2RGBA = 2 };
+    enum { kETCKindETC1 = 0, kETCKindETC2 = 1, kETCKindETC2RGBA = 2, kETCKindETC2Punchthrough = 3 };
 
     // Persistent kernel: the grid is sized to the device (SMs x resident CTAs), every warp walks 32-block slices of the
     // input.  One thread per block; the per-thread scratch of the differential / H-mode searches (the reference's
@@ -316,6 +316,7 @@ namespace
             const uint32_t block = tileBase + tid;
             const bool active = block < nBlocks;
             int alpha[16];
+            uint32_t transparentMask = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++)
             {
@@ -344,8 +345,15 @@ namespace
                         p.z = UNIFORM ? b : b * P.w[2];
                     }
                     p.w = __uint_as_float(w[k]);
-                    sPw[(q * 4 + k) * kETCThreads + tid] = p;
                     alpha[q * 4 + k] = (int)(w[k] >> 24);
+                    if (KIND == kETCKindETC2Punchthrough && alpha[q * 4 + k] < P.punchThreshold)
+                    {
+                        // CompressETC2Block zeroes the transparent pixels, ETC.cpp:1705-1718
+                        transparentMask |= 1u << (q * 4 + k);
+                        p.x = p.y = p.z = 0.0f;
+                        p.w = __uint_as_float(w[k] & 0xff000000u);
+                    }
+                    sPw[(q * 4 + k) * kETCThreads + tid] = p;
                 }
             }
             __syncwarp();
@@ -353,6 +361,8 @@ namespace
             uint32_t color[2];
             if (KIND == kETCKindETC1)
                 etc1_encode_block<UNIFORM, BT709, kETCThreads>(P, c_etcTables, L, S, color);
+            else if (KIND == kETCKindETC2Punchthrough)
+                etc2_punchthrough_encode_block<UNIFORM, BT709, kETCThreads>(P, c_etcTables, L, S, vote, transparentMask, color);
             else
                 etc2_encode_block<UNIFORM, BT709, kETCThreads>(P, c_etcTables, L, S, vote, color);
 
@@ -664,6 +674,10 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesFast));
         CVTT_CUDA(cudaFuncSetAttribute(bc6h_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC6HSmemBytesSlow));
@@ -835,7 +849,8 @@ namespace
         case CVTTB200_ETC1: return launch_etc_color<kETCKindETC1>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
         case CVTTB200_ETC2: return launch_etc_color<kETCKindETC2>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
         case CVTTB200_ETC2_RGBA: return launch_etc_color<kETCKindETC2RGBA>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
-        default: return fail(CVTTB200_ERR_UNSUPPORTED, "ETC2 punch-through alpha is not implemented yet");
+        case CVTTB200_ETC2_PUNCHTHROUGH: return launch_etc_color<kETCKindETC2Punchthrough>(ctx, dIn, nBlocks, dOut, P, uniform, bt709, stream);
+        default: return fail(CVTTB200_ERR_BAD_ARGUMENT, "not an ETC format");
         }
     }
 
@@ -1095,8 +1110,6 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
     const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
     if (!inBytes)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
-    if (format == CVTTB200_ETC2_PUNCHTHROUGH)
-        return fail(CVTTB200_ERR_UNSUPPORTED, "ETC2 punch-through alpha is not implemented by this build (no CPU fallback exists)");
     if (format == CVTTB200_BC7 && !plan)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
     if (nBlocks == 0)

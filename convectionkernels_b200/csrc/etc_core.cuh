@@ -42,6 +42,7 @@ namespace cvttb200
         // scalar constants of EncodePlanar's 3x3 solve (ETC.cpp:1294-1386), identical for every block and channel
         float pl_r0to1, pl_r0to2, pl_r1to2, pl_n2, pl_r2to1, pl_elim2, pl_elim1, pl_d, pl_k1;
         uint32_t flags;
+        int punchThreshold;         // CompressETC2Block, ETC.cpp:1672-1675: pixels with alpha below this are transparent
     };
 
     struct ETCTables
@@ -324,7 +325,7 @@ namespace cvttb200
         return flip ? (sector * 8 + i) : ((i >> 1) * 4 + sector * 2 + (i & 1));
     }
 
-    CVTT_HD void etc_emit_etc1(ETCBest &best, int flip, int d, const int colors[2][3], const int *tables, const uint32_t *selectors)
+    CVTT_HD void etc_emit_etc1(ETCBest &best, int flip, int d, const int colors[2][3], const int *tables, const uint32_t *selectors, bool transparent = false)
     {
         uint32_t highBits = 0, lowBits = 0;
         if (d == 0)
@@ -347,7 +348,8 @@ namespace cvttb200
         }
         highBits |= (uint32_t)tables[0] << 5;
         highBits |= (uint32_t)tables[1] << 2;
-        highBits |= (uint32_t)d << 1;
+        if (!transparent)
+            highBits |= (uint32_t)d << 1;
         highBits |= (uint32_t)flip;
         uint32_t codes = 0;     // 2 bits per block pixel
         for (int sector = 0; sector < 2; sector++)
@@ -862,6 +864,116 @@ namespace cvttb200
         return true;
     }
 
+    // FindBestDifferentialCombination, ETC.cpp:219-362, for one lane.  The attempts of the two half blocks are in the scratch
+    // arrays (numAttempts[sector] entries each: error, colour | table << 15).  winMeta receives the pair to encode, selMeta the
+    // attempts whose selectors go with it (they differ only when a transparent sector 0 borrows sector 1's colour); both stay
+    // -1 when no legal pair beats bestErrorIn.
+    CVTT_HD void etc_find_best_differential(const ETCScratch &S, const int *numAttempts, bool canIgnore0, float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
+    {
+        const float blockBestTotalError = bestErrorIn;
+        float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
+        uint32_t bestDiffMeta[2] = { 0, 0 };
+        int kept[2] = { 0, 0 };
+        for (int sector = 0; sector < 2; sector++)
+            for (int i = 0; i < numAttempts[sector]; i++)
+            {
+                const size_t slot = (size_t)(sector * kETCMaxAttempts + i) * S.stride;
+                const float error = S.drsErr[slot];
+                const uint32_t meta = S.drsMeta[slot];
+                if (error < bestDiffErrors[sector])
+                {
+                    bestDiffErrors[sector] = error;
+                    bestDiffMeta[sector] = meta;
+                }
+                // stable compaction of the attempts the slow path may look at (error < blockBestTotalError)
+                if (error < blockBestTotalError)
+                {
+                    const size_t dst = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
+                    S.drsErr[dst] = error;
+                    S.drsMeta[dst] = meta;
+                    kept[sector]++;
+                }
+            }
+
+        if (fadd(bestDiffErrors[0], bestDiffErrors[1]) < blockBestTotalError)
+        {
+            // with punch-through a fully transparent sector 0 takes the colour of sector 1 and makes any pair legal (ETC.cpp:251-260)
+            uint32_t pairMeta0 = bestDiffMeta[0];
+            if (canIgnore0)
+                pairMeta0 = (bestDiffMeta[0] & ~0x7fffu) | (bestDiffMeta[1] & 0x7fffu);
+            if (canIgnore0 || etc_differential_legal((int)(pairMeta0 & 0x7fffu), (int)(bestDiffMeta[1] & 0x7fffu)))
+            {
+                winMeta[0] = (int)pairMeta0;
+                winMeta[1] = (int)bestDiffMeta[1];
+                selMeta[0] = (int)bestDiffMeta[0];
+                selMeta[1] = (int)bestDiffMeta[1];
+                winTotal = fadd(bestDiffErrors[0], bestDiffErrors[1]);
+            }
+            else
+            {
+                // The reference sorts both lists by (error, index) and scans pairs.  Equivalent without a sort:
+                // walk sector 0 in that order by repeated "next larger key" selection; for each entry the partner
+                // is the smallest-key entry of sector 1 whose colour makes a legal differential pair.
+                float current = blockBestTotalError;
+                float lastErr = -1.0f;
+                int lastIdx = -1;
+                for (;;)
+                {
+                    int i0 = -1;
+                    float e0 = 0.0f;
+                    uint32_t m0 = 0;
+                    for (int i = 0; i < kept[0]; i++)
+                    {
+                        const size_t slot = (size_t)i * S.stride;
+                        const float e = S.drsErr[slot];
+                        const bool after = (e > lastErr) || (e == lastErr && i > lastIdx);
+                        if (after && (i0 < 0 || e < e0))
+                        {
+                            i0 = i;
+                            e0 = e;
+                            m0 = S.drsMeta[slot];
+                        }
+                    }
+                    if (i0 < 0)
+                        break;
+                    lastErr = e0;
+                    lastIdx = i0;
+                    if (e0 >= current)
+                        break;
+                    const float maxError1 = fsub(current, e0);
+                    if (maxError1 < bestDiffErrors[1])
+                        break;
+                    // the scan of sector 1 stops at the first entry with error >= maxError1; before that the first legal one wins
+                    int j1 = -1;
+                    float e1 = 0.0f;
+                    uint32_t m1 = 0;
+                    for (int j = 0; j < kept[1]; j++)
+                    {
+                        const size_t slot = (size_t)(kETCMaxAttempts + j) * S.stride;
+                        const float e = S.drsErr[slot];
+                        if (e < maxError1 && (j1 < 0 || e < e1))
+                        {
+                            const uint32_t m = S.drsMeta[slot];
+                            if (etc_differential_legal((int)(m0 & 0x7fffu), (int)(m & 0x7fffu)))
+                            {
+                                j1 = j;
+                                e1 = e;
+                                m1 = m;
+                            }
+                        }
+                    }
+                    if (j1 >= 0)
+                    {
+                        current = fadd(e0, e1);
+                        winMeta[0] = selMeta[0] = (int)m0;
+                        winMeta[1] = selMeta[1] = (int)m1;
+                        winTotal = current;
+                    }
+                }
+            }
+        }
+    }
+
     // CompressETC1BlockInternal, ETC.cpp:2624-2882.  MIN_D = 1 is the ETC2 call (differential only), 0 is ETC1.
     template<bool UNIFORM, bool BT709, int MIN_D, int STRIDE>
     CVTT_HD void etc_etc1(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, ETCBest &best)
@@ -962,105 +1074,9 @@ namespace cvttb200
                 else
                 {
                     cta_sync();
-                    // FindBestDifferentialCombination, ETC.cpp:219-362 (canIgnoreSector is false without punch-through)
-                    const float blockBestTotalError = best.error;
-                    float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
-                    uint32_t bestDiffMeta[2] = { 0, 0 };
-                    int kept[2] = { 0, 0 };
-                    for (int sector = 0; sector < 2; sector++)
-                        for (int i = 0; i < numAttempts[sector]; i++)
-                        {
-                            const size_t slot = (size_t)(sector * kETCMaxAttempts + i) * S.stride;
-                            const float error = S.drsErr[slot];
-                            const uint32_t meta = S.drsMeta[slot];
-                            if (error < bestDiffErrors[sector])
-                            {
-                                bestDiffErrors[sector] = error;
-                                bestDiffMeta[sector] = meta;
-                            }
-                            // stable compaction of the attempts the slow path may look at (error < blockBestTotalError)
-                            if (error < blockBestTotalError)
-                            {
-                                const size_t dst = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
-                                S.drsErr[dst] = error;
-                                S.drsMeta[dst] = meta;
-                                kept[sector]++;
-                            }
-                        }
-
-                    int winMeta[2] = { -1, -1 };
+                    int winMeta[2] = { -1, -1 }, selMeta[2] = { -1, -1 };
                     float winTotal = 0.0f;
-                    if (fadd(bestDiffErrors[0], bestDiffErrors[1]) < blockBestTotalError)
-                    {
-                        if (etc_differential_legal((int)(bestDiffMeta[0] & 0x7fffu), (int)(bestDiffMeta[1] & 0x7fffu)))
-                        {
-                            winMeta[0] = (int)bestDiffMeta[0];
-                            winMeta[1] = (int)bestDiffMeta[1];
-                            winTotal = fadd(bestDiffErrors[0], bestDiffErrors[1]);
-                        }
-                        else
-                        {
-                            // The reference sorts both lists by (error, index) and scans pairs.  Equivalent without a sort:
-                            // walk sector 0 in that order by repeated "next larger key" selection; for each entry the partner
-                            // is the smallest-key entry of sector 1 whose colour makes a legal differential pair.
-                            float current = blockBestTotalError;
-                            float lastErr = -1.0f;
-                            int lastIdx = -1;
-                            for (;;)
-                            {
-                                int i0 = -1;
-                                float e0 = 0.0f;
-                                uint32_t m0 = 0;
-                                for (int i = 0; i < kept[0]; i++)
-                                {
-                                    const size_t slot = (size_t)i * S.stride;
-                                    const float e = S.drsErr[slot];
-                                    const bool after = (e > lastErr) || (e == lastErr && i > lastIdx);
-                                    if (after && (i0 < 0 || e < e0))
-                                    {
-                                        i0 = i;
-                                        e0 = e;
-                                        m0 = S.drsMeta[slot];
-                                    }
-                                }
-                                if (i0 < 0)
-                                    break;
-                                lastErr = e0;
-                                lastIdx = i0;
-                                if (e0 >= current)
-                                    break;
-                                const float maxError1 = fsub(current, e0);
-                                if (maxError1 < bestDiffErrors[1])
-                                    break;
-                                // the scan of sector 1 stops at the first entry with error >= maxError1; before that the first legal one wins
-                                int j1 = -1;
-                                float e1 = 0.0f;
-                                uint32_t m1 = 0;
-                                for (int j = 0; j < kept[1]; j++)
-                                {
-                                    const size_t slot = (size_t)(kETCMaxAttempts + j) * S.stride;
-                                    const float e = S.drsErr[slot];
-                                    if (e < maxError1 && (j1 < 0 || e < e1))
-                                    {
-                                        const uint32_t m = S.drsMeta[slot];
-                                        if (etc_differential_legal((int)(m0 & 0x7fffu), (int)(m & 0x7fffu)))
-                                        {
-                                            j1 = j;
-                                            e1 = e;
-                                            m1 = m;
-                                        }
-                                    }
-                                }
-                                if (j1 >= 0)
-                                {
-                                    current = fadd(e0, e1);
-                                    winMeta[0] = (int)m0;
-                                    winMeta[1] = (int)m1;
-                                    winTotal = current;
-                                }
-                            }
-                        }
-                    }
+                    etc_find_best_differential(S, numAttempts, false, best.error, winMeta, selMeta, winTotal);
                     if (winMeta[0] >= 0)
                     {
                         bestIsThisMode = true;
@@ -1072,7 +1088,7 @@ namespace cvttb200
                             bestColors[sector] = winMeta[sector] & 0x7fff;
                             bestTables[sector] = (winMeta[sector] >> 15) & 7;
                             // the selectors are a function of (colour, table); recomputed instead of stored per attempt
-                            etc_test_half_block<UNIFORM, BT709, STRIDE>(P, T, L, flip, sector, bestColors[sector], bestTables[sector], true, bestSelectors[sector]);
+                            etc_test_half_block<UNIFORM, BT709, STRIDE>(P, T, L, flip, sector, selMeta[sector] & 0x7fff, bestTables[sector], true, bestSelectors[sector]);
                         }
                     }
                 }
@@ -1090,17 +1106,357 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // CompressETC2Block without punch-through (ETC.cpp:1664-1887): chroma split, then planar, T, T, H, differential
-    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
-    CVTT_HD void etc2_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, Vote &vote, uint32_t out[2])
+    // Punch-through alpha (EncodeETC2PunchthroughAlpha).  transparentMask: bit px set = alpha below the threshold; the lane's
+    // stored pixels are already zero there (CompressETC2Block, ETC.cpp:1706-1719).
+
+    // TestHalfBlockPunchthrough, ETC.cpp:151-217
+    template<bool UNIFORM, bool BT709, int STRIDE>
+    CVTT_HD float etc_test_half_block_punchthrough(const ETCParams &P, const ETCLane<STRIDE> &L, int flip, int sector, int packedColor, int modifier, uint32_t transparentMask, uint32_t &outSelectors)
     {
-        ETCBest best;
-        best.error = FLT_MAX;
-        best.hi = best.lo = 0;
+        int mod[3][3];
+        float modW[3][3];
+        for (int ch = 0; ch < 3; ch++)
+        {
+            const int q = (packedColor >> (ch * 5)) & 31;
+            const int unq = (q << 3) | (q >> 2);
+            mod[0][ch] = imax(unq, modifier) - modifier;
+            mod[1][ch] = unq;
+            mod[2][ch] = imin(unq + modifier, 255);
+        }
+        for (int s = 0; s < 3; s++)
+            etc_weigh<UNIFORM, BT709>(P, mod[s], modW[s]);
+        uint32_t selectors = 0;
+        float totalError = 0.0f;
+        for (int px = 0; px < 8; px++)
+        {
+            const int bp = etc_flip_pixel(flip, sector, px);
+            const F4 p = L.pw[bp * STRIDE];
+            float bestError = FLT_MAX;
+            uint32_t bestSelector = 0;
+            for (int s = 0; s < 3; s++)
+            {
+                const float e = etc_error<UNIFORM, BT709>(p, mod[s], modW[s]);
+                if (e < bestError)
+                    bestSelector = (uint32_t)s;
+                bestError = sse_min(e, bestError);
+            }
+            // table order vs encoding order: the transparent code is 1, the colours are 0, 2, 3 (ETC.cpp:199-208)
+            bestSelector = (bestSelector << 1) < 3u ? (bestSelector << 1) : 3u;
+            if ((transparentMask >> bp) & 1)
+            {
+                bestError = 0.0f;
+                bestSelector = 1;
+            }
+            totalError = fadd(totalError, bestError);
+            selectors |= bestSelector << (px * 2);
+        }
+        outSelectors = selectors;
+        return totalError;
+    }
 
-        cta_sync();
-        etc_planar<UNIFORM, BT709, STRIDE>(P, L, best);
+    // CompressETC1PunchthroughBlockInternal, ETC.cpp:2885-3080.  Quirks kept: the per-sector count the reference calls
+    // "sectorNumOpaque" counts the *transparent* pixels (:2954-2956), and only sector 0 can ever be ignored (:2944).
+    template<bool UNIFORM, bool BT709, int STRIDE>
+    CVTT_HD void etc_etc1_punchthrough(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, uint32_t transparentMask, ETCBest &best)
+    {
+        bool bestIsThisMode = false;
+        int bestColors[2] = { 0, 0 }, bestTables[2] = { 0, 0 }, bestFlip = 0;
+        uint32_t bestSelectors[2] = { 0, 0 };
 
+        for (int flip = 0; flip < 2; flip++)
+        {
+            int cumulative[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } }, numT[2] = { 0, 0 };
+            for (int sector = 0; sector < 2; sector++)
+                for (int px = 0; px < 8; px++)
+                {
+                    const int bp = etc_flip_pixel(flip, sector, px);
+                    const F4 p = L.pw[bp * STRIDE];
+                    for (int ch = 0; ch < 3; ch++)
+                        cumulative[sector][ch] += etc_px(p, ch);
+                    numT[sector] += (int)((transparentMask >> bp) & 1);
+                }
+            const bool canIgnore0 = numT[0] == 8;
+
+            int numAttempts[2] = { 0, 0 };
+            for (int sector = 0; sector < 2; sector++)
+            {
+                const int n = numT[sector];
+                const int denominator = imax(1, n) << 8, addend = n << 7, cumulativeMax = wrap_u16(255 * n);
+                for (int table = 0; table < 8; table++)
+                {
+                    cta_sync();
+                    const int modifier = -T.etc1Modifiers[table][0];       // 8, 17, 29, 42, 60, 80, 106, 183
+                    int lastColor = -1;
+                    for (int om = -n; om <= n; om++)
+                    {
+                        const int offset = wrap_s16(om * modifier);
+                        int packed = 0;
+                        for (int ch = 0; ch < 3; ch++)
+                        {
+                            const int cu = imin(cumulativeMax, imax(0, wrap_s16(cumulative[sector][ch] + offset)));
+                            const int numerator = wrap_u16(wrap_u16((cu << 5) - cu) + wrap_u16((cu >> 3) + addend));
+                            packed |= (numerator / denominator) << (ch * 5);
+                        }
+                        if (om != -n && packed == lastColor)
+                            continue;
+                        lastColor = packed;
+                        uint32_t selectors;
+                        const float error = etc_test_half_block_punchthrough<UNIFORM, BT709, STRIDE>(P, L, flip, sector, packed, modifier, transparentMask, selectors);
+                        const size_t slot = (size_t)(sector * kETCMaxAttempts + numAttempts[sector]) * S.stride;
+                        S.drsErr[slot] = error;
+                        S.drsMeta[slot] = (uint32_t)packed | ((uint32_t)table << 15);
+                        numAttempts[sector]++;
+                    }
+                }
+            }
+
+            cta_sync();
+            int winMeta[2] = { -1, -1 }, selMeta[2] = { -1, -1 };
+            float winTotal = 0.0f;
+            etc_find_best_differential(S, numAttempts, canIgnore0, best.error, winMeta, selMeta, winTotal);
+            if (winMeta[0] >= 0)
+            {
+                bestIsThisMode = true;
+                best.error = winTotal;
+                bestFlip = flip;
+                for (int sector = 0; sector < 2; sector++)
+                {
+                    bestColors[sector] = winMeta[sector] & 0x7fff;
+                    bestTables[sector] = (winMeta[sector] >> 15) & 7;
+                    etc_test_half_block_punchthrough<UNIFORM, BT709, STRIDE>(P, L, flip, sector, selMeta[sector] & 0x7fff, -T.etc1Modifiers[bestTables[sector]][0], transparentMask, bestSelectors[sector]);
+                }
+            }
+        }
+
+        if (bestIsThisMode)
+        {
+            int colors[2][3];
+            for (int sector = 0; sector < 2; sector++)
+                for (int ch = 0; ch < 3; ch++)
+                    colors[sector][ch] = (bestColors[sector] >> (ch * 5)) & 31;
+            etc_emit_etc1(best, bestFlip, 1, colors, bestTables, bestSelectors, true);
+        }
+    }
+
+    // EncodeVirtualTModePunchthrough, ETC.cpp:887-1262: T and H mode share their colour set once code 2 means "transparent".
+    // Cross-lane: the offset walk starts at minus the largest line-pixel count of the call and steps by two (:1038), and the
+    // candidate list has the same never-written slot as the opaque T mode (:1109-1116).
+    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
+    CVTT_HD void etc_virtual_t_punchthrough(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, Vote &vote, uint32_t isolatedBaseMask, uint32_t transparentMask, ETCBest &best)
+    {
+        const uint32_t opaqueMask = ~transparentMask & 0xffffu;
+        const uint32_t isolatedMask = isolatedBaseMask & opaqueMask, lineMask = ~isolatedBaseMask & opaqueMask;
+        int isolatedTotal[3] = { 0, 0, 0 }, lineTotal[3] = { 0, 0, 0 }, numIsolated = 0, numLine = 0;
+        for (int px = 0; px < 16; px++)
+        {
+            const F4 p = L.pw[px * STRIDE];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int v = etc_px(p, ch);
+                if ((isolatedMask >> px) & 1)
+                    isolatedTotal[ch] += v;
+                if ((lineMask >> px) & 1)
+                    lineTotal[ch] += v;
+            }
+            numIsolated += (int)((isolatedMask >> px) & 1);
+            numLine += (int)((lineMask >> px) & 1);
+        }
+
+        int isolatedQ[3], hQ[8][3], isolatedColor[3];
+        {
+            const int divisor = numIsolated * 34, addend = (numIsolated << 4) | numIsolated;
+            int targets[3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int numerator = wrap_u16(isolatedTotal[ch] + isolatedTotal[ch] + (BT709 ? 0 : addend));
+                isolatedQ[ch] = (divisor == 0) ? 0 : (numerator / divisor);
+                targets[ch] = numerator;
+                for (int table = 0; table < 8; table++)
+                {
+                    const int offsetTotal = wrap_u16(isolatedTotal[ch] + wrap_u16(T.thModifier[table] * numIsolated));
+                    const int hNumerator = wrap_u16(offsetTotal + offsetTotal + addend);
+                    hQ[table][ch] = (divisor == 0) ? 0 : (hNumerator / divisor);
+                }
+            }
+            if (BT709)
+                etc_resolve_th_bt709(isolatedQ, targets, numIsolated);
+            for (int table = 0; table < 8; table++)
+                for (int ch = 0; ch < 3; ch++)
+                    hQ[table][ch] = imin(15, hQ[table][ch]);
+            for (int ch = 0; ch < 3; ch++)
+                isolatedColor[ch] = wrap_u16(isolatedQ[ch] | (isolatedQ[ch] << 4));
+        }
+
+        float isolatedError[16];
+        {
+            float isoW[3];
+            etc_weigh<UNIFORM, BT709>(P, isolatedColor, isoW);
+            for (int px = 0; px < 16; px++)
+                isolatedError[px] = ((transparentMask >> px) & 1) ? 0.0f : etc_error<UNIFORM, BT709>(L.pw[px * STRIDE], isolatedColor, isoW);
+        }
+
+        bool bestIsThisMode = false, bestIsHMode = false;
+        uint32_t bestSelectors = 0;
+        int bestTable = 0, bestLineColor = 0, bestHModeColor2 = 0;
+
+        const int lineDivisor = numLine * 34, lineAddend = (numLine << 4) | numLine;
+        const int clusterMaxLine = vote.max(numLine);
+
+        for (int table = 0; table < 8; table++)
+        {
+            cta_sync();
+            const int modifier = T.thModifier[table];
+            const int modifierOffset = modifier + modifier;
+
+            auto lineColorAt = [&](int offs) -> int
+            {
+                const int clamped = imax(-numLine, imin(numLine, offs));
+                int q[3], targets[3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const int numerator = imax(0, wrap_s16(wrap_s16(lineTotal[ch] + lineTotal[ch] + (BT709 ? 0 : lineAddend)) + wrap_s16(clamped * modifierOffset)));
+                    const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
+                    q[ch] = imin(15, divided);
+                    targets[ch] = numerator;
+                }
+                if (BT709)
+                    etc_resolve_th_bt709(q, targets, numLine);
+                return (q[0] << 10) | (q[1] << 5) | q[2];
+            };
+
+            int numUnique = 0, lastColor = -1;
+            for (int offs = -clusterMaxLine; offs <= clusterMaxLine; offs += 2)
+            {
+                const int packed = lineColorAt(offs);
+                if (numUnique == 0 || packed != lastColor)
+                {
+                    numUnique++;
+                    lastColor = packed;
+                }
+            }
+            const int maxUnique = vote.max(numUnique);
+            const int numCandidates = numUnique + ((numUnique < maxUnique) ? 1 : 0);
+
+            int hModeColor[3];
+            float hW[3], hModeErrors[16];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                const int q = hQ[table][ch];
+                hModeColor[ch] = imax(0, ((q << 4) | q) - modifier);
+            }
+            etc_weigh<UNIFORM, false>(P, hModeColor, hW);
+            for (int px = 0; px < 16; px++)
+                hModeErrors[px] = ((transparentMask >> px) & 1) ? 0.0f : etc_error<UNIFORM, false>(L.pw[px * STRIDE], hModeColor, hW);
+            const int packedHModeColor2 = (hQ[table][0] << 10) | (hQ[table][1] << 5) | hQ[table][2];
+            const bool tableLowBitIsZero = (table & 1) == 0;
+
+            int offs = -clusterMaxLine;
+            lastColor = -1;
+            for (int ci = 0; ci < numCandidates; ci++)
+            {
+                int packedColor = 0;
+                if (ci < numUnique)
+                {
+                    for (;;)
+                    {
+                        const int packed = lineColorAt(offs);
+                        offs += 2;
+                        if (packed != lastColor)
+                        {
+                            lastColor = packed;
+                            packedColor = packed;
+                            break;
+                        }
+                    }
+                }
+
+                int lineColors[2][3];
+                float lineW[2][3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const int q = (packedColor >> (10 - ch * 5)) & 15;
+                    const int unq = (q << 4) | q;
+                    lineColors[0][ch] = imin(255, unq + modifier);
+                    lineColors[1][ch] = imax(0, unq - modifier);
+                }
+                etc_weigh<UNIFORM, false>(P, lineColors[0], lineW[0]);
+                etc_weigh<UNIFORM, false>(P, lineColors[1], lineW[1]);
+
+                float bestLineError[16];
+                uint32_t lineSelectors = 0;
+                float tModeError = 0.0f, hModeError = 0.0f;
+                for (int px = 0; px < 16; px++)
+                {
+                    const F4 p = L.pw[px * STRIDE];
+                    const float e0 = etc_error<UNIFORM, false>(p, lineColors[0], lineW[0]), e1 = etc_error<UNIFORM, false>(p, lineColors[1], lineW[1]);
+                    lineSelectors |= ((e0 <= e1) ? 1u : 3u) << (px * 2);
+                    float e = sse_min(e0, e1);
+                    if ((transparentMask >> px) & 1)
+                        e = 0.0f;
+                    bestLineError[px] = e;
+                    tModeError = fadd(tModeError, sse_min(e, isolatedError[px]));
+                    hModeError = fadd(hModeError, sse_min(e, hModeErrors[px]));
+                }
+
+                const bool hLessError = hModeError < tModeError;
+                const bool hModeTableLowBitMustBeZero = packedColor < packedHModeColor2;
+                const bool useHMode = hLessError && (hModeTableLowBitMustBeZero == tableLowBitIsZero);
+                const float roundBestError = useHMode ? hModeError : tModeError;
+                if (roundBestError < best.error)
+                {
+                    uint32_t selectors = 0;
+                    for (int px = 0; px < 16; px++)
+                    {
+                        uint32_t selector = (lineSelectors >> (px * 2)) & 3u;
+                        const float isolatedPixelError = useHMode ? hModeErrors[px] : isolatedError[px];
+                        if (isolatedPixelError < bestLineError[px])
+                            selector = 0;
+                        if ((transparentMask >> px) & 1)
+                            selector = 2;
+                        selectors |= selector << (px * 2);
+                    }
+                    best.error = roundBestError;
+                    bestLineColor = packedColor;
+                    bestSelectors = selectors;
+                    bestTable = table;
+                    bestIsHMode = useHMode;
+                    bestHModeColor2 = packedHModeColor2;
+                    bestIsThisMode = true;
+                }
+            }
+        }
+
+        if (bestIsThisMode)
+        {
+            if (bestIsHMode)
+            {
+                // T mode: C1, C2+M, transparent, C2-M;  H mode: C1+M, C1-M, transparent, C2-M  (ETC.cpp:1236-1256)
+                uint32_t signBits = 0, sectorBits = 0;
+                for (int px = 0; px < 16; px++)
+                {
+                    const uint32_t selector = (bestSelectors >> (px * 2)) & 3u;
+                    sectorBits |= ((0x5u >> selector) & 1u) << px;        // selectorRemapSector { 1, 0, 1, 0 }
+                    signBits |= ((0x9u >> selector) & 1u) << px;          // selectorRemapSign   { 1, 0, 0, 1 }
+                }
+                const int blockColors[2] = { bestLineColor, bestHModeColor2 };
+                etc_emit_h(best, blockColors, sectorBits, signBits, bestTable, false);
+            }
+            else
+            {
+                int lineColor[3];
+                for (int ch = 0; ch < 3; ch++)
+                    lineColor[ch] = (bestLineColor >> (10 - ch * 5)) & 15;
+                etc_emit_t(best, lineColor, isolatedQ, bestSelectors, bestTable, false);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // CompressETC2Block without punch-through (ETC.cpp:1664-1887): chroma split, then planar, T, T, H, differential
+    // chroma-plane split of CompressETC2Block (ETC.cpp:1723-1848); numOpaque is 16 without punch-through
+    template<bool UNIFORM, int STRIDE>
+    CVTT_HD uint32_t etc2_chroma_split(const ETCParams &P, const ETCLane<STRIDE> &L, int numOpaque)
+    {
         float chromaDelta[16][2];
         if (UNIFORM)
         {
@@ -1116,13 +1472,14 @@ namespace cvttb200
             }
             for (int px = 0; px < 16; px++)
             {
-                chromaDelta[px][0] = (float)((coords[px][0] << 4) - centroid[0]);
-                chromaDelta[px][1] = fmul((float)((coords[px][1] << 4) - centroid[1]), 0.57735026918962576450914878050196f);
+                chromaDelta[px][0] = (float)(coords[px][0] * numOpaque - centroid[0]);
+                chromaDelta[px][1] = fmul((float)(coords[px][1] * numOpaque - centroid[1]), 0.57735026918962576450914878050196f);
             }
         }
         else
         {
             float coords[16][2], centroid[2] = { 0.0f, 0.0f };
+            const float numOpaqueF = (float)numOpaque;
             for (int px = 0; px < 16; px++)
             {
                 const F4 p = L.pw[px * STRIDE];
@@ -1134,7 +1491,7 @@ namespace cvttb200
                     centroid[ch] = fadd(centroid[ch], coords[px][ch]);
             for (int px = 0; px < 16; px++)
                 for (int ch = 0; ch < 2; ch++)
-                    chromaDelta[px][ch] = fsub(fmul(coords[px][ch], 16.0f), centroid[ch]);
+                    chromaDelta[px][ch] = fsub(fmul(coords[px][ch], numOpaqueF), centroid[ch]);
         }
 
         float covXX = 0.0f, covYY = 0.0f, covXY = 0.0f;
@@ -1157,12 +1514,77 @@ namespace cvttb200
         for (int px = 0; px < 16; px++)
             if (fadd(fmul(chromaDelta[px][0], dx), fmul(chromaDelta[px][1], dy)) < 0.0f)
                 sectorMask |= 1u << px;
+        return sectorMask;
+    }
 
+    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
+    CVTT_HD void etc2_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, Vote &vote, uint32_t out[2])
+    {
+        ETCBest best;
+        best.error = FLT_MAX;
+        best.hi = best.lo = 0;
+
+        cta_sync();
+        etc_planar<UNIFORM, BT709, STRIDE>(P, L, best);
+
+        uint32_t sectorMask = etc2_chroma_split<UNIFORM, STRIDE>(P, L, 16);
         etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
         sectorMask ^= 0xffffu;
         etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
         etc_h_mode<UNIFORM, BT709, STRIDE>(P, T, L, S, sectorMask, best);
         etc_etc1<UNIFORM, BT709, 1, STRIDE>(P, T, L, S, best);
+
+        out[0] = best.hi;
+        out[1] = best.lo;
+    }
+
+    // CompressETC2Block with punch-through alpha (ETC.cpp:1664-1887).  The lane's pixels below the threshold are already zero
+    // (transparentMask).  Cross-lane: the opaque stages run for a group unless all of its lanes are fully transparent, the
+    // punch-through stages run if any lane has a transparent pixel; a lane with a transparent pixel restarts from FLT_MAX
+    // before the punch-through stages, so only fully opaque lanes keep their opaque-stage result.  The stage barriers are
+    // CTA-wide, so a stage runs for the whole CTA when any of its groups needs it and the groups that do not need it drop
+    // what it produced.
+    template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
+    CVTT_HD void etc2_punchthrough_encode_block(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, const ETCScratch &S, Vote &vote, uint32_t transparentMask, uint32_t out[2])
+    {
+        ETCBest best;
+        best.error = FLT_MAX;
+        best.hi = best.lo = 0;
+
+        const bool anyTransparent = transparentMask != 0, allTransparent = transparentMask == 0xffffu;
+        const bool groupOpaqueStages = vote.max(allTransparent ? 0 : 1) != 0;
+        const bool groupPunchStages = vote.max(anyTransparent ? 1 : 0) != 0;
+        int numOpaque = 16;
+        for (int px = 0; px < 16; px++)
+            numOpaque -= (int)((transparentMask >> px) & 1);
+
+        uint32_t sectorMask = etc2_chroma_split<UNIFORM, STRIDE>(P, L, numOpaque);
+
+        if (cta_any(groupOpaqueStages))
+        {
+            etc_planar<UNIFORM, BT709, STRIDE>(P, L, best);
+            etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
+            etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask ^ 0xffffu, best);
+            etc_h_mode<UNIFORM, BT709, STRIDE>(P, T, L, S, sectorMask ^ 0xffffu, best);
+            etc_etc1<UNIFORM, BT709, 1, STRIDE>(P, T, L, S, best);
+            if (!groupOpaqueStages)
+            {
+                best.error = FLT_MAX;
+                best.hi = best.lo = 0;
+            }
+        }
+
+        if (cta_any(groupPunchStages))
+        {
+            const ETCBest opaqueBest = best;
+            if (anyTransparent)
+                best.error = FLT_MAX;
+            etc_virtual_t_punchthrough<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, transparentMask, best);
+            etc_virtual_t_punchthrough<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask ^ 0xffffu, transparentMask, best);
+            etc_etc1_punchthrough<UNIFORM, BT709, STRIDE>(P, T, L, S, transparentMask, best);
+            if (!groupPunchStages)
+                best = opaqueBest;
+        }
 
         out[0] = best.hi;
         out[1] = best.lo;

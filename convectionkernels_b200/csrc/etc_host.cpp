@@ -2,6 +2,7 @@
 #include "etc_host.h"
 
 #include <math.h>
+#include <algorithm>
 #include <string.h>
 
 #include "etc_tables.inc"
@@ -12,6 +13,11 @@ namespace cvttb200
     {
         memset(&P, 0, sizeof(P));
         P.flags = options.flags;
+        {
+            // CompressETC2Block, ETC.cpp:1672-1675 (std::min / std::max operand order kept for NaN thresholds)
+            const float fThreshold = std::max<float>(std::min<float>(1.0f, options.threshold), 0.0f) * 255.0f;
+            P.punchThreshold = (int)static_cast<uint16_t>(floorf(fThreshold + 1.0f));
+        }
         const float cd[3] = { options.redWeight, options.greenWeight, options.blueWeight };
         for (int ch = 0; ch < 3; ch++)
         {

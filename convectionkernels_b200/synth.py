@@ -113,6 +113,35 @@ def random_blocks_rgba8(n, seed=0, kind="mix"):
     return blocks
 
 
+def punchthrough_blocks_rgba8(n, seed=0):
+    """RGBA8 blocks for EncodeETC2PunchthroughAlpha: the colour content of random_blocks_rgba8 with alpha patterns that exercise
+    every branch of the reference's punch-through flow (ETC.cpp:1664-1887): opaque blocks, fully transparent blocks, binary and
+    continuous alpha, a single hole, a transparent half, plus whole 8-block groups that are all opaque / all transparent."""
+    rng = np.random.default_rng(seed)
+    b = random_blocks_rgba8(n, seed=seed).copy()
+    kind = rng.integers(0, 6, size=n)
+    group = np.arange(n) // 8
+    kind[group % 7 == 0] = 0
+    kind[group % 7 == 1] = 1
+    for i in range(n):
+        k = kind[i]
+        if k == 0:
+            b[i, :, 3] = 255
+        elif k == 1:
+            b[i, :, 3] = rng.integers(0, 100)
+        elif k == 2:
+            b[i, :, 3] = rng.integers(0, 2, size=16) * 255
+        elif k == 3:
+            b[i, :, 3] = rng.integers(0, 256, size=16)
+        elif k == 4:
+            b[i, :, 3] = 255
+            b[i, rng.integers(0, 16), 3] = 0
+        else:
+            b[i, :8, 3] = 0
+            b[i, 8:, 3] = 255
+    return b
+
+
 def hdr_ramp_f16(h=4096, w=4096, seed=99, signed=False):
     """Config 3: HDR ramp R=0.01*2^(x/64), G=0.02*2^(y/64), B=0.5+noise; returns int16 half bit patterns, RGBA."""
     rng = np.random.default_rng(seed)

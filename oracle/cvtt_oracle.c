@@ -775,7 +775,31 @@ static void try_single_plane(uint32_t flags, const uint16_t pixels[16][4], const
                     }
                 }
             }
-            /* Flags::BC7_TrySingleColor (:1436-1570) is not restated: callers reject the flag. */
+            if (flags & FLAG_BC7_TrySingleColor)
+            {
+                /* Flags::BC7_TrySingleColor, :1436-1570 -> TrySingleColorRGBAMultiTable, :940-1040.  The table loop accepts an entry
+                   under better = AndNot(pti, Less(avgError, bestAverageError)) (:997-998) and ParallelMath::AndNot(a, b) is
+                   a & ~b (ParallelMath.h:901-906).  pti is false on every path this oracle accepts (RespectPunchThrough is
+                   rejected below), so no entry of the single-colour tables is ever taken and the candidate that reaches the
+                   error test is the initial one (:948-961): end points and reconstruction (0, 0, 0, 255), index 0.  The tables
+                   (ConvectionKernels_BC7_SingleColor.h) and the average (:1438-1452) therefore have no observable effect and
+                   are not restated. */
+                static const uint16_t reconstructed[4] = { 0, 0, 0, 255 };
+                agg_error aggError;
+                agg_init(&aggError);
+                for (int pxi = 0; pxi < shapeLength; pxi++)
+                    compute_error_ldr(reconstructed, pixels[pxlist[pxi]], numRealChannels, &aggError);
+                float error = agg_finalize(&aggError, 4, flags, channelWeightsSq) + staticAlphaError;
+                if (error < temps->shapeBestError[shape])
+                {
+                    temps->shapeBestError[shape] = error;
+                    for (int epi = 0; epi < 2; epi++)
+                        for (int ch = 0; ch < numRealChannels; ch++)
+                            temps->shapeBestEP[shape][epi][ch] = reconstructed[ch];
+                    for (int pxi = 0; pxi < shapeLength; pxi++)
+                        temps->fragmentBestIndexes[shapeStart + pxi] = 0;
+                }
+            }
         }
 
         /* partition scan (:1573-1660).  For mode 7 the reference assigns a misspelt variable (:1593-1596), so all 64
@@ -1269,11 +1293,10 @@ int cvtt_oracle_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t *out, 
 {
     if (!blocks || !out || !options || !plan || (nBlocks % 8) != 0)
         return -1;
-    /* BC7_TrySingleColor needs the reference's 36 KB single-colour tables (not restated).  BC7_RespectPunchThrough is
-       not restated either: the reference masks commits with AndNot(punchThroughInvalid, better) = invalid & ~better
+    /* BC7_RespectPunchThrough is not restated: the reference masks commits with AndNot(punchThroughInvalid, better) = invalid & ~better
        (ConvectionKernels_BC67.cpp:1411, ParallelMath.h:898-903), guarded by AnySet(better) over the 8 lanes (:1406),
        so a block's result depends on its neighbours' per-trial errors; that needs a lock-step 8-lane model. */
-    if (options->flags & (FLAG_BC7_TrySingleColor | FLAG_BC7_RespectPunchThrough))
+    if (options->flags & FLAG_BC7_RespectPunchThrough)
         return -2;
 
     init_tables();

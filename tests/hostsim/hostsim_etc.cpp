@@ -10,7 +10,7 @@ using namespace cvttb200;
 
 namespace
 {
-    // kind: 0 ETC1, 1 ETC2 RGB, 2 ETC2 RGBA, 3 ETC2 alpha, 4 EAC R11 unsigned, 5 EAC R11 signed
+    // kind: 0 ETC1, 1 ETC2 RGB, 2 ETC2 RGBA, 3 ETC2 alpha, 4 EAC R11 unsigned, 5 EAC R11 signed, 6 ETC2 RGB + punch-through alpha
     void run_lane(int lane, GroupShared *shared, const ETCParams *P, int kind, const uint8_t *blocks, size_t nBlocks, uint8_t *out)
     {
         HostVote vote;
@@ -24,11 +24,12 @@ namespace
         {
             const size_t b = base + lane;
             uint32_t color[2] = { 0, 0 }, alpha[2] = { 0, 0 };
-            if (kind <= 3)
+            if (kind <= 3 || kind == 6)
             {
                 const uint8_t *src = blocks + b * 64;
                 F4 pw[16];
                 int a[16];
+                uint32_t transparentMask = 0;
                 for (int px = 0; px < 16; px++)
                 {
                     const uint8_t *s = src + px * 4;
@@ -46,6 +47,13 @@ namespace
                     }
                     pw[px].w = as_float((uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24));
                     a[px] = s[3];
+                    if (kind == 6 && a[px] < P->punchThreshold)
+                    {
+                        // CompressETC2Block, ETC.cpp:1705-1718
+                        transparentMask |= 1u << px;
+                        pw[px].x = pw[px].y = pw[px].z = 0.0f;
+                        pw[px].w = as_float((uint32_t)s[3] << 24);
+                    }
                 }
                 ETCLane<1> L;
                 L.pw = pw;
@@ -64,6 +72,14 @@ namespace
                         if (uniform) etc2_encode_block<true, true, 1>(*P, T, L, S, vote, color); else etc2_encode_block<false, true, 1>(*P, T, L, S, vote, color);
                     }
                     else if (uniform) etc2_encode_block<true, false, 1>(*P, T, L, S, vote, color); else etc2_encode_block<false, false, 1>(*P, T, L, S, vote, color);
+                }
+                else if (kind == 6)
+                {
+                    if (bt709)
+                    {
+                        if (uniform) etc2_punchthrough_encode_block<true, true, 1>(*P, T, L, S, vote, transparentMask, color); else etc2_punchthrough_encode_block<false, true, 1>(*P, T, L, S, vote, transparentMask, color);
+                    }
+                    else if (uniform) etc2_punchthrough_encode_block<true, false, 1>(*P, T, L, S, vote, transparentMask, color); else etc2_punchthrough_encode_block<false, false, 1>(*P, T, L, S, vote, transparentMask, color);
                 }
                 if (kind == 2 || kind == 3)
                     etc_alpha_encode_block(T, a, false, false, alpha);
@@ -86,12 +102,12 @@ namespace
             }
             uint32_t words[4];
             int n = 0;
-            if (kind >= 2)
+            if (kind >= 2 && kind != 6)
             {
                 words[n++] = etc_bswap(alpha[0]);
                 words[n++] = etc_bswap(alpha[1]);
             }
-            if (kind <= 2)
+            if (kind <= 2 || kind == 6)
             {
                 words[n++] = etc_bswap(color[0]);
                 words[n++] = etc_bswap(color[1]);

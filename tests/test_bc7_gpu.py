@@ -92,8 +92,9 @@ def test_argument_and_flag_errors():
     with pytest.raises(api.CvttError) as e:
         api.encode("BC7", np.zeros((12, 16, 4), np.uint8), o, p)
     assert e.value.status == -1
+    o.flags |= api.Flags.BC7_RespectPunchThrough
     with pytest.raises(api.CvttError) as e:
-        api.encode("ETC2_PUNCHTHROUGH", np.zeros((8, 16, 4), np.uint8), o)
+        api.encode("BC7", np.zeros((8, 16, 4), np.uint8), o, p)
     assert e.value.status == -2                   # not implemented is reported, never silently computed elsewhere
 
 

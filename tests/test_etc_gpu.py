@@ -77,12 +77,30 @@ def test_fake_bt709_against_reference(reference, fmt, flags):
     assert (got == want).all(), first_mismatch(want, got)
 
 
-def test_unsupported_variants_fail_loudly():
-    blocks = synth.random_blocks_rgba8(8, seed=1)
+@pytest.mark.parametrize("flags,threshold", [(0x108, 0.5), (0x308, 0.9), (0x508, 0.3), (0xF08, 0.5), (0x108, 2.0), (0x108, -1.0)])
+def test_punchthrough_against_reference(reference, flags, threshold):
+    """EncodeETC2PunchthroughAlpha: mixed opaque / transparent / partly transparent blocks, whole groups of each, thresholds inside
+    and outside [0, 1]; 8200 blocks = 16 CTAs of 512 plus a ragged tail, so CTAs mix groups that need different stages"""
+    blocks = synth.punchthrough_blocks_rgba8(8200, seed=55)
     o = api.Options()
-    with pytest.raises(api.CvttError) as e:
-        api.encode("ETC2_PUNCHTHROUGH", blocks, o)
-    assert e.value.status == -2
+    o.flags, o.threshold = flags, threshold
+    want = reference.encode("ETC2_PUNCHTHROUGH", blocks, _opt_bytes(o), threads=0)
+    got = api.EncodeETC2PunchthroughAlpha(blocks, o)
+    assert got.shape == (8200, 8)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_punchthrough_opaque_image_and_stage_skipping(reference):
+    """all-opaque input never enters the punch-through stages (the CTA-wide vote skips them) and equals what the reference produces;
+    all-transparent input skips the opaque stages"""
+    blocks = synth.random_blocks_rgba8(2048, seed=8).copy()
+    blocks[:, :, 3] = 255
+    o = api.Options()
+    want = reference.encode("ETC2_PUNCHTHROUGH", blocks, _opt_bytes(o), threads=0)
+    assert (api.EncodeETC2PunchthroughAlpha(blocks, o) == want).all()
+    blocks[:, :, 3] = 0
+    want = reference.encode("ETC2_PUNCHTHROUGH", blocks, _opt_bytes(o), threads=0)
+    assert (api.EncodeETC2PunchthroughAlpha(blocks, o) == want).all()
 
 
 def test_full_size_properties(reference):

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT, golden_names, load_golden, first_mismatch
 
-KIND = {"ETC1": 0, "ETC2": 1, "ETC2_RGBA": 2, "ETC2_ALPHA": 3, "EAC_R11U": 4, "EAC_R11S": 5}
+KIND = {"ETC1": 0, "ETC2": 1, "ETC2_RGBA": 2, "ETC2_ALPHA": 3, "EAC_R11U": 4, "EAC_R11S": 5, "ETC2_PUNCHTHROUGH": 6}
 
 
 @pytest.fixture(scope="module")
@@ -47,4 +47,19 @@ def test_t_mode_group_coupling(hostsim_etc, reference):
     want = reference.encode("ETC2", blocks, opt)
     out = np.zeros_like(want)
     assert hostsim_etc.hostsim_encode_etc(1, blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data) == 0
+    assert (out == want).all(), first_mismatch(want, out)
+
+
+@pytest.mark.parametrize("flags,threshold", [(0x108, 0.5), (0x308, -1.0), (0xD08, 1.0)])
+def test_punchthrough_group_coupling(hostsim_etc, reference, flags, threshold):
+    """EncodeETC2PunchthroughAlpha: which stages run depends on the other blocks of the group (ETC.cpp:1720,1850,1865), and the
+    virtual T mode walks offsets up to the group's largest line-pixel count (ETC.cpp:1017-1044)"""
+    from convectionkernels_b200 import api, synth
+    blocks = synth.punchthrough_blocks_rgba8(1024, seed=77)
+    o = api.Options()
+    o.flags, o.threshold = flags, threshold
+    opt = np.frombuffer(bytes(memoryview(o)), np.uint8)
+    want = reference.encode("ETC2_PUNCHTHROUGH", blocks, opt)
+    out = np.zeros_like(want)
+    assert hostsim_etc.hostsim_encode_etc(6, blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data) == 0
     assert (out == want).all(), first_mismatch(want, out)

@@ -73,6 +73,6 @@ def test_group_coupling_is_reproduced(oracle, reference):
 def test_oracle_rejects_unrestated_flags(oracle):
     blocks = np.zeros((8, 16, 4), np.uint8)
     opt = np.zeros(44, np.uint8)
-    opt[0:4] = np.frombuffer(struct.pack("<I", 0x010), np.uint8)
+    opt[0:4] = np.frombuffer(struct.pack("<I", 0x020), np.uint8)
     with pytest.raises(ValueError):
         oracle.encode_bc7(blocks, opt, oracle.plan_from_quality(100))

@@ -15,14 +15,19 @@ os.makedirs(OUT, exist_ok=True)
 rcp = R.rcp_table()
 
 
-def options(flags=None, refine=None, weights=None, refine_bc6h=None, seeds=None, refine_s3tc=None, refine_iic=None):
+def options(flags=None, refine=None, weights=None, refine_bc6h=None, seeds=None, refine_s3tc=None, refine_iic=None, threshold=None):
     o = R.default_options().copy()
     if flags is not None:
         o[0:4] = np.frombuffer(struct.pack("<I", flags), np.uint8)
+    if threshold is not None:
+        o[4:8] = np.frombuffer(struct.pack("<f", threshold), np.uint8)
     if weights is not None:
         o[8:24] = np.frombuffer(struct.pack("<4f", *weights), np.uint8)
     if refine is not None:
         o[24:28] = np.frombuffer(struct.pack("<i", refine), np.uint8)
+    for offset, value in ((28, refine_bc6h), (32, refine_iic), (36, refine_s3tc), (40, seeds)):
+        if value is not None:
+            o[offset:offset + 4] = np.frombuffer(struct.pack("<i", value), np.uint8)
     return o
 
 
@@ -94,3 +99,10 @@ save("bc1_random_alpha_exhaustive", "BC1", rba[:128], options(flags=0x188))
 save("bc3_random_exhaustive_uniform", "BC3", rba[:128], options(flags=0x288))
 save("etc2rgba_random_bt709", "ETC2_RGBA", rb, options(flags=0x508))
 save("etc1_random_bt709_accurate_uniform", "ETC1", rb, options(flags=0xF08))
+
+# EncodeETC2PunchthroughAlpha: mixed alpha patterns, default / uniform / fake BT.709, thresholds inside and outside [0, 1]
+pt = synth.punchthrough_blocks_rgba8(512, seed=41)
+save("etc2punch_mixed", "ETC2_PUNCHTHROUGH", pt, options())
+save("etc2punch_mixed_uniform_thr09", "ETC2_PUNCHTHROUGH", pt[:256], options(flags=0x308, threshold=0.9))
+save("etc2punch_mixed_bt709_thr03", "ETC2_PUNCHTHROUGH", pt[:256], options(flags=0x508, threshold=0.3))
+save("etc2punch_mixed_thr2", "ETC2_PUNCHTHROUGH", pt[:64], options(threshold=2.0))
