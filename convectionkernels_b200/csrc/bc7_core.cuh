@@ -459,12 +459,77 @@ namespace cvttb200
         f2 err;
         int seqX, seqY;
         f2 e0[NCH], e1[NCH];  // biased
+
+        // one finished refine round of both chains: each lane keeps its (error, sequence number) minimum
+        CVTT_HD void trial(int sx, int sy, const f2 &shapeError, const f2 *q0b, const f2 *q1b)
+        {
+            if (shapeError.x < err.x || (shapeError.x == err.x && sx < seqX))
+            {
+                err.x = shapeError.x;
+                seqX = sx;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                {
+                    e0[ch].x = q0b[ch].x;
+                    e1[ch].x = q1b[ch].x;
+                }
+            }
+            if (shapeError.y < err.y || (shapeError.y == err.y && sy < seqY))
+            {
+                err.y = shapeError.y;
+                seqY = sy;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                {
+                    e0[ch].y = q0b[ch].y;
+                    e1[ch].y = q1b[ch].y;
+                }
+            }
+        }
+    };
+
+    // Flags::BC7_RespectPunchThrough, modes 6 and 7 (BC67.cpp:1281-1303,1400-1428).  A parity combination that would move
+    // a punch-through block's alpha off 0 / 255 is "invalid" for that block.  What the reference does with that:
+    //   * a parity combination invalid for all 8 blocks of the call is skipped (:1300)
+    //   * if it is invalid for none, trials commit normally
+    //   * otherwise (:1409-1416) a trial that is better for at least one block of the call is committed under
+    //     AndNot(invalid, better), and ParallelMath::AndNot(a, b) is a & ~b (ParallelMath.h:901-906): the blocks that take
+    //     the trial are the INVALID ones for which it is NOT better; valid blocks take nothing.
+    // Commits are therefore neither monotonic nor independent of the neighbours, so the trials run one chain at a time in
+    // the reference's (pIter, tweak, refine) order (fp32 lane x; lane y repeats it) with one group vote per trial.
+    template<int NCH, class Vote>
+    struct BC7PunchCommit
+    {
+        Vote *vote;
+        float err;
+        uint32_t e0, e1;                 // packed endpoint bytes
+        bool invalid, groupAnyInvalid, groupAllInvalid;
+
+        CVTT_HD void trial(int, int, const f2 &shapeError, const f2 *q0b, const f2 *q1b)
+        {
+            const bool better = !groupAllInvalid && shapeError.x < err;
+            if (vote->any(better))
+            {
+                const bool take = groupAnyInvalid ? (invalid && !better) : better;
+                if (take)
+                {
+                    err = shapeError.x;
+                    e0 = e1 = 0;
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++)
+                    {
+                        e0 |= (as_uint(q0b[ch].x) & 0xffu) << (8 * ch);
+                        e1 |= (as_uint(q1b[ch].x) & 0xffu) << (8 * ch);
+                    }
+                }
+            }
+        }
     };
 
     // refine rounds of one pair of trial chains starting from the tweaked endpoints u0/u1
-    template<int MODE, bool FAST, int STRIDE>
+    template<int MODE, bool FAST, int STRIDE, class Commit>
     CVTT_HD void bc7_trial_pair(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const float *sumV, float staticAlphaError,
-        const f2 *u0, const f2 *u1, int p0x, int p0y, int p1x, int p1y, int seqX, int seqY, bool invalidX, bool invalidY, BC7PairBest<BC7ModeT<MODE>::NCH> &best)
+        const f2 *u0, const f2 *u1, int p0x, int p0y, int p1x, int p1y, int seqX, int seqY, Commit &best)
     {
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
@@ -536,32 +601,7 @@ namespace cvttb200
             if (NCH == 3)
                 shapeError = f2_add(shapeError, staticAlphaError);
 
-            {
-                const int sx = seqX + refine, sy = seqY + refine;
-                // Flags::BC7_RespectPunchThrough masks the commits of parity combinations that would move alpha off 0 / 255 (BC67.cpp:1406-1414)
-                if (!invalidX && (shapeError.x < best.err.x || (shapeError.x == best.err.x && sx < best.seqX)))
-                {
-                    best.err.x = shapeError.x;
-                    best.seqX = sx;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                    {
-                        best.e0[ch].x = q0b[ch].x;
-                        best.e1[ch].x = q1b[ch].x;
-                    }
-                }
-                if (!invalidY && (shapeError.y < best.err.y || (shapeError.y == best.err.y && sy < best.seqY)))
-                {
-                    best.err.y = shapeError.y;
-                    best.seqY = sy;
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-                    {
-                        best.e0[ch].y = q0b[ch].y;
-                        best.e1[ch].y = q1b[ch].y;
-                    }
-                }
-            }
+            best.trial(seqX + refine, seqY + refine, shapeError, q0b, q1b);
 
             // EndpointRefiner::GetRefinedEndpointsLDR (EndpointRefiner.h:99-152)
             if (!lastRound)
@@ -592,7 +632,7 @@ namespace cvttb200
 
     template<int MODE, bool FAST, int STRIDE>
     CVTT_HD void bc7_shape_trials(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
-        const float *sumV, float staticAlphaError, uint32_t punchInvalid, BC7ShapeBest &out)
+        const float *sumV, float staticAlphaError, BC7ShapeBest &out)
     {
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
@@ -626,8 +666,7 @@ namespace cvttb200
                     // lanes: pIter = 2 pp and 2 pp + 1, i.e. first parity bit 0 and 1
                     const int p1 = M::SHAREDP ? 0 : pp;
                     const int seqX = ((pp * 2) * 4 + tweak) << 16, seqY = ((pp * 2 + 1) * 4 + tweak) << 16;
-                    bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 1, M::SHAREDP ? 0 : p1, M::SHAREDP ? 1 : p1, seqX, seqY,
-                                                       ((punchInvalid >> (pp * 2)) & 1) != 0, ((punchInvalid >> (pp * 2 + 1)) & 1) != 0, best);
+                    bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 1, M::SHAREDP ? 0 : p1, M::SHAREDP ? 1 : p1, seqX, seqY, best);
                 }
             }
         }
@@ -647,7 +686,7 @@ namespace cvttb200
                     u0[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf0, offs[ch]), base[ch]), 0.0f, 255.0f));
                     u1[ch] = f2_rne(f2_clamp_for_round(f2_add(f2_mul(tf1, offs[ch]), base[ch]), 0.0f, 255.0f));
                 }
-                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 0, 0, 0, tweak << 16, pairFull ? (tweakY << 16) : 0x7ff00000, false, false, best);
+                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, staticAlphaError, u0, u1, 0, 0, 0, 0, tweak << 16, pairFull ? (tweakY << 16) : 0x7ff00000, best);
             }
         }
 
@@ -662,6 +701,57 @@ namespace cvttb200
         }
         out.e0 = r0;
         out.e1 = r1;
+    }
+
+    // bc7_shape_trials for modes 6 / 7 under Flags::BC7_RespectPunchThrough, see BC7PunchCommit.  punchInvalid: bit pIter.
+    template<int MODE, bool FAST, int STRIDE, class Vote>
+    CVTT_HD void bc7_shape_trials_punch(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
+        const float *sumV, uint32_t punchInvalid, Vote &vote, BC7ShapeBest &out)
+    {
+        typedef BC7ModeT<MODE> M;
+        enum { NCH = M::NCH };
+        const IndexConst &ic = P.ic[M::IB - 2];
+
+        BC7PunchCommit<NCH, Vote> commit;
+        commit.vote = &vote;
+        commit.err = FLT_MAX;
+        commit.e0 = commit.e1 = 0;
+
+#pragma unroll 1
+        for (int pIter = 0; pIter < 4; pIter++)
+        {
+            commit.invalid = ((punchInvalid >> pIter) & 1) != 0;
+            commit.groupAllInvalid = vote.all(commit.invalid);
+            commit.groupAnyInvalid = vote.any(commit.invalid);
+            if (!vote.warp_any(!commit.groupAllInvalid))
+                continue;       // no group of the warp tries this parity combination
+#pragma unroll 1
+            for (int tweak = 0; tweak < seeds; tweak++)
+            {
+                const float tf0 = ic.tweak[tweak][0], tf1 = ic.tweak[tweak][1];
+                f2 u0[NCH], u1[NCH];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++)
+                {
+                    u0[ch] = f2_splat(rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf0)), 0.0f, 255.0f)));
+                    u1[ch] = f2_splat(rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf1)), 0.0f, 255.0f)));
+                }
+                bc7_trial_pair<MODE, FAST, STRIDE>(P, gv, gw, n, sumV, 0.0f, u0, u1, pIter & 1, pIter & 1, pIter >> 1, pIter >> 1, 0, 0, commit);
+            }
+        }
+        out.err = commit.err;
+        out.e0 = commit.e0;
+        out.e1 = commit.e1;
+    }
+
+    template<int MODE, bool FAST, int STRIDE, bool PUNCH, class Vote>
+    CVTT_HD void bc7_shape_trials_67(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
+        const float *sumV, uint32_t punchInvalid, Vote &vote, BC7ShapeBest &out)
+    {
+        if (PUNCH)
+            bc7_shape_trials_punch<MODE, FAST, STRIDE>(P, gv, gw, n, seeds, base, offs, sumV, punchInvalid, vote, out);
+        else
+            bc7_shape_trials<MODE, FAST, STRIDE>(P, gv, gw, n, seeds, base, offs, sumV, 0.0f, out);
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -1305,8 +1395,16 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // The whole search for one block.
-    template<bool FAST, int STRIDE>
-    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, uint32_t out[4])
+    struct BC7NoVote      // the search without Flags::BC7_RespectPunchThrough has no per-trial group votes
+    {
+        CVTT_HD bool any(bool x) const { return x; }
+        CVTT_HD bool all(bool x) const { return x; }
+        CVTT_HD bool warp_any(bool x) const { return x; }
+    };
+
+    // PUNCH: Flags::BC7_RespectPunchThrough; vote = the reference's AnySet / AllSet over the 8 blocks of one call
+    template<bool FAST, int STRIDE, bool PUNCH, class Vote>
+    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, uint32_t out[4])
     {
         BC7Work work;
         work.error = FLT_MAX;
@@ -1322,9 +1420,8 @@ namespace cvttb200
         uint32_t res[kBC7MaxSlots][4];
 
         const bool trySingleColor = (P.flags & kFlag_BC7_TrySingleColor) != 0;
-        // Flags::BC7_RespectPunchThrough is rejected by the host (see launch_bc7): the reference's masking at BC67.cpp:1411 has
-        // the same inverted AndNot, which makes commits order dependent; the hook for a per-parity mask is kept.
-        const uint32_t punchInvalid67 = 0;
+        // BC67.cpp:1286-1295: parity 0 cannot keep alpha 255, parity 3 cannot keep alpha 0, mixed parities keep neither
+        const uint32_t punchInvalid67 = !lf.isPunchThrough ? 0u : ((lf.blockHasNonZeroAlpha ? 1u : 0u) | 6u | (lf.blockHasNonMaxAlpha ? 8u : 0u));
 
         const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;                   // BC67.cpp:1121
         const bool allowMode7 = lf.anyBlockHasAlpha || (P.mode7RGBPartitionEnabled != 0); // BC67.cpp:1078
@@ -1405,22 +1502,22 @@ namespace cvttb200
                         switch (mode)
                         {
                         case 0:
-                            bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
                             if (trySingleColor)
                                 bc7_try_single_color<0, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
                             break;
                         case 1:
-                            bc7_shape_trials<1, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            bc7_shape_trials<1, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
                             if (trySingleColor)
                                 bc7_try_single_color<1, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
                             break;
                         case 2:
-                            bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
                             if (trySingleColor)
                                 bc7_try_single_color<2, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
                             break;
                         default:
-                            bc7_shape_trials<3, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, 0, best);
+                            bc7_shape_trials<3, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
                             if (trySingleColor)
                                 bc7_try_single_color<3, STRIDE>(P, L, n, staticAlphaError, best, scIndex);
                             break;
@@ -1428,7 +1525,7 @@ namespace cvttb200
                     }
                     else if (mode == 6)
                     {
-                        bc7_shape_trials<6, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, punchInvalid67, best);
+                        bc7_shape_trials_67<6, FAST, STRIDE, PUNCH>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, punchInvalid67, vote, best);
                         if (trySingleColor)
                             bc7_try_single_color<6, STRIDE>(P, L, n, 0.0f, best, scIndex);
                     }
@@ -1436,7 +1533,7 @@ namespace cvttb200
                     {
                         if (!lf.warpAnyMode7)
                             continue;
-                        bc7_shape_trials<7, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, punchInvalid67, best);
+                        bc7_shape_trials_67<7, FAST, STRIDE, PUNCH>(P, L.gv, L.gw, n, seeds, baseRGBA, offsRGBA, sumV, punchInvalid67, vote, best);
                         if (trySingleColor)
                             bc7_try_single_color<7, STRIDE>(P, L, n, 0.0f, best, scIndex);
                     }

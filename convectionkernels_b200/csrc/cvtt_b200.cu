@@ -112,13 +112,23 @@ namespace
             atomicAdd(mismatches, bad);
     }
 
+    // The reference's AnySet / AllSet over the 8 lanes of one call (ParallelMath.h:1260-1278): ballots restricted to
+    // the lane's 8-lane segment.  Every lane of the warp executes every vote (control flow around votes is uniform).
+    struct SegmentVote
+    {
+        uint32_t segMask;
+        __device__ __forceinline__ bool any(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) != 0; }
+        __device__ __forceinline__ bool all(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) == segMask; }
+        __device__ __forceinline__ bool warp_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
+    };
+
     // One thread per block, warp = 4 reference groups of one class; see cvtt_common.cuh / bc7_core.cuh.
     //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (512 B contiguous per group) and
     //    keeps it packed in shared memory, laid out [pixel][thread] (conflict-free)
     //  * per pixel subset the search gathers the subset's pixels once into two [index][thread] arrays of fp32x4 (biased
     //    value, pre-weighted value); every trial then streams them with 128-bit conflict-free loads
     //  * output: one 128-bit store per thread
-    template<bool FAST>
+    template<bool FAST, bool PUNCH>
     __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
     bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
                       const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists)
@@ -196,7 +206,17 @@ namespace
         lf.warpAnyMode7 = __any_sync(0xffffffffu, active && mode7);
 
         uint32_t o[4];
-        bc7_encode_block<FAST, kBC7Threads>(P, c_bc7PackTables, L, lf, o);
+        if (PUNCH)
+        {
+            SegmentVote vote;
+            vote.segMask = segMask;
+            bc7_encode_block<FAST, kBC7Threads, true>(P, c_bc7PackTables, L, lf, vote, o);
+        }
+        else
+        {
+            BC7NoVote vote;
+            bc7_encode_block<FAST, kBC7Threads, false>(P, c_bc7PackTables, L, lf, vote, o);
+        }
 
         if (active)
             out[block] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -213,16 +233,6 @@ namespace
     constexpr size_t kBC6HSmemBytesSlow = (size_t)kBC6HThreads * 96 * 4, kBC6HSmemBytesFast = (size_t)kBC6HThreads * 128 * 4;
 
     __constant__ BC6HTables c_bc6hTables;
-
-    // The reference's AnySet / AllSet over the 8 lanes of one call (ParallelMath.h:1260-1278): ballots restricted to
-    // the lane's 8-lane segment.  Every lane of the warp executes every vote (control flow around votes is uniform).
-    struct SegmentVote
-    {
-        uint32_t segMask;
-        __device__ __forceinline__ bool any(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) != 0; }
-        __device__ __forceinline__ bool all(bool x) const { return (__ballot_sync(0xffffffffu, x) & segMask) == segMask; }
-        __device__ __forceinline__ bool warp_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
-    };
 
     // One thread per block, warp = 4 reference groups.  Input: PixelBlockF16 = int16 [16][4] (128 B, alpha ignored), read
     // with eight 128-bit loads per thread; converted once into [word][thread] planes in shared memory (384 B per thread, so
@@ -656,10 +666,14 @@ namespace
             cudaGetLastError();
         }
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc7PackTables, &bc7_pack_tables(), sizeof(BC7PackTables)));
-        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
-        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
         CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
@@ -856,8 +870,6 @@ namespace
 
     int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, cudaStream_t stream)
     {
-        if (options.flags & kFlag_BC7_RespectPunchThrough)
-            return fail(CVTTB200_ERR_UNSUPPORTED, "Flags::BC7_RespectPunchThrough is not implemented (the reference masks its commits with inverted operands, BC67.cpp:1411)");
         if (nBlocks > 0xffffff00u)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
 
@@ -880,10 +892,15 @@ namespace
         // at most three partially filled warps (one per class)
         const unsigned warps = nGroups / 4 + 3;
         const unsigned grid = (warps + kBC7Threads / 32 - 1) / (kBC7Threads / 32);
-        if (options.flags & kFlag_BC7_FastIndexing)
-            bc7_encode_kernel<true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        const bool fast = (options.flags & kFlag_BC7_FastIndexing) != 0, punch = (options.flags & kFlag_BC7_RespectPunchThrough) != 0;
+        if (fast && !punch)
+            bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else if (!fast && !punch)
+            bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else if (fast)
+            bc7_encode_kernel<true, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
         else
-            bc7_encode_kernel<false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+            bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
         g_launches++;
         CVTT_CUDA(cudaFreeAsync(dScratch, stream));
         CVTT_CUDA(cudaGetLastError());

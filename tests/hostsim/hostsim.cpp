@@ -2,12 +2,35 @@
 // so the kernel logic can be checked against the oracle in the GPU-less dev container.  It emulates the
 // kernel's warp of 32 lanes = 4 reference groups; it is NOT part of the product library and the product never
 // falls back to it.
+#include <thread>
 #include <vector>
 #include <xmmintrin.h>
 
 #include "../../convectionkernels_b200/csrc/bc7_host.h"
+#include "host_vote.h"
 
 using namespace cvttb200;
+
+namespace
+{
+    template<bool PUNCH, class Vote>
+    void encode_lane(const BC7Params &P, const BC7PackTables &T, bool fast, const BC7LaneFlags &lf, Vote &vote, const uint8_t *block, uint8_t *out)
+    {
+        uint32_t raw[16];
+        memcpy(raw, block, 64);
+        F4 gv[16], gw[16];
+        BC7Lane<1> L;
+        L.raw = raw;
+        L.gv = gv;
+        L.gw = gw;
+        uint32_t o[4];
+        if (fast)
+            bc7_encode_block<true, 1, PUNCH>(P, T, L, lf, vote, o);
+        else
+            bc7_encode_block<false, 1, PUNCH>(P, T, L, lf, vote, o);
+        memcpy(out, o, 16);
+    }
+}
 
 extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const BC7PlanPOD *plan, const float *rcpTable, int warpFlagsAllTrue)
 {
@@ -70,19 +93,30 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
             lf[l].warpAnyPCA4 = warpFlagsAllTrue ? true : wPCA4;
             lf[l].warpAnyExpand = true;
             lf[l].warpAnyMode7 = warpFlagsAllTrue ? true : wM7;
-            uint32_t raw[16];
-            memcpy(raw, blocks + (warpBase + l) * 64, 64);
-            F4 gv[16], gw[16];
-            BC7Lane<1> L;
-            L.raw = raw;
-            L.gv = gv;
-            L.gw = gw;
-            uint32_t o[4];
-            if (fast)
-                bc7_encode_block<true, 1>(P, T, L, lf[l], o);
-            else
-                bc7_encode_block<false, 1>(P, T, L, lf[l], o);
-            memcpy(out + (warpBase + l) * 16, o, 16);
+        }
+        if (options->flags & kFlag_BC7_RespectPunchThrough)
+        {
+            // per-trial group votes: the eight lanes of a group run as eight threads (host_vote.h)
+            for (size_t g = 0; g < lanes; g += 8)
+            {
+                GroupShared shared;
+                std::vector<std::thread> threads;
+                for (size_t l = g; l < g + 8; l++)
+                    threads.emplace_back([&, l]()
+                    {
+                        HostVote vote;
+                        vote.g = &shared;
+                        encode_lane<true>(P, T, fast, lf[l], vote, blocks + (warpBase + l) * 64, out + (warpBase + l) * 16);
+                    });
+                for (auto &t : threads)
+                    t.join();
+            }
+        }
+        else
+        {
+            BC7NoVote vote;
+            for (size_t l = 0; l < lanes; l++)
+                encode_lane<false>(P, T, fast, lf[l], vote, blocks + (warpBase + l) * 64, out + (warpBase + l) * 16);
         }
     }
     return 0;

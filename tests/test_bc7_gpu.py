@@ -92,10 +92,24 @@ def test_argument_and_flag_errors():
     with pytest.raises(api.CvttError) as e:
         api.encode("BC7", np.zeros((12, 16, 4), np.uint8), o, p)
     assert e.value.status == -1
-    o.flags |= api.Flags.BC7_RespectPunchThrough
     with pytest.raises(api.CvttError) as e:
-        api.encode("BC7", np.zeros((8, 16, 4), np.uint8), o, p)
-    assert e.value.status == -2                   # not implemented is reported, never silently computed elsewhere
+        api.encode("BC7", np.zeros((8, 16, 4), np.uint8), o, None)
+    assert e.value.status == -1                   # BC7 without a plan
+
+
+@pytest.mark.parametrize("flags,quality", [(0x128, 100), (0x1a8, 40), (0x138, 70), (0x328, 100)])
+def test_respect_punch_through_against_reference(reference, flags, quality):
+    """Flags::BC7_RespectPunchThrough: the commits of modes 6 / 7 are masked per group with the reference's inverted AndNot
+    (BC67.cpp:1406-1416), so results depend on the other blocks of the 8-block call; mixed opaque / binary / continuous alpha"""
+    blocks = synth.punchthrough_blocks_rgba8(4096 + 24, seed=61)
+    o, p = api.Options(), api.BC7EncodingPlan()
+    o.flags = flags
+    api.ConfigureBC7EncodingPlanFromQuality(p, quality)
+    want = reference.encode("BC7", blocks, _opt_bytes(o), _plan_bytes(p), threads=0)
+    got = api.EncodeBC7(blocks, o, p)
+    assert (got == want).all(), first_mismatch(want, got)
+    o.flags = flags & ~0x20
+    assert (api.EncodeBC7(blocks, o, p) != got).any()          # the flag does change results on this input
 
 
 def test_against_reference_on_this_host(reference):

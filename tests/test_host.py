@@ -84,7 +84,7 @@ def hostsim():
     out = os.path.join(ROOT, "tests", "_build", "libcvtt_hostsim.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     csrc = os.path.join(ROOT, "convectionkernels_b200", "csrc")
-    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-w", "-DCVTT_HOSTSIM", "-I", csrc, "-o", out,
+    subprocess.check_call(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off", "-msse2", "-pthread", "-w", "-DCVTT_HOSTSIM", "-I", csrc, "-o", out,
                            os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp"), os.path.join(csrc, "bc7_host.cpp")])
     H = ctypes.CDLL(out)
     H.hostsim_encode_bc7.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]

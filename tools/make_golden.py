@@ -106,3 +106,7 @@ save("etc2punch_mixed", "ETC2_PUNCHTHROUGH", pt, options())
 save("etc2punch_mixed_uniform_thr09", "ETC2_PUNCHTHROUGH", pt[:256], options(flags=0x308, threshold=0.9))
 save("etc2punch_mixed_bt709_thr03", "ETC2_PUNCHTHROUGH", pt[:256], options(flags=0x508, threshold=0.3))
 save("etc2punch_mixed_thr2", "ETC2_PUNCHTHROUGH", pt[:64], options(threshold=2.0))
+
+# Flags::BC7_RespectPunchThrough (exact and fast indexing, with BC7_TrySingleColor): commits of modes 6 / 7 depend on the group
+save("bc7_punch_respect_q100", "BC7", pt[:256], options(flags=0x128), q100)
+save("bc7_punch_respect_fast_sc_q40", "BC7", pt[256:512], options(flags=0x1b8), q40)
