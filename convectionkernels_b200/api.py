@@ -108,6 +108,7 @@ def _lib():
         L.cvttb200_input_block_bytes.restype = ctypes.c_size_t
         L.cvttb200_output_block_bytes.restype = ctypes.c_size_t
         L.cvttb200_encode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cvttb200_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.cvttb200_set_rcp_table.argtypes = [ctypes.c_void_p]
         L.cvttb200_get_rcp_table.argtypes = [ctypes.c_void_p]
         _LIB = L
@@ -306,6 +307,46 @@ def tiled_block_count(width, height):
     L = _lib()
     L.cvttb200_tiled_block_count.restype = ctypes.c_size_t
     return int(L.cvttb200_tiled_block_count(int(width), int(height)))
+
+
+def decode(fmt, pBC, out=None):
+    """Decodes n 16-byte blocks (numpy array or torch CUDA tensor) of `fmt` ("BC7" -> (n, 16, 4) uint8 PixelBlockU8, "BC6HU" /
+    "BC6HS" -> (n, 16, 4) int16 PixelBlockF16 half bits, alpha = 0x3c00)."""
+    L = _lib()
+    f = FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
+    is_bc7 = f == FORMATS["BC7"]
+    if _is_torch(pBC):
+        import torch
+        src = pBC.contiguous()
+        n = (src.numel() * src.element_size()) // 16
+        if out is None:
+            out = torch.empty((n, 16, 4), dtype=torch.uint8 if is_bc7 else torch.int16, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream if src.is_cuda else None
+        with torch.cuda.device(src.device if src.is_cuda else torch.cuda.current_device()):
+            st = L.cvttb200_decode(f, src.data_ptr(), n, out.data_ptr(), stream)
+    else:
+        src = np.ascontiguousarray(pBC)
+        n = (src.size * src.itemsize) // 16
+        if out is None:
+            out = np.empty((n, 16, 4), dtype=np.uint8 if is_bc7 else np.int16)
+        st = L.cvttb200_decode(f, src.ctypes.data, n, out.ctypes.data, None)
+    _check(st)
+    return out
+
+
+def DecodeBC7(pBC, out=None):
+    """cvtt::Kernels::DecodeBC7, reference ConvectionKernels.h:275 / ConvectionKernels_API.cpp:288-298"""
+    return decode("BC7", pBC, out)
+
+
+def DecodeBC6HU(pBC, out=None):
+    """cvtt::Kernels::DecodeBC6HU, reference ConvectionKernels.h:273 / ConvectionKernels_API.cpp:300-310"""
+    return decode("BC6HU", pBC, out)
+
+
+def DecodeBC6HS(pBC, out=None):
+    """cvtt::Kernels::DecodeBC6HS, reference ConvectionKernels.h:274 / ConvectionKernels_API.cpp:312-322"""
+    return decode("BC6HS", pBC, out)
 
 
 def tile_image(image, out=None):

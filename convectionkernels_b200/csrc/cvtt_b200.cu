@@ -20,6 +20,7 @@
 #include "bc6h_host.h"
 #include "etc_host.h"
 #include "s3tc_host.h"
+#include "decode_core.cuh"
 
 using namespace cvttb200;
 
@@ -576,6 +577,88 @@ namespace
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// BC7 / BC6H decoders (DecodeBC7 / DecodeBC6HU / DecodeBC6HS): 16 bytes in, 64 or 128 bytes out per block
+
+namespace
+{
+    constexpr int kDecodeThreads = 256;
+
+    struct DecodeTables
+    {
+        BC7PackTables bc7;
+        BC6HTables bc6h;
+    };
+    __device__ DecodeTables g_decodeTables;         // global-memory copy: the decoders index the tables per lane
+
+    // The warp's output tile in shared memory as 16-byte chunks, CHUNKS per block.  A lane writes its own block's chunks, the
+    // warp then streams the tile out with consecutive lanes on consecutive chunks; the XOR keeps both phases conflict-free.
+    template<int CHUNKS>
+    struct TileSink
+    {
+        uint4 *tile;
+        uint32_t lane;
+        __device__ __forceinline__ static uint32_t slot(uint32_t t, uint32_t q)
+        {
+            return t * CHUNKS + (q ^ (CHUNKS == 4 ? ((t >> 1) & 3u) : (t & 7u)));
+        }
+        __device__ __forceinline__ void put4(int q, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const
+        {
+            tile[slot(lane, (uint32_t)q)] = make_uint4(a, b, c, d);
+        }
+    };
+
+    // KIND: 0 BC7, 1 BC6H unsigned, 2 BC6H signed.  One thread per block, warps walk 32-block slices (persistent grid).
+    template<int KIND>
+    __global__ void __launch_bounds__(kDecodeThreads)
+    decode_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
+    {
+        constexpr int CHUNKS = (KIND == 0) ? 4 : 8;
+        __shared__ __align__(16) DecodeTables sTables;
+        __shared__ __align__(16) uint4 sTile[kDecodeThreads * CHUNKS];
+
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_decodeTables);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sTables);
+            for (uint32_t i = threadIdx.x; i < sizeof(DecodeTables) / 4; i += kDecodeThreads)
+                dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+
+        const uint32_t lane = threadIdx.x & 31, warpInCta = threadIdx.x >> 5;
+        TileSink<CHUNKS> sink;
+        sink.tile = sTile + warpInCta * 32 * CHUNKS;
+        sink.lane = lane;
+
+        const uint32_t warpsPerGrid = gridDim.x * (kDecodeThreads / 32);
+        const uint32_t nSlices = (nBlocks + 31) / 32;
+        for (uint32_t slice = blockIdx.x * (kDecodeThreads / 32) + warpInCta; slice < nSlices; slice += warpsPerGrid)
+        {
+            const uint32_t block = slice * 32 + lane;
+            if (block < nBlocks)
+            {
+                const uint4 v = __ldg(in + block);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                if (KIND == 0)
+                    bc7_decode_block(sTables.bc7, w, sink);
+                else
+                    bc6h_decode_block(sTables.bc6h, w, KIND == 2, sink);
+            }
+            __syncwarp();
+            const uint32_t valid = min(32u, nBlocks - slice * 32) * CHUNKS;
+            uint4 *dst = out + (size_t)slice * 32 * CHUNKS;
+#pragma unroll
+            for (int k = 0; k < CHUNKS; k++)
+            {
+                const uint32_t c = k * 32 + lane;
+                if (c < valid)
+                    dst[c] = sink.tile[TileSink<CHUNKS>::slot(c / CHUNKS, c % CHUNKS)];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // =========================================================================================================
 // Host state
 
@@ -675,6 +758,12 @@ namespace
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CVTT_CUDA(cudaMemcpyToSymbol(c_bc6hTables, &bc6h_tables(), sizeof(BC6HTables)));
+        {
+            DecodeTables dt;
+            dt.bc7 = bc7_pack_tables();
+            dt.bc6h = bc6h_tables();
+            CVTT_CUDA(cudaMemcpyToSymbol(g_decodeTables, &dt, sizeof(dt)));
+        }
         CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
@@ -903,6 +992,28 @@ namespace
             bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
         g_launches++;
         CVTT_CUDA(cudaFreeAsync(dScratch, stream));
+        CVTT_CUDA(cudaGetLastError());
+        return CVTTB200_OK;
+    }
+}
+
+
+namespace
+{
+    int launch_decode(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, cudaStream_t stream)
+    {
+        if (nBlocks > 0xffffff00u)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
+        const unsigned grid = (unsigned)std::min<size_t>((nBlocks + kDecodeThreads - 1) / kDecodeThreads, (size_t)ctx.numSMs * 8);
+        const uint4 *in = (const uint4 *)dIn;
+        uint4 *out = (uint4 *)dOut;
+        if (format == CVTTB200_BC7)
+            decode_kernel<0><<<grid, kDecodeThreads, 0, stream>>>(in, out, (uint32_t)nBlocks);
+        else if (format == CVTTB200_BC6HU)
+            decode_kernel<1><<<grid, kDecodeThreads, 0, stream>>>(in, out, (uint32_t)nBlocks);
+        else
+            decode_kernel<2><<<grid, kDecodeThreads, 0, stream>>>(in, out, (uint32_t)nBlocks);
+        g_launches++;
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
     }
@@ -1184,6 +1295,57 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
 
     if (!outOnDevice)
         CVTT_CUDA(cudaMemcpyAsync(out, dOut, nBlocks * outBytes, cudaMemcpyDeviceToHost, stream));
+    if (!inOnDevice || !outOnDevice)
+        CVTT_CUDA(cudaStreamSynchronize(stream));
+    return CVTTB200_OK;
+}
+
+int cvttb200_decode(int format, const void *encoded, size_t nBlocks, void *pixelBlocks, void *streamPtr)
+{
+    if (!encoded || !pixelBlocks)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
+    if (format != CVTTB200_BC7 && format != CVTTB200_BC6HU && format != CVTTB200_BC6HS)
+        return fail(CVTTB200_ERR_UNSUPPORTED, "the reference decodes BC7, BC6HU and BC6HS only");
+    if (nBlocks == 0)
+        return CVTTB200_OK;
+    const size_t inBytes = 16, outBytes = cvttb200_input_block_bytes(format);      // a decoded block is the encoder's input block
+
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int device = 0;
+    {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "cudaGetDevice");
+    }
+    DeviceContext *ctx = nullptr;
+    int rc = get_context(device, &ctx);
+    if (rc != CVTTB200_OK)
+        return rc;
+
+    cudaStream_t stream = (cudaStream_t)streamPtr;
+    const bool inOnDevice = is_device_pointer(encoded), outOnDevice = is_device_pointer(pixelBlocks);
+    const void *dIn = encoded;
+    void *dOut = pixelBlocks;
+    if (!inOnDevice)
+    {
+        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, nBlocks * inBytes);
+        if (rc != CVTTB200_OK)
+            return rc;
+        CVTT_CUDA(cudaMemcpyAsync(ctx->stageIn, encoded, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
+        dIn = ctx->stageIn;
+    }
+    if (!outOnDevice)
+    {
+        rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, nBlocks * outBytes);
+        if (rc != CVTTB200_OK)
+            return rc;
+        dOut = ctx->stageOut;
+    }
+    rc = launch_decode(*ctx, format, dIn, nBlocks, dOut, stream);
+    if (rc != CVTTB200_OK)
+        return rc;
+    if (!outOnDevice)
+        CVTT_CUDA(cudaMemcpyAsync(pixelBlocks, dOut, nBlocks * outBytes, cudaMemcpyDeviceToHost, stream));
     if (!inOnDevice || !outOnDevice)
         CVTT_CUDA(cudaStreamSynchronize(stream));
     return CVTTB200_OK;

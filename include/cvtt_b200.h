@@ -181,6 +181,14 @@ int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t bl
 int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out,
                     const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *stream);
 
+/* ---- decoders ---------------------------------------------------------------------------------------------
+ * cvtt::Kernels::DecodeBC7 / DecodeBC6HU / DecodeBC6HS (ConvectionKernels.h:273-275, ConvectionKernels_API.cpp:288-322 ->
+ * BC7Computer::UnpackOne BC67.cpp:2206-2423, BC6HComputer::UnpackOne :3059-3289).  format: CVTTB200_BC7 (-> PixelBlockU8, 64 B
+ * per block) or CVTTB200_BC6HU / CVTTB200_BC6HS (-> PixelBlockF16, 128 B per block, alpha = 1.0).  Any block count; blocks are
+ * independent.  Pointer kinds, stream and return value as for cvttb200_encode.  Invalid blocks decode like the reference's:
+ * BC7 without a mode bit -> all zero, reserved BC6H modes -> (0, 0, 0, 1.0). */
+int cvttb200_decode(int format, const void *encoded, size_t nBlocks, void *pixelBlocks, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

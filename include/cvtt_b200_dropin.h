@@ -6,7 +6,7 @@
 // by  #include "cvtt_b200_dropin.h"         + link -lcvtt_b200
 // and keeps calling cvtt::Kernels::EncodeBC7 / EncodeBC1..5 / EncodeBC6H* / EncodeETC* with 8 blocks per call.  For
 // throughput, call cvtt::Kernels::B200::Encode with a whole image's blocks instead (same result, one launch).  The decoders
-// (DecodeBC7 / DecodeBC6H*) are CPU code in the reference and are not part of this library.
+// (DecodeBC7 / DecodeBC6HU / DecodeBC6HS) are provided the same way (B200::Decode for whole images).
 //
 // Types derive from the C PODs, so their layout is the reference's by construction (checked by static_assert below).
 // Error behaviour: the reference's functions return void and only assert; this shim prints cvttb200_last_error() and
@@ -102,6 +102,12 @@ namespace cvtt
             {
                 Check(cvttb200_encode(CVTTB200_BC7, pBlocks, numBlocks, pBC, &options, &encodingPlan, cudaStream), "EncodeBC7");
             }
+
+            // whole-image decode: format is CVTTB200_BC7 (PixelBlockU8 out) or CVTTB200_BC6HU / _BC6HS (PixelBlockF16 out)
+            inline void Decode(int format, void *pBlocks, const uint8_t *pBC, size_t numBlocks, void *cudaStream = NULL)
+            {
+                Check(cvttb200_decode(format, pBC, numBlocks, pBlocks, cudaStream), "Decode");
+            }
         }
 
         // The reference's entry points (ConvectionKernels.h:242-259): NumParallelBlocks blocks in, NumParallelBlocks blocks out.
@@ -127,6 +133,11 @@ namespace cvtt
         {
             B200::Encode(isSigned ? CVTTB200_EAC_R11S : CVTTB200_EAC_R11U, pBC, pBlocks, NumParallelBlocks, options);
         }
+
+        // ConvectionKernels.h:273-275
+        inline void DecodeBC6HU(PixelBlockF16 *pBlocks, const uint8_t *pBC) { B200::Decode(CVTTB200_BC6HU, pBlocks, pBC, NumParallelBlocks); }
+        inline void DecodeBC6HS(PixelBlockF16 *pBlocks, const uint8_t *pBC) { B200::Decode(CVTTB200_BC6HS, pBlocks, pBC, NumParallelBlocks); }
+        inline void DecodeBC7(PixelBlockU8 *pBlocks, const uint8_t *pBC) { B200::Decode(CVTTB200_BC7, pBlocks, pBC, NumParallelBlocks); }
 
         inline ETC2CompressionData *AllocETC2Data(allocFunc_t allocFunc, void *context, const Options &options)
         {

@@ -94,6 +94,17 @@ class Reference:
         assert rc == 0
         return out
 
+    def decode(self, fmt, bc):
+        """cvtt::Kernels::DecodeBC7 / DecodeBC6HU / DecodeBC6HS on n encoded blocks (n % 8 == 0)"""
+        bc = _as_u8(bc)
+        n = bc.size // 16
+        assert n % 8 == 0
+        out = np.zeros((n, 16, 4), dtype=np.uint8 if fmt == "BC7" else np.int16)
+        rc = self.lib.cvttref_decode(FMT[fmt], bc.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise ValueError("cvttref_decode rc=%d" % rc)
+        return out
+
     def rcp(self, v):
         return float(self.lib.cvttref_rcp(ctypes.c_float(v)))
 
