@@ -333,10 +333,16 @@ namespace cvttb200
     // ---------------------------------------------------------------------------------------------------------
     // One pair of trials of the inner search (one per fp32 lane): index selection, reconstruction error and
     // (REFINE) the refiner's sums over the n gathered pixels (BC67.cpp:1355-1392).
-    //   nom = -(q0 + kMagic), nd64 = -(q1 - q0) / 64, nbq = -(q0 + 1/128): negated so that the loop only adds
+    //   nom = -(q0 + kMagic), nd64 = -((q1 - q0) / 64 + 2^-20): negated so that the loop only adds.
+    //
+    // Reconstruction in one rounding.  ReconstructLDR_BC7 is floor(x + 1/2) with x = q0 + w (q1 - q0) / 64, a multiple of
+    // 1/64.  fma(w, nd64, nom) evaluates -(x + w 2^-20) - kMagic exactly and rounds it once, at kMagic's scale, to an
+    // integer (round-to-nearest-even).  The w 2^-20 <= 2^-14 term only matters when x is exactly half way (it is then the
+    // tie-break towards x + 1/2, which is what the floor does); any other x is at least 1/64 away from a half.  For w = 0,
+    // x = q0 is an integer.  (q1 - q0) / 64 + 2^-20 needs 22 significant bits, so nd64 is exact.
     template<int NCH, int IB, bool FAST, bool REFINE, int STRIDE>
     CVTT_HD f2 bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const f2 *nom, const f2 *axis, const f2 *nd64,
-        const f2 *nbq, f2 *tv, f2 &tt, f2 &ts)
+        f2 *tv, f2 &tt, f2 &ts)
     {
         const float maxV = (float)((1 << IB) - 1), wScale = 64.0f / (float)((1 << IB) - 1), rcpMaxIndex = 1.0f / (float)((1 << IB) - 1);
         f2 acc[NCH];
@@ -364,7 +370,7 @@ namespace cvttb200
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
-                const f2 df = f2_add(f2_sub(f2_fma(wf, nd64[ch], nbq[ch]), kMagic), pv[ch]);
+                const f2 df = f2_add(f2_fma(wf, nd64[ch], nom[ch]), pv[ch]);
                 if (FAST)
                     acc[ch] = f2_fma(df, df, acc[ch]);              // exact (< 2^24)
                 else
@@ -390,7 +396,7 @@ namespace cvttb200
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
                     {
-                        const f2 df = f2_add(f2_sub(f2_fma(awf, nd64[ch], nbq[ch]), kMagic), pv[ch]);
+                        const f2 df = f2_add(f2_fma(awf, nd64[ch], nom[ch]), pv[ch]);
                         const f2 sq = f2_mul(df, df);
                         altError = (ch == 0) ? f2_mul(sq, P.wSq[0]) : f2_add(altError, f2_mul(sq, P.wSq[ch]));
                     }
@@ -565,7 +571,7 @@ namespace cvttb200
 
             // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
             // the fourth channel contributes exactly +0 to every sum below and is left out.
-            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH], nbq[NCH];
+            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
@@ -584,8 +590,7 @@ namespace cvttb200
             {
                 axis[ch] = f2_mul(f2_mul(dW[ch], P.w[ch]), mdl);
                 nom[ch] = f2_neg(q0b[ch]);
-                nd64[ch] = f2_mul(dq[ch], -0.015625f);                  // exact
-                nbq[ch] = f2_sub(f2_sub(kMagic, q0b[ch]), 0.0078125f);  // -(q0 + 1/128), both steps exact
+                nd64[ch] = f2_fma(dq[ch], -0.015625f, f2_splat(-9.5367431640625e-07f));     // -(dq / 64 + 2^-20), exact
             }
 
             f2 tv[NCH], tt = f2_splat(0.0f), ts = f2_splat(0.0f);
@@ -595,9 +600,9 @@ namespace cvttb200
 
             f2 shapeError;
             if (lastRound)
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, nbq, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
             else
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, nbq, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
             if (NCH == 3)
                 shapeError = f2_add(shapeError, staticAlphaError);
 

@@ -1,0 +1,298 @@
+// BC7 translation unit of libcvtt_b200.so: classification pre-pass, encode kernels, their launch and device set-up.
+// Built with -fmad=false (numerical contract); see build.py.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cvtt_internal.h"
+#include "bc7_host.h"
+#include "cvtt_segment.cuh"
+
+using namespace cvttb200;
+
+namespace
+{
+    constexpr int kBC7Threads = 384;     // 12 warps = 48 reference groups per CTA, one CTA per SM
+    constexpr int kBC7CtasPerSM = 1;
+    // per thread: 16 packed pixels + 16 gathered biased pixels + 16 gathered pre-weighted pixels
+    constexpr size_t kBC7SmemBytes = (size_t)kBC7Threads * 16 * (sizeof(uint32_t) + 2 * sizeof(F4));
+
+    __constant__ BC7PackTables c_bc7PackTables;
+
+    // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
+    // group-wide votes of BC7Computer::TrySinglePlane (BC67.cpp:1069-1072), so that every warp of the encode kernel
+    // holds four groups that walk the same set of modes.  Pure scheduling: the encode kernel recomputes the votes.
+    //   class 0: opaque group (RGB modes, no 4-channel fits, mode 7 only if the plan asks for it on RGB)
+    //   class 1: some block has alpha and some block is (nearly) opaque: every mode runs
+    //   class 2: every block has alpha <= 250 somewhere: RGB modes 0-3 are off
+    // lists[c * nGroups + i] = i-th group of class c (order within a class is not deterministic and does not matter).
+    __global__ void __launch_bounds__(256)
+    bc7_classify_kernel(const uint4 *__restrict__ in, uint32_t nBlocks, uint32_t nGroups, uint32_t *__restrict__ counts, uint32_t *__restrict__ lists)
+    {
+        const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool active = block < nBlocks;
+        uint32_t minAlpha = 255;
+        if (active)
+        {
+            const uint4 *src = in + (size_t)block * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                minAlpha = min(minAlpha, min(min(v.x >> 24, v.y >> 24), min(v.z >> 24, v.w >> 24)));
+            }
+        }
+        const uint32_t segMask = 0xffu << (threadIdx.x & 24);
+        const bool anyAlpha = (__ballot_sync(0xffffffffu, active && minAlpha < 255) & segMask) != 0;
+        const bool allowRGB = (__ballot_sync(0xffffffffu, active && minAlpha > 250) & segMask) != 0;
+        if (active && (threadIdx.x & 7) == 0)
+        {
+            const int cls = !anyAlpha ? 0 : (allowRGB ? 1 : 2);
+            const uint32_t pos = atomicAdd(counts + cls, 1u);
+            lists[(size_t)cls * nGroups + pos] = block >> 3;
+        }
+    }
+
+    // cvttb200_selftest: f2_div against the compiler's IEEE division
+    __device__ __forceinline__ uint32_t selftest_hash(uint64_t x)
+    {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+        return (uint32_t)x;
+    }
+
+    __device__ __forceinline__ float selftest_operand(uint32_t h)
+    {
+        // sign | exponent in [127 - 40, 127 + 40] | 23 random mantissa bits
+        const uint32_t e = 127u - 40u + (h >> 23) % 81u;
+        return __uint_as_float((h & 0x80000000u) | (e << 23) | (h & 0x007fffffu));
+    }
+
+    __global__ void selftest_div_kernel(uint64_t samples, uint64_t seed, unsigned long long *mismatches)
+    {
+        unsigned long long bad = 0;
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < samples; i += (uint64_t)gridDim.x * blockDim.x)
+        {
+            const uint32_t h0 = selftest_hash(seed + 4 * i), h1 = selftest_hash(seed + 4 * i + 1), h2 = selftest_hash(seed + 4 * i + 2), h3 = selftest_hash(seed + 4 * i + 3);
+            f2 a = f2_make(selftest_operand(h0), selftest_operand(h1));
+            const f2 b = f2_make(selftest_operand(h2), selftest_operand(h3));
+            if ((h0 & 0xff) == 0)
+                a.x = 0.0f;
+            if ((h1 & 0xff) == 1)       // small integers over small integers, the shape of maxV / lenSq
+            {
+                a.y = (float)(1 + (h1 >> 8) % 15);
+            }
+            const f2 q = f2_div(a, b);
+            const float wx = __fdiv_rn(a.x, b.x), wy = __fdiv_rn(a.y, b.y);
+            if (__float_as_uint(q.x) != __float_as_uint(wx) && !(q.x == 0.0f && wx == 0.0f))
+                bad++;
+            if (__float_as_uint(q.y) != __float_as_uint(wy) && !(q.y == 0.0f && wy == 0.0f))
+                bad++;
+        }
+        if (bad)
+            atomicAdd(mismatches, bad);
+    }
+
+
+    // One thread per block, warp = 4 reference groups of one class; see cvtt_common.cuh / bc7_core.cuh.
+    //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (512 B contiguous per group) and
+    //    keeps it packed in shared memory, laid out [pixel][thread] (conflict-free)
+    //  * per pixel subset the search gathers the subset's pixels once into two [index][thread] arrays of fp32x4 (biased
+    //    value, pre-weighted value); every trial then streams them with 128-bit conflict-free loads
+    //  * output: one 128-bit store per thread
+    template<bool FAST, bool PUNCH>
+    __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
+    bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists)
+    {
+        extern __shared__ __align__(16) unsigned char smem[];
+        F4 *sGv = reinterpret_cast<F4 *>(smem);
+        F4 *sGw = sGv + 16 * kBC7Threads;
+        uint32_t *sRaw = reinterpret_cast<uint32_t *>(sGw + 16 * kBC7Threads);
+
+        const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+        // warp -> (class, four groups of that class); the expensive classes go first so that the tail of the launch is
+        // filled by the cheap opaque warps
+        const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
+        const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
+        uint32_t warp = blockIdx.x * (kBC7Threads / 32) + (tid >> 5);
+        uint32_t cls, clsCount;
+        if (warp < w1) { cls = 1; clsCount = n1; }
+        else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
+        else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
+        else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
+        const uint32_t slot = warp * 4 + (lane >> 3);
+        const bool active = slot < clsCount;
+        const uint32_t block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
+
+        BC7Lane<kBC7Threads> L;
+        L.raw = sRaw + tid;
+        L.gv = sGv + tid;
+        L.gw = sGw + tid;
+
+        uint32_t minAlpha = 255, maxAlpha = 0;
+        bool isPunchThrough = true;
+        if (active)
+        {
+            const uint4 *src = in + (size_t)block * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const uint4 v = __ldg(src + q);
+                minAlpha = min(minAlpha, min(min(v.x >> 24, v.y >> 24), min(v.z >> 24, v.w >> 24)));
+                maxAlpha = max(maxAlpha, max(max(v.x >> 24, v.y >> 24), max(v.z >> 24, v.w >> 24)));
+                const uint32_t a[4] = { v.x >> 24, v.y >> 24, v.z >> 24, v.w >> 24 };
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    isPunchThrough = isPunchThrough && (a[k] == 0 || a[k] == 255);
+                sRaw[(q * 4 + 0) * kBC7Threads + tid] = v.x;
+                sRaw[(q * 4 + 1) * kBC7Threads + tid] = v.y;
+                sRaw[(q * 4 + 2) * kBC7Threads + tid] = v.z;
+                sRaw[(q * 4 + 3) * kBC7Threads + tid] = v.w;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int px = 0; px < 16; px++)
+                sRaw[px * kBC7Threads + tid] = 0xff000000u;
+        }
+        __syncwarp();
+
+        // group votes (reference AnySet over the 8 lanes of one call, BC67.cpp:1069-1072) and warp-level skips
+        const uint32_t segMask = 0xffu << (lane & 24);
+        const uint32_t hasAlphaBallot = __ballot_sync(0xffffffffu, active && minAlpha < 255);
+        const uint32_t allowRGBBallot = __ballot_sync(0xffffffffu, active && minAlpha > 250);
+        BC7LaneFlags lf;
+        lf.anyBlockHasAlpha = (hasAlphaBallot & segMask) != 0;
+        lf.allowRGBModes = (allowRGBBallot & segMask) != 0;
+        lf.blockHasNonMaxAlpha = minAlpha < 255;
+        lf.blockHasNonZeroAlpha = maxAlpha > 0;
+        lf.isPunchThrough = isPunchThrough;
+        const bool usePCA4 = lf.anyBlockHasAlpha || !lf.allowRGBModes;
+        const bool mode7 = lf.anyBlockHasAlpha || P.mode7RGBPartitionEnabled != 0;
+        lf.warpAnyRGB = __any_sync(0xffffffffu, active && lf.allowRGBModes);
+        lf.warpAnyPCA4 = __any_sync(0xffffffffu, active && usePCA4);
+        lf.warpAnyExpand = true;
+        lf.warpAnyMode7 = __any_sync(0xffffffffu, active && mode7);
+
+        uint32_t o[4];
+        if (PUNCH)
+        {
+            SegmentVote vote;
+            vote.segMask = segMask;
+            bc7_encode_block<FAST, kBC7Threads, true>(P, c_bc7PackTables, L, lf, vote, o);
+        }
+        else
+        {
+            BC7NoVote vote;
+            bc7_encode_block<FAST, kBC7Threads, false>(P, c_bc7PackTables, L, lf, vote, o);
+        }
+
+        if (active)
+            out[block] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+namespace cvttb200
+{
+    int bc7_device_setup()
+    {
+        CVTT_CUDA(cudaMemcpyToSymbol(c_bc7PackTables, &bc7_pack_tables(), sizeof(BC7PackTables)));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7SmemBytes));
+        CVTT_CUDA(cudaFuncSetAttribute(bc7_encode_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        return CVTTB200_OK;
+    }
+
+    // f2_div against __fdiv_rn on `samples` operand pairs (cvttb200_selftest)
+    int bc7_selftest_div(uint64_t samples, uint64_t seed, uint64_t *mismatches)
+    {
+        unsigned long long *dBad = nullptr;
+        CVTT_CUDA(cudaMalloc((void **)&dBad, sizeof(unsigned long long)));
+        CVTT_CUDA(cudaMemset(dBad, 0, sizeof(unsigned long long)));
+        selftest_div_kernel<<<148 * 8, 256>>>(samples, seed, dBad);
+        g_launches++;
+        unsigned long long bad = 0;
+        cudaError_t e = cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost);
+        cudaFree(dBad);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "selftest_div_kernel");
+        *mismatches = bad;
+        return CVTTB200_OK;
+    }
+
+    // caller holds g_mutex and has made ctx.device current
+    static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, const uint32_t **dCmds)
+    {
+        for (size_t i = 0; i < ctx.plans.size(); i++)
+            if (memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
+            {
+                *dCmds = ctx.plans[i].dCmds;
+                return CVTTB200_OK;
+            }
+        std::vector<uint32_t> cmds;
+        const int slots = bc7_compile_plan(plan, cmds);
+        if (slots > kBC7MaxSlots)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "BC7 plan needs more result slots than the kernel provides");
+        if (ctx.plans.size() >= 16)
+        {
+            cudaFree(ctx.plans.front().dCmds);
+            ctx.plans.erase(ctx.plans.begin());
+        }
+        PlanCacheEntry entry;
+        entry.plan = plan;
+        entry.dCmds = nullptr;
+        CVTT_CUDA(cudaMalloc(&entry.dCmds, cmds.size() * sizeof(uint32_t)));
+        CVTT_CUDA(cudaMemcpy(entry.dCmds, cmds.data(), cmds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ctx.plans.push_back(entry);
+        *dCmds = entry.dCmds;
+        return CVTTB200_OK;
+    }
+
+    int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, const float *rcpN, cudaStream_t stream)
+    {
+        if (nBlocks > 0xffffff00u)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
+
+        BC7Params P;
+        bc7_fill_params(P, options, plan, rcpN);
+        const uint32_t *dCmds = nullptr;
+        int rc = get_plan_commands(ctx, plan, &dCmds);
+        if (rc != CVTTB200_OK)
+            return rc;
+        P.cmds = dCmds;
+
+        // stream-ordered scratch for the group classification: counts[4] then lists[3][nGroups]
+        const uint32_t nGroups = (uint32_t)(nBlocks / 8);
+        uint32_t *dScratch = nullptr;
+        CVTT_CUDA(cudaMallocAsync((void **)&dScratch, (4 + 3 * (size_t)nGroups) * sizeof(uint32_t), stream));
+        CVTT_CUDA(cudaMemsetAsync(dScratch, 0, 4 * sizeof(uint32_t), stream));
+        bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
+        g_launches++;
+
+        // at most three partially filled warps (one per class)
+        const unsigned warps = nGroups / 4 + 3;
+        const unsigned grid = (warps + kBC7Threads / 32 - 1) / (kBC7Threads / 32);
+        const bool fast = (options.flags & kFlag_BC7_FastIndexing) != 0, punch = (options.flags & kFlag_BC7_RespectPunchThrough) != 0;
+        if (fast && !punch)
+            bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else if (!fast && !punch)
+            bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else if (fast)
+            bc7_encode_kernel<true, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        else
+            bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+        g_launches++;
+        CVTT_CUDA(cudaFreeAsync(dScratch, stream));
+        CVTT_CUDA(cudaGetLastError());
+        return CVTTB200_OK;
+    }
+}

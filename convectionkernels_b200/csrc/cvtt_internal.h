@@ -1,0 +1,56 @@
+// Host-side plumbing shared by the translation units of libcvtt_b200.so: error reporting, the per-device context and the
+// launch entry points each kernel TU exports (bc7_kernels.cu, bc6h_kernels.cu, etc_kernels.cu, s3tc_kernels.cu).  The TUs
+// are independent (own kernels, own __constant__ tables), so the library needs no relocatable device code and the TUs
+// compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/cvtt_b200.h"
+#include "cvtt_common.cuh"
+
+namespace cvttb200
+{
+    extern std::atomic<uint64_t> g_launches;          // kernels launched by this library (cvttb200_launch_count)
+
+    int fail(int code, const std::string &msg);
+    int fail_cuda(cudaError_t e, const char *what);
+
+#define CVTT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ::cvttb200::fail_cuda(e_, #call); } while (0)
+
+    struct PlanCacheEntry
+    {
+        BC7PlanPOD plan;
+        uint32_t *dCmds;
+    };
+
+    struct DeviceContext
+    {
+        int device = -1;
+        bool ready = false;
+        int numSMs = 0;
+        std::vector<PlanCacheEntry> plans;
+        void *stageIn = nullptr, *stageOut = nullptr;
+        size_t stageInBytes = 0, stageOutBytes = 0;
+    };
+
+    // Per-TU device set-up (constant tables, kernel attributes) for the current device, and the launches.  All return a
+    // CVTTB200_* code; the caller holds the library mutex and has made the context's device current.  rcpN is the host's
+    // _mm_rcp_ps table (cvttb200_set_rcp_table).
+    int bc7_device_setup();
+    int launch_bc7(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const BC7PlanPOD &plan, const float *rcpN, cudaStream_t stream);
+    int bc7_selftest_div(uint64_t samples, uint64_t seed, uint64_t *mismatches);
+
+    int bc6h_device_setup();
+    int launch_bc6h(const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, bool isSigned, const float *rcpN, cudaStream_t stream);
+
+    int etc_device_setup();
+    int launch_etc(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, cudaStream_t stream);
+
+    int launch_s3tc(int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const float *rcpN, cudaStream_t stream);
+}
