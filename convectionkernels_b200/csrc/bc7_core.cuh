@@ -333,16 +333,30 @@ namespace cvttb200
     // ---------------------------------------------------------------------------------------------------------
     // One pair of trials of the inner search (one per fp32 lane): index selection, reconstruction error and
     // (REFINE) the refiner's sums over the n gathered pixels (BC67.cpp:1355-1392).
-    //   nom = -(q0 + kMagic), nd64 = -((q1 - q0) / 64 + 2^-20): negated so that the loop only adds.
+    //   nom = -(q0 + kMagic), nd64 = -((q1 - q0) / 64 + 2^-20), nk = -(kMagic + q0 - (q1 - q0)): negated so that the
+    //   loop only adds.
     //
     // Reconstruction in one rounding.  ReconstructLDR_BC7 is floor(x + 1/2) with x = q0 + w (q1 - q0) / 64, a multiple of
-    // 1/64.  fma(w, nd64, nom) evaluates -(x + w 2^-20) - kMagic exactly and rounds it once, at kMagic's scale, to an
-    // integer (round-to-nearest-even).  The w 2^-20 <= 2^-14 term only matters when x is exactly half way (it is then the
-    // tie-break towards x + 1/2, which is what the floor does); any other x is at least 1/64 away from a half.  For w = 0,
-    // x = q0 is an integer.  (q1 - q0) / 64 + 2^-20 needs 22 significant bits, so nd64 is exact.
+    // 1/64.  With wq = 64 + w, fma(wq, nd64, nk) evaluates -(x + wq 2^-20) - kMagic exactly and rounds it once, at
+    // kMagic's scale, to an integer (round-to-nearest-even).  The wq 2^-20 <= 2^-13 term only matters when x is exactly
+    // half way (it is then the tie-break towards x + 1/2, which is what the floor does); any other x is at least 1/64
+    // away from a half.  (q1 - q0) / 64 + 2^-20 needs 22 significant bits, so nd64 is exact.
+    //
+    // The weight never passes through the fp32 pipe: kMagic + index holds the index in its low mantissa bits, a byte
+    // permute looks 2 w up in a register table and one shift-add forms the bits of the float 64 + w (0x42800000 +
+    // (w << 17); 64 + 64 carries into the exponent as it should).  Both are ALU-pipe instructions; the packed FADD2 /
+    // FFMA2 stream, which saturates the FMA pipe in this loop, loses the index -> weight FFMA2 and both unbiasing adds.
+    template<int IB>
+    CVTT_HD float bc7_weight_plus_64(float indexBiased)
+    {
+        // 2 * g_weights2 / g_weights3 (BC67.cpp:121-132) as bytes
+        const uint32_t lo = (IB == 2) ? 0x80562A00u : 0x36241200u, hi = (IB == 2) ? 0u : 0x806E5C4Au;
+        return as_float((prmt(lo, hi, as_uint(indexBiased)) << 16) + 0x42800000u);
+    }
+
     template<int NCH, int IB, bool FAST, bool REFINE, int STRIDE>
     CVTT_HD f2 bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const f2 *nom, const f2 *axis, const f2 *nd64,
-        f2 *tv, f2 &tt, f2 &ts)
+        const f2 *nk, f2 *tv, f2 &tt, f2 &ts)
     {
         const float maxV = (float)((1 << IB) - 1), wScale = 64.0f / (float)((1 << IB) - 1), rcpMaxIndex = 1.0f / (float)((1 << IB) - 1);
         f2 acc[NCH];
@@ -351,7 +365,7 @@ namespace cvttb200
             acc[ch] = f2_splat(0.0f);
         f2 slowErr = f2_splat(0.0f);
 
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < n; i++)
         {
             const F4 p = gv[i * STRIDE];
@@ -362,15 +376,25 @@ namespace cvttb200
 #pragma unroll
             for (int ch = 1; ch < NCH; ch++)
                 dist = f2_add(dist, f2_mul(f2_add(nom[ch], pv[ch]), axis[ch]));
-            f2 idxf = f2_rne(f2_clamp_for_round(dist, 0.0f, maxV));
+            const f2 idxb = f2_add(f2_clamp_for_round(dist, 0.0f, maxV), kMagic);      // kMagic + index
+            f2 idxf = f2_splat(0.0f);
+            if (REFINE || !FAST || IB == 4)
+                idxf = f2_sub(idxb, kMagic);
 
             // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43); df is the negated difference
-            const f2 wf = f2_sub(f2_fma(idxf, wScale, kMagic), kMagic);
+            f2 wq;
+            if (IB == 4)
+            {
+                const f2 wb = f2_fma(idxf, wScale, kMagic);                            // kMagic + weight
+                wq = f2_make(as_float((as_uint(wb.x) << 17) + 0x42800000u), as_float((as_uint(wb.y) << 17) + 0x42800000u));
+            }
+            else
+                wq = f2_make(bc7_weight_plus_64<IB>(idxb.x), bc7_weight_plus_64<IB>(idxb.y));
             f2 d2[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
-                const f2 df = f2_add(f2_fma(wf, nd64[ch], nom[ch]), pv[ch]);
+                const f2 df = f2_add(f2_fma(wq, nd64[ch], nk[ch]), pv[ch]);
                 if (FAST)
                     acc[ch] = f2_fma(df, df, acc[ch]);              // exact (< 2^24)
                 else
@@ -396,7 +420,7 @@ namespace cvttb200
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
                     {
-                        const f2 df = f2_add(f2_fma(awf, nd64[ch], nom[ch]), pv[ch]);
+                        const f2 df = f2_add(f2_fma(awf, nd64[ch], nom[ch]), pv[ch]);     // w instead of 64 + w: same rounding argument
                         const f2 sq = f2_mul(df, df);
                         altError = (ch == 0) ? f2_mul(sq, P.wSq[0]) : f2_add(altError, f2_mul(sq, P.wSq[ch]));
                     }
@@ -571,7 +595,7 @@ namespace cvttb200
 
             // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
             // the fourth channel contributes exactly +0 to every sum below and is left out.
-            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH];
+            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH], nk[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
@@ -591,6 +615,7 @@ namespace cvttb200
                 axis[ch] = f2_mul(f2_mul(dW[ch], P.w[ch]), mdl);
                 nom[ch] = f2_neg(q0b[ch]);
                 nd64[ch] = f2_fma(dq[ch], -0.015625f, f2_splat(-9.5367431640625e-07f));     // -(dq / 64 + 2^-20), exact
+                nk[ch] = f2_add(nom[ch], dq[ch]);                                           // -(kMagic + q0 - dq), exact
             }
 
             f2 tv[NCH], tt = f2_splat(0.0f), ts = f2_splat(0.0f);
@@ -600,9 +625,9 @@ namespace cvttb200
 
             f2 shapeError;
             if (lastRound)
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, nk, tv, tt, ts);
             else
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, nk, tv, tt, ts);
             if (NCH == 3)
                 shapeError = f2_add(shapeError, staticAlphaError);
 

@@ -12,8 +12,9 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL, check=True)
-cub = max((os.path.join(tmp, f) for f in os.listdir(tmp)), key=os.path.getsize)
-dis = subprocess.run(["nvdisasm", "-gi", "-c", cub], stdout=subprocess.PIPE, text=True).stdout.splitlines()
+dis = []
+for f in sorted(os.listdir(tmp)):          # one cubin per translation unit
+    dis += subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], stdout=subprocess.PIPE, text=True).stdout.splitlines()
 
 # line table of the kernel: offset -> inline chain [(file, line) innermost first]; a chain persists until the next one
 table, chain, fresh, inside = {}, [("?", 0)], True, False
