@@ -333,32 +333,35 @@ namespace cvttb200
     // ---------------------------------------------------------------------------------------------------------
     // One pair of trials of the inner search (one per fp32 lane): index selection, reconstruction error and
     // (REFINE) the refiner's sums over the n gathered pixels (BC67.cpp:1355-1392).
-    //   nom = -(q0 + kMagic), nd64 = -((q1 - q0) / 64 + 2^-20), nk = -(kMagic + q0 - (q1 - q0)): negated so that the
-    //   loop only adds.
+    //   nom = -(q0 + kMagic), nd64 = -((q1 - q0) / 64 + 2^-20): negated so that the loop only adds.
     //
     // Reconstruction in one rounding.  ReconstructLDR_BC7 is floor(x + 1/2) with x = q0 + w (q1 - q0) / 64, a multiple of
-    // 1/64.  With wq = 64 + w, fma(wq, nd64, nk) evaluates -(x + wq 2^-20) - kMagic exactly and rounds it once, at
-    // kMagic's scale, to an integer (round-to-nearest-even).  The wq 2^-20 <= 2^-13 term only matters when x is exactly
-    // half way (it is then the tie-break towards x + 1/2, which is what the floor does); any other x is at least 1/64
-    // away from a half.  (q1 - q0) / 64 + 2^-20 needs 22 significant bits, so nd64 is exact.
+    // 1/64.  fma(w, nd64, nom) evaluates -(x + w 2^-20) - kMagic exactly and rounds it once, at kMagic's scale, to an
+    // integer (round-to-nearest-even).  The w 2^-20 <= 2^-14 term only matters when x is exactly half way (it is then the
+    // tie-break towards x + 1/2, which is what the floor does); any other x is at least 1/64 away from a half.  For w = 0,
+    // x = q0 is an integer.  (q1 - q0) / 64 + 2^-20 needs 22 significant bits, so nd64 is exact.
     //
-    // The weight never passes through the fp32 pipe: kMagic + index holds the index in its low mantissa bits, a byte
-    // permute looks 2 w up in a register table and one shift-add forms the bits of the float 64 + w (0x42800000 +
-    // (w << 17); 64 + 64 carries into the exponent as it should).  Both are ALU-pipe instructions; the packed FADD2 /
-    // FFMA2 stream, which saturates the FMA pipe in this loop, loses the index -> weight FFMA2 and both unbiasing adds.
-    template<int IB>
-    CVTT_HD float bc7_weight_plus_64(float indexBiased)
-    {
-        // 2 * g_weights2 / g_weights3 (BC67.cpp:121-132) as bytes
-        const uint32_t lo = (IB == 2) ? 0x80562A00u : 0x36241200u, hi = (IB == 2) ? 0u : 0x806E5C4Au;
-        return as_float((prmt(lo, hi, as_uint(indexBiased)) << 16) + 0x42800000u);
-    }
+    // Index -> weight in one rounding from the *biased* index.  g_weights2/3/4 (BC67.cpp:121-132) are rne(i * 64 / maxIndex);
+    // any multiplier close enough to 64 / maxIndex gives the same integers, and a short dyadic one, s = 683/32, 585/64,
+    // 273/64, makes kMagic * s and kMagic - kMagic * s exactly representable, so fma(kMagic + i, s, kMagic - kMagic * s)
+    // = rne(i * s) + kMagic with no intermediate rounding (no product i * s lands on a half: checked for every index).
+    // The unbiased index is then only needed by the refiner.
+    //
+    // Instruction forms (tools/ubench/pipe_rates.cu, cycles per warp instruction per scheduler at this kernel's occupancy):
+    // FADD2 reg + scalar register 2.1, FADD2 reg + reg 2.25, FFMA2 2.6-2.8, FADD2 with an *immediate* 3.4, FMNMX free next
+    // to packed ops, LOP3 / PRMT +2.4.  Hence kMagic is passed in a register (m) and the weight stays on the fp32 pipe.
+    template<int IB> struct BC7WeightScale;
+    template<> struct BC7WeightScale<2> { static constexpr float s = 21.34375f; };
+    template<> struct BC7WeightScale<3> { static constexpr float s = 9.140625f; };
+    template<> struct BC7WeightScale<4> { static constexpr float s = 4.265625f; };
 
     template<int NCH, int IB, bool FAST, bool REFINE, int STRIDE>
     CVTT_HD f2 bc7_trial_pixels(const BC7Params &P, const F4 *gv, const F4 *gw, int n, const f2 *nom, const f2 *axis, const f2 *nd64,
-        const f2 *nk, f2 *tv, f2 &tt, f2 &ts)
+        f2 *tv, f2 &tt, f2 &ts)
     {
         const float maxV = (float)((1 << IB) - 1), wScale = 64.0f / (float)((1 << IB) - 1), rcpMaxIndex = 1.0f / (float)((1 << IB) - 1);
+        const float ws = BC7WeightScale<IB>::s, wsBias = kMagic - kMagic * ws;           // both exact
+        const float m = magic_in_register();
         f2 acc[NCH];
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
@@ -376,25 +379,18 @@ namespace cvttb200
 #pragma unroll
             for (int ch = 1; ch < NCH; ch++)
                 dist = f2_add(dist, f2_mul(f2_add(nom[ch], pv[ch]), axis[ch]));
-            const f2 idxb = f2_add(f2_clamp_for_round(dist, 0.0f, maxV), kMagic);      // kMagic + index
+            const f2 idxb = f2_add(f2_clamp_for_round(dist, 0.0f, maxV), m);           // kMagic + index
             f2 idxf = f2_splat(0.0f);
-            if (REFINE || !FAST || IB == 4)
-                idxf = f2_sub(idxb, kMagic);
+            if (REFINE || !FAST)
+                idxf = f2_sub(idxb, m);
 
             // ReconstructLDR_BC7 (IndexSelector.h:90-100) + ComputeErrorLDR (BCCommon.h:24-43); df is the negated difference
-            f2 wq;
-            if (IB == 4)
-            {
-                const f2 wb = f2_fma(idxf, wScale, kMagic);                            // kMagic + weight
-                wq = f2_make(as_float((as_uint(wb.x) << 17) + 0x42800000u), as_float((as_uint(wb.y) << 17) + 0x42800000u));
-            }
-            else
-                wq = f2_make(bc7_weight_plus_64<IB>(idxb.x), bc7_weight_plus_64<IB>(idxb.y));
+            const f2 wf = f2_sub(f2_fma(idxb, ws, wsBias), m);
             f2 d2[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
-                const f2 df = f2_add(f2_fma(wq, nd64[ch], nk[ch]), pv[ch]);
+                const f2 df = f2_add(f2_fma(wf, nd64[ch], nom[ch]), pv[ch]);
                 if (FAST)
                     acc[ch] = f2_fma(df, df, acc[ch]);              // exact (< 2^24)
                 else
@@ -420,7 +416,7 @@ namespace cvttb200
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++)
                     {
-                        const f2 df = f2_add(f2_fma(awf, nd64[ch], nom[ch]), pv[ch]);     // w instead of 64 + w: same rounding argument
+                        const f2 df = f2_add(f2_fma(awf, nd64[ch], nom[ch]), pv[ch]);
                         const f2 sq = f2_mul(df, df);
                         altError = (ch == 0) ? f2_mul(sq, P.wSq[0]) : f2_add(altError, f2_mul(sq, P.wSq[ch]));
                     }
@@ -595,7 +591,7 @@ namespace cvttb200
 
             // IndexSelector<4>::Init (IndexSelector.h:27-78).  For NCH == 3 the alpha endpoints are both 255, so
             // the fourth channel contributes exactly +0 to every sum below and is left out.
-            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH], nk[NCH];
+            f2 dq[NCH], dW[NCH], axis[NCH], nom[NCH], nd64[NCH];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
@@ -615,7 +611,6 @@ namespace cvttb200
                 axis[ch] = f2_mul(f2_mul(dW[ch], P.w[ch]), mdl);
                 nom[ch] = f2_neg(q0b[ch]);
                 nd64[ch] = f2_fma(dq[ch], -0.015625f, f2_splat(-9.5367431640625e-07f));     // -(dq / 64 + 2^-20), exact
-                nk[ch] = f2_add(nom[ch], dq[ch]);                                           // -(kMagic + q0 - dq), exact
             }
 
             f2 tv[NCH], tt = f2_splat(0.0f), ts = f2_splat(0.0f);
@@ -625,9 +620,9 @@ namespace cvttb200
 
             f2 shapeError;
             if (lastRound)
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, nk, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, false, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
             else
-                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, nk, tv, tt, ts);
+                shapeError = bc7_trial_pixels<NCH, M::IB, FAST, true, STRIDE>(P, gv, gw, n, nom, axis, nd64, tv, tt, ts);
             if (NCH == 3)
                 shapeError = f2_add(shapeError, staticAlphaError);
 
