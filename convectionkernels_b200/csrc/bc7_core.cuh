@@ -302,18 +302,19 @@ namespace cvttb200
     {
         typedef BC7ModeT<MODE> M;
         const float qMul = M::WITHP ? (float)((1 << (M::BITS + 1)) - 1) / 512.0f : (float)((1 << M::BITS) - 1) / 256.0f;
-        const f2 vb = f2_add(f2_fma(c, qMul, qAddP), kMagic);
+        const float m = magic_in_register();          // register operand, see bc7_trial_pixels
+        const f2 vb = f2_add(f2_fma(c, qMul, qAddP), m);
         if (M::UNQ)
         {
             const int s = M::UNQ ? 2 * M::UNQ - 8 : 0;
             const float uMul = (float)(1 << (8 - M::UNQ)), uScale = 1.0f / (float)(1 << s), uOff = -(float)((1 << s) - 1) / (float)(1 << (s + 1));
-            const f2 v = f2_sub(vb, kMagic);
+            const f2 v = f2_sub(vb, m);
             const f2 v2 = M::WITHP ? f2_fma(v, 2.0f, p) : v;
-            const f2 flb = f2_add(f2_fma(v2, uScale, uOff), kMagic);
+            const f2 flb = f2_add(f2_fma(v2, uScale, uOff), m);
             return f2_fma(v2, uMul, flb);
         }
         else if (M::WITHP)
-            return f2_fma(f2_sub(vb, kMagic), 2.0f, pM);
+            return f2_fma(f2_sub(vb, m), 2.0f, pM);
         else
             return vb;
     }
@@ -565,7 +566,7 @@ namespace cvttb200
 
         const f2 qA0 = f2_make(bc7_quant_add<MODE>(p0x), bc7_quant_add<MODE>(p0y)), qA1 = f2_make(bc7_quant_add<MODE>(p1x), bc7_quant_add<MODE>(p1y));
         const f2 pf0 = f2_make((float)p0x, (float)p0y), pf1 = f2_make((float)p1x, (float)p1y);
-        const f2 pM0 = f2_add(pf0, kMagic), pM1 = f2_add(pf1, kMagic);
+        const f2 pM0 = f2_add(pf0, magic_in_register()), pM1 = f2_add(pf1, magic_in_register());
 
         f2 e0[NCH], e1[NCH];
 #pragma unroll
