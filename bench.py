@@ -153,6 +153,95 @@ def reference_arm(args):
     }))
 
 
+def sharded_texture(args):
+    """BASELINE.json configs[4]: EncodeBC7 quality 100 on ONE 8192x8192 RGBA8 texture (4 194 304 blocks) that lives on
+    rank 0; per step the 8-block-group ranges are scattered to the ranks over NCCL, encoded, and the encoded ranges gathered
+    on rank 0 (strong scaling: total work fixed).  Device-timed, max over ranks; prints one JSON line."""
+    import torch
+    import torch.distributed as dist
+    from convectionkernels_b200 import api, synth, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    api.init(local_rank)
+
+    side = 8192
+    n_blocks = (side // 4) * (side // 4)
+    d_all = None
+    if rank == 0:
+        img = np.concatenate([np.concatenate([synth.mixed_rgba8(SIDE, SIDE, seed=1234 + 2 * r + c) for c in range(2)], axis=1) for r in range(2)], axis=0)
+        d_all = torch.from_numpy(synth.image_to_blocks(img).reshape(-1)).to(dev)
+    opt, plan = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(plan, 100)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        if distributed:
+            local = sharding.scatter_blocks(d_all, n_blocks, IN_BYTES, src=0, device=dev)
+        else:
+            local = d_all
+        enc = api.encode("BC7", local.reshape(-1, IN_BYTES), opt, plan)
+        if distributed:
+            return sharding.gather_encoded(enc, n_blocks, OUT_BYTES, dst=0)
+        return enc
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        barrier()
+        e0.record()
+        out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    barrier()
+    launches = api.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([total], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    if rank == 0:
+        # size-independent check at full size: the sharded result equals a single-GPU encode of sampled group ranges
+        ok = True
+        full = out.reshape(n_blocks, OUT_BYTES)
+        for first in (0, n_blocks // 2 - 4096, n_blocks - 8192):
+            ref = api.encode("BC7", d_all.reshape(n_blocks, IN_BYTES)[first:first + 8192].contiguous(), opt, plan)
+            ok = ok and bool((ref == full[first:first + 8192]).all())
+        print(json.dumps({
+            "metric": METRIC, "value": n_blocks * args.steps / (total_ms / 1e3) / 1e6, "unit": "Mblocks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "EncodeBC7 plan=FromQuality(100) Options=default ONE 8192x8192 synthetic RGBA8 (4194304 blocks) on rank 0, 8-block-group ranges scattered / gathered over NCCL inside the step",
+                       "parallelism": "block-range shard x%d" % world, "l2": "256 MiB flush write between timed iterations"},
+            "clocks": sampler.summary(), "gpu_launches": int(launches), "sharded_equals_single_gpu_on_sampled_ranges": ok,
+        }))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,12 +249,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--format", default="BC7", choices=sorted(FORMAT_CONFIGS))
+    ap.add_argument("--workload", default="texture4096", choices=["texture4096", "shard8192"],
+                    help="texture4096: every rank encodes its own 4096x4096 texture (weak scaling, the default contract); "
+                         "shard8192: BASELINE.json configs[4], ONE 8192x8192 texture on rank 0, block ranges scattered to the ranks, "
+                         "encoded and gathered back inside the timed step (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     select_format(args.format)
 
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.workload == "shard8192":
+        sharded_texture(args)
         return
 
     import torch

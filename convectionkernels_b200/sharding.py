@@ -34,6 +34,9 @@ def scatter_blocks(blocks, n_blocks, block_bytes, src=0, device=None, group=None
         flat = blocks.reshape(-1)
         chunks = []
         for first, n in ranges:
+            if n * block_bytes == pad:          # equal ranges (the usual case): send views, no staging copy
+                chunks.append(flat[first * block_bytes:(first + n) * block_bytes])
+                continue
             c = torch.zeros(pad, dtype=torch.uint8, device=device)
             c[: n * block_bytes] = flat[first * block_bytes:(first + n) * block_bytes]
             chunks.append(c)
@@ -49,9 +52,12 @@ def gather_encoded(encoded, n_blocks, out_block_bytes, dst=0, group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     ranges = shard_ranges(n_blocks, world)
     pad = max(n for _, n in ranges) * out_block_bytes
-    send = torch.zeros(pad, dtype=torch.uint8, device=encoded.device)
     flat = encoded.reshape(-1)
-    send[: flat.numel()] = flat
+    if flat.numel() == pad:
+        send = flat
+    else:
+        send = torch.zeros(pad, dtype=torch.uint8, device=encoded.device)
+        send[: flat.numel()] = flat
     if rank == dst:
         parts = [torch.empty(pad, dtype=torch.uint8, device=encoded.device) for _ in range(world)]
         dist.gather(send, parts, dst=dst, group=group)
