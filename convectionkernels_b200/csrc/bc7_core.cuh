@@ -90,6 +90,7 @@ namespace cvttb200
         bool blockHasNonZeroAlpha, isPunchThrough;   // this block: max alpha > 0; every alpha is 0 or 255 (BC67.cpp:1056-1067)
         // warp-level "does any lane need this path" (pure work skipping, never changes a lane's result)
         bool warpAnyRGB, warpAnyPCA4, warpAnyExpand, warpAnyMode7;
+        bool warpHasWork;           // false for a warp that holds no block at all
     };
 
     struct BC7Work   // BC67::WorkInfo, BC67.cpp:59-76, in packed form
@@ -1464,6 +1465,12 @@ namespace cvttb200
                 cta_sync();
             if (op == kCmdEnd)
                 break;
+            if (!lf.warpHasWork)
+            {
+                // a warp without blocks (the dealt-out tail of a CTA) only walks the stream for the barriers
+                pc += (op == kCmdShape) ? 2 + (int)((w0 >> 8) & 0xff) : (op == kCmdEval ? 2 : 1);
+                continue;
+            }
 
             if (op == kCmdShape)
             {

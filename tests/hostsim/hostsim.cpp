@@ -92,6 +92,7 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
             lf[l].warpAnyRGB = warpFlagsAllTrue ? true : wRGB;
             lf[l].warpAnyPCA4 = warpFlagsAllTrue ? true : wPCA4;
             lf[l].warpAnyExpand = true;
+            lf[l].warpHasWork = true;
             lf[l].warpAnyMode7 = warpFlagsAllTrue ? true : wM7;
         }
         if (options->flags & kFlag_BC7_RespectPunchThrough)
