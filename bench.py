@@ -35,12 +35,12 @@ CPU_SAMPLE_BLOCKS = 262144               # first 1024 rows of the texture
 # (configs[2] BC6HU, configs[3] ETC2_RGBA) or any other implemented format; the JSON contract is the same.
 # name -> (workload text, metric, input kind, bytes read per block, bytes written per block, dominant kernel)
 FORMAT_CONFIGS = {
-    "BC7": ("EncodeBC7 plan=FromQuality(100) Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) BC7 q100", "rgba8", 64, 16, "bc7_encode_kernel<true>"),
+    "BC7": ("EncodeBC7 plan=FromQuality(100) Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) BC7 q100", "rgba8", 64, 16, "bc7_encode_kernel<true,false>"),
     "BC6HU": ("EncodeBC6HU Options=default (slow indexing) 4096x4096 synthetic F16 HDR ramp (1048576 blocks) per GPU", "Mblocks/s (4x4) BC6HU", "f16", 128, 16, "bc6h_encode_kernel<false,false>"),
     "BC6HS": ("EncodeBC6HS Options=default 4096x4096 synthetic signed F16 HDR ramp per GPU", "Mblocks/s (4x4) BC6HS", "f16s", 128, 16, "bc6h_encode_kernel<true,false>"),
-    "ETC2_RGBA": ("EncodeETC2RGBA Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) ETC2 RGBA", "rgba8", 64, 16, "etc_encode_kernel<2,false>"),
-    "ETC2": ("EncodeETC2 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC2 RGB", "rgba8", 64, 8, "etc_encode_kernel<1,false>"),
-    "ETC1": ("EncodeETC1 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC1", "rgba8", 64, 8, "etc_encode_kernel<0,false>"),
+    "ETC2_RGBA": ("EncodeETC2RGBA Options=default 4096x4096 synthetic RGBA8 (1048576 blocks) per GPU", "Mblocks/s (4x4) ETC2 RGBA", "rgba8", 64, 16, "etc_encode_kernel<2,false,false>"),
+    "ETC2": ("EncodeETC2 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC2 RGB", "rgba8", 64, 8, "etc_encode_kernel<1,false,false>"),
+    "ETC1": ("EncodeETC1 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) ETC1", "rgba8", 64, 8, "etc_encode_kernel<0,false,false>"),
     "ETC2_ALPHA": ("EncodeETC2Alpha 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) EAC alpha", "rgba8", 64, 8, "eac_encode_kernel<0>"),
     "BC1": ("EncodeBC1 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC1", "rgba8", 64, 8, "s3tc_encode_kernel<BC1>"),
     "BC2": ("EncodeBC2 Options=default 4096x4096 synthetic RGBA8 per GPU", "Mblocks/s (4x4) BC2", "rgba8", 64, 16, "s3tc_encode_kernel<BC2>"),
@@ -368,6 +368,13 @@ def main():
                     "kernel": KERNEL_NAME, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_BLOCK * BLOCKS,
                     "note": "compute-bound path (millions of instructions per block against <= 144 bytes); the binding unit is the FP32 pipe / issue slots, see fma_pipe_frac_ncu, issue_slot_frac_ncu and DESIGN.md",
                     "issue_slot_frac_ncu": prof.get("issue_slot_frac"), "fma_pipe_frac_ncu": prof.get("fma_pipe_frac")}
+        # the same issue-slot fraction from THIS run's kernel time: instructions per block (committed ncu capture) x blocks
+        # / 32 lanes, over the 4 schedulers x SMs x the SM clock sampled during the timed region
+        ipb, clk = prof.get("warp_instructions_per_block"), sampler.summary().get("sm_mhz")
+        if ipb and clk:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            roofline["issue_slot_frac_live"] = ipb * BLOCKS / 32.0 / (kernel_ms / 1e3 * sms * 4 * clk * 1e6)
+            roofline["instructions_per_block_ncu"] = ipb
 
         # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same texture
         cpu = None
