@@ -109,6 +109,7 @@ def _lib():
         L.cvttb200_output_block_bytes.restype = ctypes.c_size_t
         L.cvttb200_encode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.cvttb200_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        L.cvttb200_encode_multi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.cvttb200_set_rcp_table.argtypes = [ctypes.c_void_p]
         L.cvttb200_get_rcp_table.argtypes = [ctypes.c_void_p]
         _LIB = L
@@ -214,6 +215,39 @@ def encode(fmt, pBlocks, options, encodingPlan=None, out=None):
     if n * inb != nbytes:
         raise ValueError("input size is not a whole number of blocks")
     _check(st)
+    return out
+
+
+def encode_multi(fmt, pBlocks, options, encodingPlan=None, devices=None, out=None):
+    """cvttb200_encode_multi: encodes host blocks (numpy, n % 8 == 0) on several GPUs of this process, sharded by whole
+    8-block groups; `devices` is a list of device indices (None = every visible device).  Returns a (n, outBytes) uint8 array
+    byte-identical to encode() on one device."""
+    L = _lib()
+    f = FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
+    inb, outb = L.cvttb200_input_block_bytes(f), L.cvttb200_output_block_bytes(f)
+    keep = []
+
+    def struct_arg(obj, ctype):
+        r = _as_struct_ptr(obj, ctype)
+        if isinstance(r, tuple):
+            keep.append(r[1])
+            return r[0]
+        return r
+
+    src = np.ascontiguousarray(pBlocks)
+    nbytes = src.size * src.itemsize
+    n = nbytes // inb
+    if n * inb != nbytes:
+        raise ValueError("input size is not a whole number of blocks")
+    if out is None:
+        out = np.empty((n, outb), dtype=np.uint8)
+    if devices is None:
+        dev_arr, n_dev = None, 0
+    else:
+        dev_arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        n_dev = len(devices)
+    _check(L.cvttb200_encode_multi(f, src.ctypes.data, n, out.ctypes.data, struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan),
+                                   ctypes.cast(dev_arr, ctypes.c_void_p) if dev_arr is not None else None, n_dev))
     return out
 
 

@@ -7,6 +7,7 @@
 #include <xmmintrin.h>
 
 #include <algorithm>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -182,7 +183,7 @@ namespace
 {    thread_local std::string t_lastError;
 
     std::mutex g_mutex;
-    std::vector<DeviceContext> g_contexts;
+    std::deque<DeviceContext> g_contexts;             // references stay valid while contexts are added
     float g_rcpN[17];
     bool g_rcpOverridden = false, g_rcpReady = false;
 }
@@ -324,6 +325,27 @@ namespace
     }
 }
 
+namespace
+{
+    // format -> kernel launch; caller holds g_mutex and has made ctx.device current
+    int dispatch_encode(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const cvttb200_options *options, const cvttb200_bc7_plan *plan, cudaStream_t stream)
+    {
+        OptionsPOD opt;
+        memcpy(&opt, options, sizeof(opt));
+        if (format == CVTTB200_BC7)
+        {
+            BC7PlanPOD planPOD;
+            memcpy(&planPOD, plan, sizeof(planPOD));
+            return launch_bc7(ctx, dIn, nBlocks, dOut, opt, planPOD, g_rcpN, stream);
+        }
+        if (format <= CVTTB200_BC5S)
+            return launch_s3tc(format, dIn, nBlocks, dOut, opt, g_rcpN, stream);
+        if (format == CVTTB200_BC6HU || format == CVTTB200_BC6HS)
+            return launch_bc6h(dIn, nBlocks, dOut, opt, format == CVTTB200_BC6HS, g_rcpN, stream);
+        return launch_etc(ctx, format, dIn, nBlocks, dOut, opt, stream);
+    }
+}
+
 // =========================================================================================================
 // C ABI
 
@@ -356,6 +378,7 @@ void cvttb200_shutdown(void)
             cudaFree(c.plans[k].dCmds);
         if (c.stageIn) cudaFree(c.stageIn);
         if (c.stageOut) cudaFree(c.stageOut);
+        if (c.multiStream) cudaStreamDestroy(c.multiStream);
     }
     g_contexts.clear();
     cudaSetDevice(prev);
@@ -570,20 +593,7 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
         dOut = ctx->stageOut;
     }
 
-    OptionsPOD opt;
-    memcpy(&opt, options, sizeof(opt));
-    if (format == CVTTB200_BC7)
-    {
-        BC7PlanPOD planPOD;
-        memcpy(&planPOD, plan, sizeof(planPOD));
-        rc = launch_bc7(*ctx, dIn, nBlocks, dOut, opt, planPOD, g_rcpN, stream);
-    }
-    else if (format <= CVTTB200_BC5S)
-        rc = launch_s3tc(format, dIn, nBlocks, dOut, opt, g_rcpN, stream);
-    else if (format == CVTTB200_BC6HU || format == CVTTB200_BC6HS)
-        rc = launch_bc6h(dIn, nBlocks, dOut, opt, format == CVTTB200_BC6HS, g_rcpN, stream);
-    else
-        rc = launch_etc(*ctx, format, dIn, nBlocks, dOut, opt, stream);
+    rc = dispatch_encode(*ctx, format, dIn, nBlocks, dOut, options, plan, stream);
     if (rc != CVTTB200_OK)
         return rc;
 
@@ -592,6 +602,99 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
     if (!inOnDevice || !outOnDevice)
         CVTT_CUDA(cudaStreamSynchronize(stream));
     return CVTTB200_OK;
+}
+
+int cvttb200_encode_multi(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan,
+                          const int *devices, int nDevices)
+{
+    if (!blocks || !out || !options)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
+    if (nBlocks % 8 != 0)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "nBlocks must be a multiple of 8 (cvtt::NumParallelBlocks)");
+    const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
+    if (!inBytes)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
+    if (format == CVTTB200_BC7 && !plan)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
+    if (is_device_pointer(blocks) || is_device_pointer(out))
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_encode_multi takes host buffers (use cvttb200_encode per device for device memory)");
+
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int count = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return fail(CVTTB200_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + " (libcvtt_b200 has no CPU fallback)");
+    }
+    if (nDevices <= 0)
+        nDevices = count;
+    std::vector<int> ids((size_t)nDevices);
+    for (int i = 0; i < nDevices; i++)
+    {
+        ids[(size_t)i] = devices ? devices[i] : i;
+        if (ids[(size_t)i] < 0 || ids[(size_t)i] >= count)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "device index out of range");
+        for (int k = 0; k < i; k++)
+            if (ids[(size_t)k] == ids[(size_t)i])
+                return fail(CVTTB200_ERR_BAD_ARGUMENT, "a device is listed twice");
+    }
+    if (nBlocks == 0)
+        return CVTTB200_OK;
+
+    int prev = 0;
+    CVTT_CUDA(cudaGetDevice(&prev));
+
+    // Contiguous ranges of whole 8-block groups (a group is one reference call and is never split); every device copies its
+    // range in, encodes it and copies the result back on its own stream, then all streams are joined.
+    const size_t nGroups = nBlocks / 8;
+    std::vector<DeviceContext *> used;
+    int rc = CVTTB200_OK;
+    for (int i = 0; i < nDevices && rc == CVTTB200_OK; i++)
+    {
+        const size_t first = nGroups * (size_t)i / (size_t)nDevices * 8, end = nGroups * (size_t)(i + 1) / (size_t)nDevices * 8, n = end - first;
+        if (n == 0)
+            continue;
+        cudaError_t e = cudaSetDevice(ids[(size_t)i]);
+        if (e != cudaSuccess)
+        {
+            rc = fail_cuda(e, "cudaSetDevice");
+            break;
+        }
+        DeviceContext *ctx = nullptr;
+        rc = get_context(ids[(size_t)i], &ctx);
+        if (rc != CVTTB200_OK)
+            break;
+        if (!ctx->multiStream && (e = cudaStreamCreateWithFlags(&ctx->multiStream, cudaStreamNonBlocking)) != cudaSuccess)
+        {
+            rc = fail_cuda(e, "cudaStreamCreateWithFlags");
+            break;
+        }
+        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, n * inBytes);
+        if (rc == CVTTB200_OK)
+            rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, n * outBytes);
+        if (rc != CVTTB200_OK)
+            break;
+        used.push_back(ctx);
+        if ((e = cudaMemcpyAsync(ctx->stageIn, (const unsigned char *)blocks + first * inBytes, n * inBytes, cudaMemcpyHostToDevice, ctx->multiStream)) != cudaSuccess)
+        {
+            rc = fail_cuda(e, "cudaMemcpyAsync (host to device)");
+            break;
+        }
+        rc = dispatch_encode(*ctx, format, ctx->stageIn, n, ctx->stageOut, options, plan, ctx->multiStream);
+        if (rc != CVTTB200_OK)
+            break;
+        if ((e = cudaMemcpyAsync((unsigned char *)out + first * outBytes, ctx->stageOut, n * outBytes, cudaMemcpyDeviceToHost, ctx->multiStream)) != cudaSuccess)
+            rc = fail_cuda(e, "cudaMemcpyAsync (device to host)");
+    }
+    for (size_t k = 0; k < used.size(); k++)
+    {
+        cudaSetDevice(used[k]->device);
+        const cudaError_t e = cudaStreamSynchronize(used[k]->multiStream);
+        if (e != cudaSuccess && rc == CVTTB200_OK)
+            rc = fail_cuda(e, "cudaStreamSynchronize");
+    }
+    cudaSetDevice(prev);
+    return rc;
 }
 
 int cvttb200_decode(int format, const void *encoded, size_t nBlocks, void *pixelBlocks, void *streamPtr)

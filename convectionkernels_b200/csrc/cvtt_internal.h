@@ -37,6 +37,7 @@ namespace cvttb200
         std::vector<PlanCacheEntry> plans;
         void *stageIn = nullptr, *stageOut = nullptr;
         size_t stageInBytes = 0, stageOutBytes = 0;
+        cudaStream_t multiStream = nullptr;           // this device's stream of cvttb200_encode_multi
     };
 
     // Per-TU device set-up (constant tables, kernel attributes) for the current device, and the launches.  All return a

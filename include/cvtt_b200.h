@@ -181,6 +181,16 @@ int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t bl
 int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out,
                     const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *stream);
 
+/* The same call over several GPUs of this process (the reference itself is single threaded and leaves
+ * parallelism to its caller, README.md:57).  `blocks` and `out` are HOST buffers.  The blocks are split into nDevices contiguous
+ * ranges of whole 8-block groups -- a group is one reference call (cvtt::NumParallelBlocks, ConvectionKernels.h:71) and is never
+ * split, because the reference decides some things jointly for its 8 blocks -- and every device copies its range in, encodes it
+ * and copies the result back on a stream of its own; the call returns when `out` is complete.  The result is byte-identical to
+ * cvttb200_encode on one device.  devices == NULL means devices 0 .. nDevices - 1; nDevices <= 0 means every visible device.
+ * The current device of the calling thread is preserved.  Returns a cvttb200_status. */
+int cvttb200_encode_multi(int format, const void *blocks, size_t nBlocks, void *out,
+                          const cvttb200_options *options, const cvttb200_bc7_plan *plan, const int *devices, int nDevices);
+
 /* ---- decoders ---------------------------------------------------------------------------------------------
  * cvtt::Kernels::DecodeBC7 / DecodeBC6HU / DecodeBC6HS (ConvectionKernels.h:273-275, ConvectionKernels_API.cpp:288-322 ->
  * BC7Computer::UnpackOne BC67.cpp:2206-2423, BC6HComputer::UnpackOne :3059-3289).  format: CVTTB200_BC7 (-> PixelBlockU8, 64 B
