@@ -20,6 +20,10 @@ __global__ void k(float *out, unsigned long long *cycles, float a0, float b0)
     asm volatile("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b0 * 0.25f));
     asm volatile("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(b0 + 1.0f), "f"(a0 + 2.0f));
     float s[CHAINS];
+    double dd[CHAINS];
+    const double da = (double)a0 * 1.0000001, db = (double)b0 * 0.3;
+    for (int i = 0; i < CHAINS; i++)
+        dd[i] = (double)threadIdx.x + i;
     for (int i = 0; i < CHAINS; i++)
     {
         asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r[i]) : "f"(a0 + i + threadIdx.x), "f"(b0 - i - threadIdx.x));
@@ -128,6 +132,27 @@ __global__ void k(float *out, unsigned long long *cycles, float a0, float b0)
                 asm volatile("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(s[i]));
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(bb), "l"(b));
             }
+            else if (KIND == 24) // DFMA alone
+            {
+                double &d = reinterpret_cast<double &>(r[i]);
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d) : "d"(da), "d"(db));
+            }
+            else if (KIND == 25) // FFMA2 + DFMA
+            {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(a), "l"(b));
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(da), "d"(db));
+            }
+            else if (KIND == 26) // 2 FFMA2 + DFMA
+            {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(a), "l"(b));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c) : "l"(a), "l"(r[(i + 3) % CHAINS]));
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(da), "d"(db));
+            }
+            else if (KIND == 27) // F2F f32 -> f64
+            {
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(dd[i]) : "f"(s[i]));
+                s[i] += 1.0f;
+            }
             else if (KIND == 10) // 2 FFMA2 + 1 scalar FFMA
             {
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[i]) : "l"(a), "l"(b));
@@ -141,7 +166,7 @@ __global__ void k(float *out, unsigned long long *cycles, float a0, float b0)
     {
         float x, y;
         asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(r[i]));
-        acc += x + y + s[i];
+        acc += x + y + s[i] + (float)dd[i];
     }
     float x, y;
     asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(c));
@@ -186,6 +211,10 @@ int main()
         run<9>("FFMA2 + LOP3 (per instruction)", 2, threads);
         run<7>("FFMA2 + FADD2 (per instruction)", 2, threads);
         run<10>("FFMA2 + FFMA scalar (per instruction)", 2, threads);
+        run<24>("DFMA", 1, threads);
+        run<25>("FFMA2 + DFMA (per instruction)", 2, threads);
+        run<26>("2 FFMA2 + DFMA (per instruction)", 3, threads);
+        run<27>("F2F.F64.F32 (+ FADD)", 2, threads);
         run<21>("FADD2 reg, c[magic] scalar", 1, threads);
         run<22>("FADD2 reg, reg pair (hoisted constant)", 1, threads);
         run<23>("FFMA2 reg, scalar.F32, reg", 1, threads);
