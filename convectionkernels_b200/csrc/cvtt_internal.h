@@ -38,6 +38,7 @@ namespace cvttb200
         void *stageIn = nullptr, *stageOut = nullptr;
         size_t stageInBytes = 0, stageOutBytes = 0;
         cudaStream_t multiStream = nullptr;           // this device's stream of cvttb200_encode_multi
+        cudaStream_t pipeStream[2] = { nullptr, nullptr };   // host-buffer calls of the fast formats: chunks alternate between two streams
     };
 
     // Per-TU device set-up (constant tables, kernel attributes) for the current device, and the launches.  All return a

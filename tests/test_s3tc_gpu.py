@@ -66,3 +66,17 @@ def test_exhaustive_against_reference(reference, fmt):
         want = reference.encode(fmt, blocks, _opt_bytes(o), threads=0)
         got = api.encode(fmt, blocks, o)
         assert (got == want).all(), first_mismatch(want, got)
+
+
+@pytest.mark.parametrize("fmt", ["BC1", "BC3", "BC5S"])
+def test_host_buffers_take_the_chunked_pipeline(fmt):
+    """Host-buffer calls of the fast formats are cut into 131072-block chunks on two streams (cvtt_b200.cu); the result must not
+    depend on it: two whole chunks plus a ragged tail of 37 groups against the one-launch device-pointer path."""
+    import torch
+    n = 131072 * 2 + 8 * 37
+    blocks = synth.random_blocks_rgba8(n, seed=91)
+    want = api.encode(fmt, torch.from_numpy(blocks).cuda(), api.Options()).cpu().numpy()
+    got = api.encode(fmt, blocks, api.Options())
+    assert (got == want).all(), first_mismatch(want, got)
+    again = api.encode(fmt, blocks[: 131072 * 2 - 8], api.Options())          # below the threshold: single launch
+    assert (again == want[: 131072 * 2 - 8]).all()
