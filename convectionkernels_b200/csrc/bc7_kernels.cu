@@ -279,8 +279,10 @@ namespace cvttb200
         bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
         g_launches++;
 
-        // at most three partially filled warps (one per class).  (Dealing the warps out over whole waves -- 11 or 12 warps per
-        // CTA instead of a partial last wave -- was measured slower: 7.57 against 7.80 Mblocks/s.)
+        // at most three partially filled warps (one per class).  Two ways of avoiding the partial last wave were measured and
+        // dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
+        // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
+        // 1 048 576 blocks, 3 % slower at 524 288).
         const unsigned warps = nGroups / 4 + 3;
         const unsigned grid = (warps + kBC7Threads / 32 - 1) / (kBC7Threads / 32);
         const bool fast = (options.flags & kFlag_BC7_FastIndexing) != 0, punch = (options.flags & kFlag_BC7_RespectPunchThrough) != 0;
