@@ -379,6 +379,8 @@ def main():
         # CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same texture
         cpu = None
         try:
+            if world > 1:
+                raise RuntimeError("measured at N=1 only (the other ranks share the host cores)")
             from oracle.loader import Reference
             R = Reference()
             threads = R.hardware_threads()
