@@ -562,6 +562,7 @@ namespace cvttb200
             lineTotal[ch] -= isolatedTotal[ch];
         const int numLine = 16 - numIsolated;
         const int lineDivisorV = numLine * 34, lineAddendV = (numLine << 4) | numLine;
+        const UDivisor lineDivide = udiv_prepare((uint32_t)lineDivisorV);     // up to 33 x 3 x 8 divisions by it below
 
         int isolatedQ[3], isolatedColor[3];
         {
@@ -588,7 +589,7 @@ namespace cvttb200
             for (int ch = 0; ch < 3; ch++)
             {
                 const int numerator = imax(0, wrap_s16(lineTotal[ch] + lineTotal[ch] + (BT709 ? 0 : lineAddendV) + offs * modifierOffset));
-                const int divided = (lineDivisorV == 0) ? 0 : (numerator / lineDivisorV);
+                const int divided = (lineDivisorV == 0) ? 0 : (int)udiv((uint32_t)numerator, lineDivide);
                 q[ch] = imin(15, divided);
                 targets[ch] = numerator;
             }
@@ -732,6 +733,7 @@ namespace cvttb200
             for (int sector = 0; sector < 2; sector++)
             {
                 const int count = counts[sector];
+                const UDivisor countDivide = udiv_prepare((uint32_t)(count * 34));
                 int lastColor = -1;
                 for (int offs = -count; offs <= count; offs++)
                 {
@@ -740,7 +742,7 @@ namespace cvttb200
                     {
                         int q = 0;
                         if (count != 0)
-                            q = imin(15, imax(0, wrap_s16(totals[sector][ch] * 2 + count * 17 + modifierOffset * offs)) / (count * 34));
+                            q = imin(15, (int)udiv((uint32_t)imax(0, wrap_s16(totals[sector][ch] * 2 + count * 17 + modifierOffset * offs)), countDivide));
                         packed |= q << ((2 - ch) * 5);
                     }
                     if (numUnique[sector] != 0 && packed == lastColor)
@@ -1669,13 +1671,14 @@ namespace cvttb200
 
                     uint32_t indexes[2] = { 0, 0 };
                     int totalError = 0;
+                    const UDivisor multiplierDivide = udiv_prepare((uint32_t)multiplier);
                     for (int px = 0; px < 16; px++)
                     {
                         // QuantizeETC2Alpha, ETC.cpp:2366-2411
                         const int offset = wrap_s16(pixels[px] - baseAlpha);
                         const int aboutReflectorTimes2 = wrap_s16(offset + offset + multiplier);
                         const int absTimes2 = (aboutReflectorTimes2 < 0 ? -aboutReflectorTimes2 : aboutReflectorTimes2) & 0xffff;
-                        int lookup = (absTimes2 >> 1) / multiplier;
+                        int lookup = (int)udiv((uint32_t)(absTimes2 >> 1), multiplierDivide);
                         if (lookup >= 13)
                             lookup = 12;
                         const int positiveIndex = T.alphaRounding[tableIndex][lookup];
