@@ -1184,6 +1184,7 @@ namespace cvttb200
             {
                 const int n = numT[sector];
                 const int denominator = imax(1, n) << 8, addend = n << 7, cumulativeMax = wrap_u16(255 * n);
+                const UDivisor denominatorDivide = udiv_prepare((uint32_t)denominator);
                 for (int table = 0; table < 8; table++)
                 {
                     cta_sync();
@@ -1197,7 +1198,7 @@ namespace cvttb200
                         {
                             const int cu = imin(cumulativeMax, imax(0, wrap_s16(cumulative[sector][ch] + offset)));
                             const int numerator = wrap_u16(wrap_u16((cu << 5) - cu) + wrap_u16((cu >> 3) + addend));
-                            packed |= (numerator / denominator) << (ch * 5);
+                            packed |= (int)udiv((uint32_t)numerator, denominatorDivide) << (ch * 5);
                         }
                         if (om != -n && packed == lastColor)
                             continue;
@@ -1302,6 +1303,7 @@ namespace cvttb200
         int bestTable = 0, bestLineColor = 0, bestHModeColor2 = 0;
 
         const int lineDivisor = numLine * 34, lineAddend = (numLine << 4) | numLine;
+        const UDivisor lineDivide = udiv_prepare((uint32_t)lineDivisor);
         const int clusterMaxLine = vote.max(numLine);
 
         for (int table = 0; table < 8; table++)
@@ -1317,7 +1319,7 @@ namespace cvttb200
                 for (int ch = 0; ch < 3; ch++)
                 {
                     const int numerator = imax(0, wrap_s16(wrap_s16(lineTotal[ch] + lineTotal[ch] + (BT709 ? 0 : lineAddend)) + wrap_s16(clamped * modifierOffset)));
-                    const int divided = (lineDivisor == 0) ? 0 : (numerator / lineDivisor);
+                    const int divided = (lineDivisor == 0) ? 0 : (int)udiv((uint32_t)numerator, lineDivide);
                     q[ch] = imin(15, divided);
                     targets[ch] = numerator;
                 }
