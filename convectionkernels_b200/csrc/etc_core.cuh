@@ -778,7 +778,14 @@ namespace cvttb200
             // colour pairs in the reference's stepping order (ETC.cpp:800-822); a lane only needs its own n0 * n1 steps
             const int n0 = numUnique[0], n1 = numUnique[1];
             const int combos = n0 * n1;
-            int index0 = 0, index1 = 0;
+            // The second colour only changes every n0 steps: its 16 per-pixel errors stay in registers in between, which halves
+            // the scratch loads of this loop (they were 10 % of the kernel's instructions and 12 % of its stall samples).
+            int index0 = 0, index1 = 0, loaded1 = -1;
+            float row1[16];
+            uint32_t m1 = 0;
+#pragma unroll
+            for (int px = 0; px < 16; px++)
+                row1[px] = 0.0f;
             for (int combo = 0; combo < combos; combo++)
             {
                 index0++;
@@ -787,13 +794,22 @@ namespace cvttb200
                     index0 = 0;
                 index1 = imin(n1 - 1, index1 + (overflow ? 1 : 0));
                 const int ci0 = index0, ci1 = index1 + n0;
-                const uint32_t m0 = S.hMeta[(size_t)ci0 * S.stride], m1 = S.hMeta[(size_t)ci1 * S.stride];
+                const uint32_t m0 = S.hMeta[(size_t)ci0 * S.stride];
+                if (ci1 != loaded1)
+                {
+                    loaded1 = ci1;
+                    m1 = S.hMeta[(size_t)ci1 * S.stride];
+#pragma unroll
+                    for (int px = 0; px < 16; px++)
+                        row1[px] = S.hErr[(size_t)(ci1 * 16 + px) * S.stride];
+                }
 
                 float totalError = 0.0f;
                 uint32_t sectorBits = 0;
+#pragma unroll
                 for (int px = 0; px < 16; px++)
                 {
-                    const float e0 = S.hErr[(size_t)(ci0 * 16 + px) * S.stride], e1 = S.hErr[(size_t)(ci1 * 16 + px) * S.stride];
+                    const float e0 = S.hErr[(size_t)(ci0 * 16 + px) * S.stride], e1 = row1[px];
                     totalError = fadd(totalError, sse_min(e0, e1));
                     if (e1 < e0)
                         sectorBits |= 1u << px;
