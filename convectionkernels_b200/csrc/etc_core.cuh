@@ -886,6 +886,15 @@ namespace cvttb200
     // arrays (numAttempts[sector] entries each: error, colour | table << 15).  winMeta receives the pair to encode, selMeta the
     // attempts whose selectors go with it (they differ only when a transparent sector 0 borrows sector 1's colour); both stay
     // -1 when no legal pair beats bestErrorIn.
+    //
+    // etc_find_best_differential_kept takes the attempts already filtered: per sector the smallest error of ALL attempts with
+    // its colour / table (first one on ties, in generation order) and, in the scratch arrays, only the kept[sector] attempts
+    // with error < bestErrorIn, in generation order -- the only ones the pair search can use.  The ETC1 / ETC2 differential
+    // stage filters while it generates (the block's best error cannot change during that stage), which leaves a fraction of
+    // the scratch stores and no second pass over them.
+    CVTT_HD void etc_find_best_differential_kept(const ETCScratch &S, const int *kept, const float *bestDiffErrors, const uint32_t *bestDiffMeta, bool canIgnore0,
+        float bestErrorIn, int *winMeta, int *selMeta, float &winTotal);
+
     CVTT_HD void etc_find_best_differential(const ETCScratch &S, const int *numAttempts, bool canIgnore0, float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
     {
         const float blockBestTotalError = bestErrorIn;
@@ -912,7 +921,13 @@ namespace cvttb200
                     kept[sector]++;
                 }
             }
+        etc_find_best_differential_kept(S, kept, bestDiffErrors, bestDiffMeta, canIgnore0, bestErrorIn, winMeta, selMeta, winTotal);
+    }
 
+    CVTT_HD void etc_find_best_differential_kept(const ETCScratch &S, const int *kept, const float *bestDiffErrors, const uint32_t *bestDiffMeta, bool canIgnore0,
+        float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
+    {
+        const float blockBestTotalError = bestErrorIn;
         if (fadd(bestDiffErrors[0], bestDiffErrors[1]) < blockBestTotalError)
         {
             // with punch-through a fully transparent sector 0 takes the colour of sector 1 and makes any pair legal (ETC.cpp:251-260)
@@ -1011,7 +1026,9 @@ namespace cvttb200
                         cumulative[sector][ch] += etc_px(p, ch);
                 }
 
-            int numAttempts[2] = { 0, 0 };
+            int kept[2] = { 0, 0 };
+            float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
+            uint32_t bestDiffMeta[2] = { 0, 0 };
             float bestIndError[2] = { FLT_MAX, FLT_MAX };
             uint32_t bestIndSelectors[2] = { 0, 0 };
             int bestIndColors[2] = { 0, 0 }, bestIndTable[2] = { 0, 0 };
@@ -1062,10 +1079,20 @@ namespace cvttb200
                             }
                             else
                             {
-                                const size_t slot = (size_t)(sector * kETCMaxAttempts + numAttempts[sector]) * S.stride;
-                                S.drsErr[slot] = error;
-                                S.drsMeta[slot] = (uint32_t)packed | ((uint32_t)table << 15);
-                                numAttempts[sector]++;
+                                // filtered as it is generated, see etc_find_best_differential_kept (best.error is fixed here)
+                                const uint32_t meta = (uint32_t)packed | ((uint32_t)table << 15);
+                                if (error < bestDiffErrors[sector])
+                                {
+                                    bestDiffErrors[sector] = error;
+                                    bestDiffMeta[sector] = meta;
+                                }
+                                if (error < best.error)
+                                {
+                                    const size_t slot = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
+                                    S.drsErr[slot] = error;
+                                    S.drsMeta[slot] = meta;
+                                    kept[sector]++;
+                                }
                             }
                         }
                         potentialOffsets += numOffsets;
@@ -1094,7 +1121,7 @@ namespace cvttb200
                     cta_sync();
                     int winMeta[2] = { -1, -1 }, selMeta[2] = { -1, -1 };
                     float winTotal = 0.0f;
-                    etc_find_best_differential(S, numAttempts, false, best.error, winMeta, selMeta, winTotal);
+                    etc_find_best_differential_kept(S, kept, bestDiffErrors, bestDiffMeta, false, best.error, winMeta, selMeta, winTotal);
                     if (winMeta[0] >= 0)
                     {
                         bestIsThisMode = true;
