@@ -882,48 +882,15 @@ namespace cvttb200
         return true;
     }
 
-    // FindBestDifferentialCombination, ETC.cpp:219-362, for one lane.  The attempts of the two half blocks are in the scratch
-    // arrays (numAttempts[sector] entries each: error, colour | table << 15).  winMeta receives the pair to encode, selMeta the
-    // attempts whose selectors go with it (they differ only when a transparent sector 0 borrows sector 1's colour); both stay
-    // -1 when no legal pair beats bestErrorIn.
+    // FindBestDifferentialCombination, ETC.cpp:219-362, for one lane.  winMeta receives the pair to encode (colour | table << 15
+    // per sector), selMeta the attempts whose selectors go with it (they differ only when a transparent sector 0 borrows
+    // sector 1's colour); both stay -1 when no legal pair beats bestErrorIn.
     //
-    // etc_find_best_differential_kept takes the attempts already filtered: per sector the smallest error of ALL attempts with
-    // its colour / table (first one on ties, in generation order) and, in the scratch arrays, only the kept[sector] attempts
-    // with error < bestErrorIn, in generation order -- the only ones the pair search can use.  The ETC1 / ETC2 differential
-    // stage filters while it generates (the block's best error cannot change during that stage), which leaves a fraction of
-    // the scratch stores and no second pass over them.
-    CVTT_HD void etc_find_best_differential_kept(const ETCScratch &S, const int *kept, const float *bestDiffErrors, const uint32_t *bestDiffMeta, bool canIgnore0,
-        float bestErrorIn, int *winMeta, int *selMeta, float &winTotal);
-
-    CVTT_HD void etc_find_best_differential(const ETCScratch &S, const int *numAttempts, bool canIgnore0, float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
-    {
-        const float blockBestTotalError = bestErrorIn;
-        float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
-        uint32_t bestDiffMeta[2] = { 0, 0 };
-        int kept[2] = { 0, 0 };
-        for (int sector = 0; sector < 2; sector++)
-            for (int i = 0; i < numAttempts[sector]; i++)
-            {
-                const size_t slot = (size_t)(sector * kETCMaxAttempts + i) * S.stride;
-                const float error = S.drsErr[slot];
-                const uint32_t meta = S.drsMeta[slot];
-                if (error < bestDiffErrors[sector])
-                {
-                    bestDiffErrors[sector] = error;
-                    bestDiffMeta[sector] = meta;
-                }
-                // stable compaction of the attempts the slow path may look at (error < blockBestTotalError)
-                if (error < blockBestTotalError)
-                {
-                    const size_t dst = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
-                    S.drsErr[dst] = error;
-                    S.drsMeta[dst] = meta;
-                    kept[sector]++;
-                }
-            }
-        etc_find_best_differential_kept(S, kept, bestDiffErrors, bestDiffMeta, canIgnore0, bestErrorIn, winMeta, selMeta, winTotal);
-    }
-
+    // The attempts arrive already filtered: per sector the smallest error of ALL attempts with its colour / table (the first
+    // one on ties, in generation order) and, in the scratch arrays, only the kept[sector] attempts with error < bestErrorIn,
+    // in generation order -- the only ones the pair search can use.  The differential stages filter while they generate (the
+    // block's best error cannot change during that stage), which leaves a fraction of the reference's
+    // DifferentialResolveStorage stores and no second pass over them.
     CVTT_HD void etc_find_best_differential_kept(const ETCScratch &S, const int *kept, const float *bestDiffErrors, const uint32_t *bestDiffMeta, bool canIgnore0,
         float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
     {
@@ -1222,7 +1189,9 @@ namespace cvttb200
                 }
             const bool canIgnore0 = numT[0] == 8;
 
-            int numAttempts[2] = { 0, 0 };
+            int kept[2] = { 0, 0 };
+            float bestDiffErrors[2] = { FLT_MAX, FLT_MAX };
+            uint32_t bestDiffMeta[2] = { 0, 0 };
             for (int sector = 0; sector < 2; sector++)
             {
                 const int n = numT[sector];
@@ -1248,10 +1217,20 @@ namespace cvttb200
                         lastColor = packed;
                         uint32_t selectors;
                         const float error = etc_test_half_block_punchthrough<UNIFORM, BT709, STRIDE>(P, L, flip, sector, packed, modifier, transparentMask, selectors);
-                        const size_t slot = (size_t)(sector * kETCMaxAttempts + numAttempts[sector]) * S.stride;
-                        S.drsErr[slot] = error;
-                        S.drsMeta[slot] = (uint32_t)packed | ((uint32_t)table << 15);
-                        numAttempts[sector]++;
+                        // filtered as it is generated, see etc_find_best_differential_kept (best.error is fixed in this stage)
+                        const uint32_t meta = (uint32_t)packed | ((uint32_t)table << 15);
+                        if (error < bestDiffErrors[sector])
+                        {
+                            bestDiffErrors[sector] = error;
+                            bestDiffMeta[sector] = meta;
+                        }
+                        if (error < best.error)
+                        {
+                            const size_t slot = (size_t)(sector * kETCMaxAttempts + kept[sector]) * S.stride;
+                            S.drsErr[slot] = error;
+                            S.drsMeta[slot] = meta;
+                            kept[sector]++;
+                        }
                     }
                 }
             }
@@ -1259,7 +1238,7 @@ namespace cvttb200
             cta_sync();
             int winMeta[2] = { -1, -1 }, selMeta[2] = { -1, -1 };
             float winTotal = 0.0f;
-            etc_find_best_differential(S, numAttempts, canIgnore0, best.error, winMeta, selMeta, winTotal);
+            etc_find_best_differential_kept(S, kept, bestDiffErrors, bestDiffMeta, canIgnore0, best.error, winMeta, selMeta, winTotal);
             if (winMeta[0] >= 0)
             {
                 bestIsThisMode = true;
