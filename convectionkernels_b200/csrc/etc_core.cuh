@@ -1005,9 +1005,9 @@ namespace cvttb200
                 for (int sector = 0; sector < 2; sector++)
                 {
                     const int16_t *potentialOffsets = T.potentialOffsets;
+                    cta_sync();         // one rendezvous per (flip, d, sector): the eight tables run the same code
                     for (int table = 0; table < 8; table++)
                     {
-                        cta_sync();
                         const int numOffsets = *potentialOffsets++;
                         int lastColor = -1;
                         for (int oi = 0; oi < numOffsets; oi++)
