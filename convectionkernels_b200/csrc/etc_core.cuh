@@ -602,9 +602,9 @@ namespace cvttb200
         uint32_t bestSelectors = 0;
         int bestTable = 0, bestLineColor = 0;
 
+        cta_sync();     // keeps the warps of the CTA in the same code region (instruction cache), see DESIGN.md
         for (int table = 0; table < 8; table++)
         {
-            cta_sync();     // keeps the warps of the CTA in the same code region (instruction cache), see DESIGN.md
             const int modifier = T.thModifier[table];
             const int modifierOffset = modifier + modifier;
 
@@ -721,9 +721,9 @@ namespace cvttb200
         uint32_t bestSectorBits = 0, bestSignBits = 0;
         int bestColors[2] = { 0, 0 }, bestTable = 0;
 
+        cta_sync();
         for (int table = 0; table < 8; table++)
         {
-            cta_sync();
             const int modifier = T.thModifier[table];
             const int modifierOffset = modifier * 2;
             int numUnique[2] = { 0, 0 };
