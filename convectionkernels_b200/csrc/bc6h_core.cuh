@@ -712,12 +712,24 @@ namespace cvttb200
         // Combine the rounds of the two subsets; a combination that improves on the best so far is committed with the
         // modes of this (partitioned, precision) that can encode it (BC67.cpp:2915-2985).
         const int numMeta1 = partitioned ? kMeta : 1;
+
+        // Most of the 12 x 12 combinations cannot improve on the best so far.  fl(a + b) is monotonic in b, so a subset-0 round
+        // whose error plus the SMALLEST valid subset-1 error is not below the lane's best has no partner that is; best.error
+        // only falls during the scan, which keeps the test conservative.  Rows that no lane of the warp can use are skipped
+        // with their twelve votes (combinations without a candidate lane are no-ops in the reference's loop as well).
+        float minErr1 = partitioned ? FLT_MAX : 0.0f;
+        if (partitioned)
+            for (int meta1 = 0; meta1 < kMeta; meta1++)
+                if ((roundValid >> (meta1 * 2 + 1)) & 1)
+                    minErr1 = sse_min(minErr1, metaErr[meta1][1]);
+
         for (int meta0 = 0; meta0 < kMeta; meta0++)
         {
             // roundValid is uniform over a group but not over the warp: only skip what every group of the warp skips, the
             // votes below must be executed by all lanes
             const bool valid0 = ((roundValid >> (meta0 * 2)) & 1) != 0;
-            if (!vote.warp_any(valid0))
+            const bool rowPossible = valid0 && ((partitioned ? fadd(metaErr[meta0][0], minErr1) : metaErr[meta0][0]) < best.error);
+            if (!vote.warp_any(rowPossible))
                 continue;
             for (int meta1 = 0; meta1 < numMeta1; meta1++)
             {

@@ -43,5 +43,5 @@ struct HostVote
     }
     bool any(bool x) { return max(x ? 1 : 0) != 0; }
     bool all(bool x) { return !any(!x); }
-    bool warp_any(bool x) { return x; }      // the argument is uniform over the group
+    bool warp_any(bool x) { return any(x); } // here the "warp" is the group; callers sit in group-uniform control flow
 };
