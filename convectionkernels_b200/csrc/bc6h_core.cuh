@@ -742,9 +742,9 @@ namespace cvttb200
                 }
                 const bool errorBetter = valid && (combinedError < best.error);
                 bool needsCommit = errorBetter;
-                bool groupActive = vote.any(errorBetter);
-                if (!vote.warp_any(groupActive))
+                if (!vote.warp_any(errorBetter))        // no lane of the warp: no group either, one vote instead of two
                     continue;
+                bool groupActive = vote.any(errorBetter);
 
                 int q[2][2][3];
                 for (int ch = 0; ch < 3; ch++)
