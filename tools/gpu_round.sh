@@ -36,5 +36,5 @@ PY
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bc7_encode -s 1 -c 1 -f -o gpurun_out/bc7_prof python /tmp/prof_small.py BC7 > gpurun_out/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bc6h_encode -s 1 -c 1 -f -o gpurun_out/bc6h_prof python /tmp/prof_small.py BC6HU > gpurun_out/ncu_full_bc6h.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:etc_encode -s 1 -c 1 -f -o gpurun_out/etc2_prof python /tmp/prof_small.py ETC2_RGBA > gpurun_out/ncu_full_etc2.log 2>&1
-tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_full_bc6h.log gpurun_out/ncu_full_etc2.log
+for f in gpurun_out/ncu_full.log gpurun_out/ncu_full_bc6h.log gpurun_out/ncu_full_etc2.log; do tail -n 2 $f; done
 fi
