@@ -120,6 +120,14 @@ namespace cvttb200
         }
     }
 
+    // etc_error (weighted form) for two colours at once in packed fp32: lane x measures cwA, lane y measures cwB.  Each lane
+    // performs exactly the scalar sequence (cw - p == cw + (-p) in IEEE arithmetic).
+    CVTT_HD f2 etc_error_pair(const F4 &p, const f2 *cw2)
+    {
+        const f2 dr = f2_sub(cw2[0], p.x), dg = f2_sub(cw2[1], p.y), db = f2_sub(cw2[2], p.z);
+        return f2_add(f2_add(f2_mul(dr, dr), f2_mul(dg, dg)), f2_mul(db, db));
+    }
+
     template<bool UNIFORM, bool BT709>
     CVTT_HD void etc_weigh(const ETCParams &P, const int *c, float *cw)
     {
@@ -658,15 +666,33 @@ namespace cvttb200
 
                 uint32_t selectors = 0;
                 float error = 0.0f;
+                const f2 pairA[3] = { f2_make(isoW[0], lineW[0][0]), f2_make(isoW[1], lineW[0][1]), f2_make(isoW[2], lineW[0][2]) };
+                const f2 pairB[3] = { f2_make(lineW[1][0], lineW[2][0]), f2_make(lineW[1][1], lineW[2][1]), f2_make(lineW[1][2], lineW[2][2]) };
                 for (int px = 0; px < 16; px++)
                 {
                     const F4 p = L.pw[px * STRIDE];
-                    float pixelError = etc_error<UNIFORM, BT709>(p, isolatedColor, isoW);
+                    float e4[4];
+                    if (!UNIFORM && !BT709)
+                    {
+                        const f2 a = etc_error_pair(p, pairA), b = etc_error_pair(p, pairB);    // isolated | line 0, line 1 | line 2
+                        e4[0] = a.x;
+                        e4[1] = a.y;
+                        e4[2] = b.x;
+                        e4[3] = b.y;
+                    }
+                    else
+                    {
+                        e4[0] = etc_error<UNIFORM, BT709>(p, isolatedColor, isoW);
+#pragma unroll
+                        for (int i = 0; i < 3; i++)
+                            e4[i + 1] = etc_error<UNIFORM, false>(p, lineColors[i], lineW[i]);
+                    }
+                    float pixelError = e4[0];
                     uint32_t pixelBestSelector = 0;
 #pragma unroll
                     for (int i = 0; i < 3; i++)
                     {
-                        const float e = etc_error<UNIFORM, false>(p, lineColors[i], lineW[i]);
+                        const float e = e4[i + 1];
                         if (e < pixelError)
                             pixelBestSelector = (uint32_t)(i + 1);
                         pixelError = sse_min(e, pixelError);
@@ -762,10 +788,22 @@ namespace cvttb200
                     etc_weigh<UNIFORM, BT709>(P, colors[0], cw[0]);
                     etc_weigh<UNIFORM, BT709>(P, colors[1], cw[1]);
                     uint32_t signBits = 0;
+                    const f2 cw2[3] = { f2_make(cw[0][0], cw[1][0]), f2_make(cw[0][1], cw[1][1]), f2_make(cw[0][2], cw[1][2]) };
                     for (int px = 0; px < 16; px++)
                     {
                         const F4 p = L.pw[px * STRIDE];
-                        const float e0 = etc_error<UNIFORM, BT709>(p, colors[0], cw[0]), e1 = etc_error<UNIFORM, BT709>(p, colors[1], cw[1]);
+                        float e0, e1;
+                        if (!UNIFORM && !BT709)
+                        {
+                            const f2 e = etc_error_pair(p, cw2);        // +modifier and -modifier colours side by side
+                            e0 = e.x;
+                            e1 = e.y;
+                        }
+                        else
+                        {
+                            e0 = etc_error<UNIFORM, BT709>(p, colors[0], cw[0]);
+                            e1 = etc_error<UNIFORM, BT709>(p, colors[1], cw[1]);
+                        }
                         if (e1 < e0)
                             signBits |= 1u << px;
                         S.hErr[(size_t)(total * 16 + px) * S.stride] = sse_min(e0, e1);
@@ -870,8 +908,7 @@ namespace cvttb200
 #pragma unroll
                 for (int h = 0; h < 2; h++)
                 {
-                    const f2 dr = f2_sub(mw[h][0], p.x), dg = f2_sub(mw[h][1], p.y), db = f2_sub(mw[h][2], p.z);
-                    const f2 e = f2_add(f2_add(f2_mul(dr, dr), f2_mul(dg, dg)), f2_mul(db, db));
+                    const f2 e = etc_error_pair(p, mw[h]);
                     e4[2 * h] = e.x;
                     e4[2 * h + 1] = e.y;
                 }
