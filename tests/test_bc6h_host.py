@@ -40,3 +40,21 @@ def test_bc6h_device_logic_on_cpu_matches_golden(hostsim_bc6h, name):
 def test_integer_quantiser_equals_directed_rounding_fp32(hostsim_bc6h):
     """the kernel's ceil(N / 31) against the reference's fp32 multiply / divide / convert under MXCSR round-up, all inputs"""
     assert hostsim_bc6h.hostsim_bc6h_quantizer_mismatches() == 0
+
+
+def test_image_content_against_reference(hostsim_bc6h, reference):
+    """The device code (compiled for the CPU) against the unmodified reference running in this process on an HDR ramp crop and
+    on random halves, unsigned and signed: exercises the pruned commit scan (rows that cannot beat the lane's best are
+    skipped) on data the fixtures do not contain.  The rcp table is this host's, like the reference's own _mm_rcp_ps."""
+    from convectionkernels_b200 import api, synth
+    opt = np.frombuffer(bytes(memoryview(api.Options())), np.uint8).copy()
+    rcp = np.ascontiguousarray(reference.rcp_table(), dtype=np.float32)      # this host's _mm_rcp_ps, as the reference itself uses it
+    for fmt, signed in (("BC6HU", 0), ("BC6HS", 1)):
+        img = synth.image_to_blocks(synth.hdr_ramp_f16(96, 96, seed=99, signed=bool(signed)))
+        rnd = synth.image_to_blocks(synth.hdr_ramp_f16(64, 64, seed=3, signed=bool(signed)))[::-1]
+        blocks = np.ascontiguousarray(np.concatenate([img, rnd]))
+        blocks = blocks[: len(blocks) // 8 * 8]
+        want = reference.encode(fmt, blocks, opt)
+        out = np.zeros_like(want)
+        assert hostsim_bc6h.hostsim_encode_bc6h(blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data) == 0
+        assert (out == want).all(), (fmt, first_mismatch(want, out))
