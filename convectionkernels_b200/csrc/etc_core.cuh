@@ -756,6 +756,10 @@ namespace cvttb200
 
             // unique colours per sector, each evaluated once against all 16 pixels (errors of the better of +-modifier)
             int total = 0;
+            float floorErr[16];
+#pragma unroll
+            for (int px = 0; px < 16; px++)
+                floorErr[px] = FLT_MAX;
             for (int sector = 0; sector < 2; sector++)
             {
                 const int count = counts[sector];
@@ -789,6 +793,7 @@ namespace cvttb200
                     etc_weigh<UNIFORM, BT709>(P, colors[1], cw[1]);
                     uint32_t signBits = 0;
                     const f2 cw2[3] = { f2_make(cw[0][0], cw[1][0]), f2_make(cw[0][1], cw[1][1]), f2_make(cw[0][2], cw[1][2]) };
+#pragma unroll
                     for (int px = 0; px < 16; px++)
                     {
                         const F4 p = L.pw[px * STRIDE];
@@ -806,7 +811,9 @@ namespace cvttb200
                         }
                         if (e1 < e0)
                             signBits |= 1u << px;
-                        S.hErr[(size_t)(total * 16 + px) * S.stride] = sse_min(e0, e1);
+                        const float em = sse_min(e0, e1);
+                        S.hErr[(size_t)(total * 16 + px) * S.stride] = em;
+                        floorErr[px] = fminf(floorErr[px], em);
                     }
                     S.hMeta[(size_t)total * S.stride] = signBits | ((uint32_t)packed << 16);
                     total++;
@@ -815,7 +822,14 @@ namespace cvttb200
 
             // colour pairs in the reference's stepping order (ETC.cpp:800-822); a lane only needs its own n0 * n1 steps
             const int n0 = numUnique[0], n1 = numUnique[1];
-            const int combos = n0 * n1;
+            // No pair can do better, pixel by pixel, than the smallest error any candidate of this table reaches there, and a
+            // sequential fp32 sum is monotonic in its terms: if even that floor does not beat the lane's best, none of the
+            // n0 * n1 pair sums can, and the lane skips them (the reference would evaluate and reject every one).
+            float floorTotal = 0.0f;
+#pragma unroll
+            for (int px = 0; px < 16; px++)
+                floorTotal = fadd(floorTotal, floorErr[px]);
+            const int combos = (floorTotal < best.error) ? n0 * n1 : 0;
             // The second colour only changes every n0 steps: its 16 per-pixel errors stay in registers in between, which halves
             // the scratch loads of this loop (they were 10 % of the kernel's instructions and 12 % of its stall samples).
             int index0 = 0, index1 = 0, loaded1 = -1;
