@@ -22,6 +22,9 @@
 
 #include "cvtt_common.cuh"
 
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 #if !defined(__CUDA_ARCH__)
 #include <xmmintrin.h>
 #endif
@@ -40,6 +43,7 @@ namespace cvttb200
         float tweak[2][4][2];              // Util::ComputeTweakFactors(tweak, range) for range 8 ([0]) and 16 ([1])
         uint32_t flags;
         int tweakRounds, refineRounds;     // clamped to 1..4 and 1..3 (BC67.cpp:2667-2675)
+        int prune;                         // skip work that provably cannot change the result (bc6h_partition); 0 only for A/B timing
     };
 
     struct BC6HTables
@@ -201,8 +205,10 @@ namespace cvttb200
         }
         else
         {
+            // e0, e1 <= 65535, so pixel31 <= 65535 and pixel31 * 31 >> 6 <= 31743: neither the 16-bit wrap nor the saturating
+            // pack of UnscaleHDRValueUnsigned can trigger
             const int pixel31 = ((64 - weight) * e0 + weight * e1 + 32) >> 6;
-            return unscale_hdr_unsigned(wrap_u16(pixel31));
+            return (pixel31 * 31) >> 6;
         }
     }
 
@@ -313,59 +319,92 @@ namespace cvttb200
         }
     }
 
+
     // ---------------------------------------------------------------------------------------------------------
-    // Per-lane pixel storage: planes of 32-bit words, element i of a plane at [i * STRIDE] (conflict-free in shared memory).
-    //   lin[px * 3 + ch] = TwosCLHalfToFloat(pixel)           (the value the errors compare against)
+    // ParallelMath::TwosCLHalfToFloat (twoscl_half_to_float above) through the hardware half -> float conversion, for 16-bit
+    // sign | exponent | mantissa patterns with exponent below 31 (unsigned pixels, and every reconstructed interpolator:
+    // BC67.cpp:766-787 clamp them to 31743).  For normal numbers the reference's bit arithmetic is the IEEE conversion.  For
+    // exponent 0 it is not: it builds 2^-15 (1 + m / 1024) and subtracts 2^-15, i.e. m 2^-25 -- HALF the IEEE value m 2^-24 --
+    // and the encoder's errors are computed with that value, so it is reproduced (tools/ubench/half_cvt_check.cu compares all
+    // patterns on the device).  The pattern 0x8000 gives -0 here and +0 there, which no caller can observe: the values are only
+    // multiplied by channel weights, subtracted from other values and squared.
+    CVTT_HD float ieee_half_bits_to_float(uint32_t u)
+    {
+#if defined(__CUDA_ARCH__)
+        return __half2float(__ushort_as_half((unsigned short)u));
+#else
+        const uint32_t sign = (u & 0x8000u) << 16, e = (u >> 10) & 31u, m = u & 0x3ffu;
+        if (e == 0)
+            return as_float(as_uint((float)m * 5.9604644775390625e-8f) | sign);       // m 2^-24, exact
+        return as_float(sign | ((e + 112u) << 23) | (m << 13));
+#endif
+    }
+
+    CVTT_HD float half_bits_to_float(uint32_t u)
+    {
+        const float f = ieee_half_bits_to_float(u);
+        return (u & 0x7c00u) ? f : fmul(f, 0.5f);
+    }
+
+    // Per-lane storage: planes of 32-bit words, element i of a plane at [i * STRIDE] (conflict-free in shared memory).
     //   pw[px * 3 + ch]  = (float)pixel * channelWeight       (EndpointSelector / EndpointRefiner input)
-    //   pix[px * 2 + k]  = pixel ch0 | ch1 << 16, pixel ch2   (only read, and only allocated, with BC6H_FastIndexing)
-    template<int STRIDE, bool WITH_PIX>
+    //   raw[px * 2 + k]  = pixel ch0 | ch1 << 16, pixel ch2   (16-bit patterns: the integers of the fast-indexing path and,
+    //                                                          read as half floats, the values the errors compare against)
+    //   tab[24]          = linear colours of the current round's interpolators (slow indexing; layout in BC6HIndexer)
+    template<int STRIDE>
     struct BC6HLane
     {
-        float *lin;
+        enum { kStride = STRIDE };
         float *pw;
-        uint32_t *pix;
+        uint32_t *raw;
+        uint32_t *tab;
 
-        CVTT_HD F4 lin_at(int px) const
-        {
-            F4 r;
-            r.x = lin[(px * 3 + 0) * STRIDE];
-            r.y = lin[(px * 3 + 1) * STRIDE];
-            r.z = lin[(px * 3 + 2) * STRIDE];
-            r.w = WITH_PIX ? as_float(pix[(px * 2 + 0) * STRIDE]) : 0.0f;
-            return r;
-        }
         CVTT_HD F4 pw_at(int px) const
         {
             F4 r;
             r.x = pw[(px * 3 + 0) * STRIDE];
             r.y = pw[(px * 3 + 1) * STRIDE];
             r.z = pw[(px * 3 + 2) * STRIDE];
-            r.w = WITH_PIX ? as_float(pix[(px * 2 + 1) * STRIDE]) : 0.0f;
+            r.w = 0.0f;
             return r;
         }
-        CVTT_HD void store(int px, const F4 &l, const F4 &q) const
+        CVTT_HD void raw_at(int px, uint32_t &w0, uint32_t &w1) const
         {
-            lin[(px * 3 + 0) * STRIDE] = l.x;
-            lin[(px * 3 + 1) * STRIDE] = l.y;
-            lin[(px * 3 + 2) * STRIDE] = l.z;
-            pw[(px * 3 + 0) * STRIDE] = q.x;
-            pw[(px * 3 + 1) * STRIDE] = q.y;
-            pw[(px * 3 + 2) * STRIDE] = q.z;
-            if (WITH_PIX)
-            {
-                pix[(px * 2 + 0) * STRIDE] = as_uint(l.w);
-                pix[(px * 2 + 1) * STRIDE] = as_uint(q.w);
-            }
+            w0 = raw[(px * 2 + 0) * STRIDE];
+            w1 = raw[(px * 2 + 1) * STRIDE];
         }
     };
 
-    // Loads one PixelBlockF16 (int16 [16][4], alpha ignored) and converts it as BC6HComputer::Pack does (BC67.cpp:2691-2715)
+    // The pixel's three values as the reference's TwosCLHalfToFloat sees them.  Signed pixels are two's complement integers
+    // (BC67.cpp:2691-2715), which that function reads as sign | 15 raw bits -- for small negative values the "exponent" is 31
+    // and the result a large finite number, not what a half conversion gives -- so the signed encoder keeps the literal formula.
+    template<bool SIGNED>
+    CVTT_HD void bc6h_raw_to_lin(uint32_t w0, uint32_t w1, float *lin)
+    {
+        if (!SIGNED)
+        {
+            lin[0] = half_bits_to_float(w0 & 0xffffu);
+            lin[1] = half_bits_to_float(w0 >> 16);
+            lin[2] = half_bits_to_float(w1 & 0xffffu);
+            return;
+        }
+        lin[0] = twoscl_half_to_float((int)(w0 & 0xffffu));
+        lin[1] = twoscl_half_to_float((int)(w0 >> 16));
+        lin[2] = twoscl_half_to_float((int)(w1 & 0xffffu));
+    }
+
+    CVTT_HD void bc6h_raw_to_int(uint32_t w0, uint32_t w1, int *c)
+    {
+        c[0] = wrap_s16((int)(w0 & 0xffffu));
+        c[1] = wrap_s16((int)(w0 >> 16));
+        c[2] = wrap_s16((int)(w1 & 0xffffu));
+    }
+
+    // Loads one PixelBlockF16 pixel (int16, alpha ignored) and converts it as BC6HComputer::Pack does (BC67.cpp:2691-2715)
     template<bool SIGNED, class Lane>
     CVTT_HD void bc6h_load_pixel(const BC6HParams &P, const Lane &L, int px, int r, int g, int b)
     {
         int c[3] = { r, g, b };
-        F4 lin, pw;
-        float lf[3], pf[3];
         for (int ch = 0; ch < 3; ch++)
         {
             int v = wrap_s16(c[ch]);
@@ -379,14 +418,10 @@ namespace cvttb200
                 v = (v > 0) ? v : 0;
             v = (v < 31743) ? v : 31743;
             c[ch] = v;
-            lf[ch] = twoscl_half_to_float(v);
-            pf[ch] = fmul((float)v, P.w[ch]);
+            L.pw[(px * 3 + ch) * Lane::kStride] = fmul((float)v, P.w[ch]);
         }
-        lin.x = lf[0]; lin.y = lf[1]; lin.z = lf[2];
-        lin.w = as_float(((uint32_t)c[0] & 0xffffu) | ((uint32_t)c[1] << 16));
-        pw.x = pf[0]; pw.y = pf[1]; pw.z = pf[2];
-        pw.w = as_float((uint32_t)c[2] & 0xffffu);
-        L.store(px, lin, pw);
+        L.raw[(px * 2 + 0) * Lane::kStride] = ((uint32_t)c[0] & 0xffffu) | ((uint32_t)c[1] << 16);
+        L.raw[(px * 2 + 1) * Lane::kStride] = (uint32_t)c[2] & 0xffffu;
     }
 
     struct BC6HBest
@@ -394,43 +429,216 @@ namespace cvttb200
         float error;
         int mode, partition;
         int ep[2][2][3];          // what goes into the block (16-bit patterns)
-        uint32_t idx[2];          // 16 x 4 bits
-    };
-
-    // One meta round's outcome for one subset
-    struct BC6HSelector
-    {
-        int e[2][3];              // interpolation endpoints (unquantised)
-        bool inverted;
+        uint32_t q[2][3];         // the committed rounds' quantised endpoints per subset and channel: ep0 | ep1 << 16
+        uint32_t inverted;        // bit s: subset s was committed with its endpoints swapped
+        bool committed;
     };
 
     // ---------------------------------------------------------------------------------------------------------
-    // All trials of one (precision, partition): fills the meta arrays, then the commit scan (BC67.cpp:2790-2988).
+    // IndexSelectorHDR of one round: set up from the quantised endpoints, then asked for the interpolator of single pixels.
+    // Indexes are not carried through the search: they are a pure function of (quantised endpoints, pixel), so the winner's
+    // are derived once per block by the same code (bc6h_derive_indexes).
+    template<bool SIGNED, bool FAST, int RANGE, int STRIDE>
+    struct BC6HIndexer
+    {
+        enum { kPairs = FAST ? 1 : RANGE / 2 };
+        f2 rw[kPairs][3];            // slow: m_reconstructedInterpolators, interpolators 2j and 2j + 1 side by side
+        int unq[2][3];               // interpolation endpoints
+        float origin[3], axis[3];    // fast: IndexSelector::Init
+
+        static CVTT_HD int weight_of(int i)
+        {
+            return wrap_u16(((RANGE == 8) ? 4681 : 2185) * i + 256) >> 9;     // g_weightReciprocals[range], IndexSelector.cpp:43-62
+        }
+
+        // q[epi][ch]: quantised endpoints as the quantiser returned them (signed values for SIGNED)
+        CVTT_HD void init(const BC6HParams &P, const BC6HLane<STRIDE> &L, const int q[2][3], int aPrec)
+        {
+            int fin[2][3];
+            for (int epi = 0; epi < 2; epi++)
+                for (int ch = 0; ch < 3; ch++)
+                    bc6h_unquantize_element<SIGNED>(q[epi][ch], aPrec, unq[epi][ch], fin[epi][ch]);
+            if (FAST)
+            {
+                float dW[3];
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    origin[ch] = (float)fin[0][ch];
+                    dW[ch] = fmul(fsub((float)fin[1][ch], origin[ch]), P.w[ch]);
+                }
+                float lenSq = fmul(dW[0], dW[0]);
+                lenSq = fadd(lenSq, fmul(dW[1], dW[1]));
+                lenSq = fadd(lenSq, fmul(dW[2], dW[2]));
+                safe_denominator(lenSq);
+                const float mdl = fdiv((float)(RANGE - 1), lenSq);
+                for (int ch = 0; ch < 3; ch++)
+                    axis[ch] = fmul(fmul(dW[ch], P.w[ch]), mdl);
+            }
+            else
+            {
+                // InitHDR (IndexSelectorHDR.h:85-108).  The linear colours go to the lane's table: as floats [i][ch] for
+                // range 8, as pairs of half patterns [ch][i / 2] for range 16 (the table has 24 words).
+#pragma unroll
+                for (int j = 0; j < RANGE / 2; j++)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++)
+                    {
+                        const uint32_t r0 = (uint32_t)bc6h_reconstruct<SIGNED>(weight_of(2 * j), unq[0][ch], unq[1][ch]) & 0xffffu;
+                        const uint32_t r1 = (uint32_t)bc6h_reconstruct<SIGNED>(weight_of(2 * j + 1), unq[0][ch], unq[1][ch]) & 0xffffu;
+                        const float f0 = half_bits_to_float(r0), f1 = half_bits_to_float(r1);
+                        rw[j][ch] = f2_make(fmul(f0, P.w[ch]), fmul(f1, P.w[ch]));
+                        if (RANGE == 8)
+                        {
+                            L.tab[((2 * j) * 3 + ch) * STRIDE] = as_uint(f0);
+                            L.tab[((2 * j + 1) * 3 + ch) * STRIDE] = as_uint(f1);
+                        }
+                        else
+                            L.tab[(ch * 8 + j) * STRIDE] = r0 | (r1 << 16);
+                    }
+            }
+        }
+
+        // Uninverted interpolator number for the pixel with raw words (w0, w1) / linear colour lin; with slow indexing rl
+        // receives that interpolator's linear colour (SelectIndexHDRSlow / SelectIndexHDRFast, IndexSelectorHDR.h:125-144).
+        CVTT_HD int select(const BC6HParams &P, const BC6HLane<STRIDE> &L, uint32_t w0, uint32_t w1, const float *lin, float *rl) const
+        {
+            if (FAST)
+            {
+                int c[3];
+                bc6h_raw_to_int(w0, w1, c);
+                float dist = fmul(fsub((float)c[0], origin[0]), axis[0]);
+                dist = fadd(dist, fmul(fsub((float)c[1], origin[1]), axis[1]));
+                dist = fadd(dist, fmul(fsub((float)c[2], origin[2]), axis[2]));
+                return packs_s16(f2i_rn(sse_clamp(dist, 0.0f, (float)(RANGE - 1))));
+            }
+            else
+            {
+                // errors of two interpolators per packed instruction, every lane with the reference's operation sequence
+                const float pl0 = fmul(lin[0], P.w[0]), pl1 = fmul(lin[1], P.w[1]), pl2 = fmul(lin[2], P.w[2]);
+                float e[RANGE];
+#pragma unroll
+                for (int j = 0; j < RANGE / 2; j++)
+                {
+                    const f2 d0 = f2_sub(pl0, rw[j][0]), d1 = f2_sub(pl1, rw[j][1]), d2 = f2_sub(pl2, rw[j][2]);
+                    const f2 err = f2_add(f2_add(f2_mul(d0, d0), f2_mul(d1, d1)), f2_mul(d2, d2));
+                    e[2 * j] = err.x;
+                    e[2 * j + 1] = err.y;
+                }
+                // "first strictly smaller in ascending order" is the lexicographic minimum of (error, index): a tournament
+                // gives the same index as the reference's sequential scan with a dependency chain of log2(RANGE) steps
+                int ix[RANGE];
+#pragma unroll
+                for (int i = 0; i < RANGE; i++)
+                    ix[i] = i;
+#pragma unroll
+                for (int step = 1; step < RANGE; step *= 2)
+#pragma unroll
+                    for (int i = 0; i + step < RANGE; i += 2 * step)
+                    {
+                        const bool better = e[i + step] < e[i];
+                        ix[i] = better ? ix[i + step] : ix[i];
+                        e[i] = better ? e[i + step] : e[i];
+                    }
+                const int index = ix[0];
+                if (RANGE == 8)
+                {
+                    rl[0] = as_float(L.tab[(index * 3 + 0) * STRIDE]);
+                    rl[1] = as_float(L.tab[(index * 3 + 1) * STRIDE]);
+                    rl[2] = as_float(L.tab[(index * 3 + 2) * STRIDE]);
+                }
+                else
+                {
+                    const int word = index >> 1, sh = (index & 1) * 16;
+                    for (int ch = 0; ch < 3; ch++)
+                        rl[ch] = half_bits_to_float((L.tab[(ch * 8 + word) * STRIDE] >> sh) & 0xffffu);
+                }
+                return index;
+            }
+        }
+
+        // error of the pixel against interpolator `raw` (ComputeErrorHDRFast / ComputeErrorHDRSlow, BCCommon.h:45-79)
+        CVTT_HD float pixel_error(const BC6HParams &P, uint32_t w0, uint32_t w1, const float *lin, int raw, const float *rl) const
+        {
+            float error = 0.0f;
+            const bool uniform = (P.flags & kFlag_Uniform) != 0;
+            if (FAST)
+            {
+                // ReconstructHDR* + SqDiffSInt16 (ParallelMath.h:996-1010)
+                int orig[3];
+                bc6h_raw_to_int(w0, w1, orig);
+                const int weight = wrap_u16(((RANGE == 8) ? 4681 : 2185) * raw + 256) >> 9;
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const int rc = bc6h_reconstruct<SIGNED>(weight, unq[0][ch], unq[1][ch]);
+                    const int hi = rc > orig[ch] ? rc : orig[ch], lo = rc > orig[ch] ? orig[ch] : rc;
+                    const uint32_t diffU = (uint32_t)wrap_u16(hi - lo);
+                    const float sq = (float)(int32_t)(diffU * diffU);
+                    error = uniform ? fadd(error, sq) : fadd(error, fmul(sq, P.wSq[ch]));
+                }
+            }
+            else
+            {
+                // SqDiff2CL(reconstructed, original)
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    const float diff = fsub(rl[ch], lin[ch]);
+                    const float sq = fmul(diff, diff);
+                    error = uniform ? fadd(error, sq) : fadd(error, fmul(sq, P.wSq[ch]));
+                }
+            }
+            return error;
+        }
+    };
+
+    // 8-bit digest (never 0) of a round's quantised endpoints, and "does any byte of (a, b, c) equal it"
+    CVTT_HD uint32_t bc6h_digest(uint32_t q0, uint32_t q1, uint32_t q2)
+    {
+        const uint32_t h = (q0 * 0x9E3779B1u) ^ (q1 * 0x85EBCA77u) ^ (q2 * 0xC2B2AE3Du);
+        return (h >> 24) | 1u;
+    }
+    CVTT_HD uint32_t bc6h_zero_byte(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
+    CVTT_HD uint32_t bc6h_byte_flags(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 15u; }      // 0x80 flags of four bytes -> four bits
+
+    // ---------------------------------------------------------------------------------------------------------
+    // All trials of one (precision, partition): the meta rounds of each subset, then the commit scan (BC67.cpp:2790-2988).
+    //
+    // Control flow is warp-uniform wherever a vote follows: a round that the group drops (below) is carried as a lane
+    // predicate (`live`) through the pixel loop instead of a group-divergent `continue`.
+    //
+    // Work that cannot change the result is skipped when no lane of the warp can use it (P.prune; the reference evaluates and
+    // rejects it).  All three tests rest on the same facts: errors are sums of non-negative terms (see `prune` below for the one
+    // configuration where they are not), fl(a + b) is monotonic in both operands, and the lane's best error only falls.
+    //   (1) after subset 0: if even its smallest round error is not below the lane's best, no combination is;
+    //   (2) in the last refinement pass (whose only product is the round's error) the pixel loop stops as soon as the partial
+    //       sum, plus the smallest subset-0 error for a subset-1 round, reaches the best -- the round is then kept with the
+    //       partial sum as its error, which cannot pass the commit test either;
+    //   (3) the commit scan is skipped when the two smallest subset errors together are not below the best.
     template<bool SIGNED, bool FAST, int RANGE, int STRIDE, class Vote>
-    CVTT_HD void bc6h_partition(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE, FAST> &L, Vote &vote, bool partitioned, int aPrec, int p,
+    CVTT_HD void bc6h_partition(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, bool partitioned, int aPrec, int p,
         const float *ufepBase /* [2][3] */, const float *ufepOffs /* [2][3] */, BC6HBest &best)
     {
         enum { kMaxTweak = 4, kMaxRefine = 3, kMeta = 12 };
         const int numSubsets = partitioned ? 2 : 1;
         const uint32_t partitionMask = partitioned ? T.partitionMask[p] : 0u;
-        const int weightRecip = (RANGE == 8) ? 4681 : 2185;           // g_weightReciprocals[range], IndexSelector.cpp:43-62
         const float maxV = (float)(RANGE - 1);
+        // not for signed fast indexing: SqDiffSInt16 (ParallelMath.h:996-1010) converts the 32-bit square as a SIGNED integer, and a
+        // sign | magnitude interpolator read as two's complement can be more than 46340 away from the pixel -- error terms can be
+        // negative there, which breaks the monotonicity the tests rely on
+        const bool prune = P.prune != 0 && !(SIGNED && FAST);
 
-        // zero-initialised like the reference build's automatics
+        // rounds that are never evaluated read as zero, like the automatics of the reference build;
+        // they are written where a round is aborted, every other round writes its own entry before anything reads it
         uint32_t metaEP[kMeta][2][3];      // [round][subset][ch]: quantised ep0 | ep1 << 16
-        uint32_t metaIdx[kMeta][2];
         float metaErr[kMeta][2];
-        for (int r = 0; r < kMeta; r++)
-            for (int s = 0; s < 2; s++)
-            {
-                metaEP[r][s][0] = metaEP[r][s][1] = metaEP[r][s][2] = 0;
-                metaIdx[r][s] = 0;
-                metaErr[r][s] = 0.0f;
-            }
         uint32_t roundValid = 0xffffffu;   // bit (round * 2 + subset); uniform over the 8 lanes of a group
+        uint32_t roundInverted = 0;        // same numbering
+        float minErr0 = FLT_MAX, minErr1 = partitioned ? FLT_MAX : 0.0f;     // smallest error of a valid round per subset
 
         for (int subset = 0; subset < numSubsets; subset++)
         {
+            if (prune && subset == 1 && !vote.warp_any(minErr0 < best.error))
+                return;
+
             const uint32_t mask = subset ? partitionMask : (~partitionMask & 0xffffu);
             int n = 0;
             float sumV[3] = { 0.0f, 0.0f, 0.0f };
@@ -443,55 +651,72 @@ namespace cvttb200
                 n++;
             }
             const int fixupIndex = (subset == 0) ? 0 : T.fixup[p];
+            uint32_t fixW0, fixW1;
+            L.raw_at(fixupIndex, fixW0, fixW1);
+            float fixPixelLin[3] = { 0.0f, 0.0f, 0.0f };
+            if (!FAST)
+                bc6h_raw_to_lin<SIGNED>(fixW0, fixW1, fixPixelLin);
+
+            uint32_t dg0 = 0, dg1 = 0, dg2 = 0;     // digests of this subset's rounds so far, one byte per round (0 = none yet)
+            float minErrS = FLT_MAX;
 
             for (int tweak = 0; tweak < kMaxTweak; tweak++)
             {
-                // EndpointRefiner sums of the previous pass; `contributed` is false after a skipped round (BC67.cpp:2843)
+                // EndpointRefiner sums of the previous pass; `contributed` is false after a dropped round (BC67.cpp:2843)
                 float tv[3] = { 0.0f, 0.0f, 0.0f }, tt = 0.0f, ts = 0.0f;
                 bool contributed = false;
 
                 for (int refinePass = 0; refinePass < kMaxRefine; refinePass++)
                 {
                     const int metaRound = tweak * kMaxRefine + refinePass;
+                    const uint32_t roundBit = 1u << (metaRound * 2 + subset);
+                    const uint32_t dgShift = (uint32_t)(metaRound & 3) * 8u;
+                    uint32_t digest;
+                    bool live = true;
+                    int ec[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+
                     if (tweak >= P.tweakRounds || refinePass >= P.refineRounds)
                     {
-                        roundValid &= ~(1u << (metaRound * 2 + subset));
-                        continue;
-                    }
-
-                    int ec[2][3];
-                    if (refinePass == 0)
-                    {
-                        // UnfinishedEndpoints::FinishHDRSigned / Unsigned
-                        const float tf[2] = { P.tweak[RANGE == 16][tweak][0], P.tweak[RANGE == 16][tweak][1] };
-                        for (int ch = 0; ch < 3; ch++)
-                            for (int epi = 0; epi < 2; epi++)
-                            {
-                                const float f = sse_clamp(fadd(ufepBase[subset * 3 + ch], fmul(ufepOffs[subset * 3 + ch], tf[epi])), SIGNED ? -31743.0f : 0.0f, 31743.0f);
-                                ec[epi][ch] = packs_s16(f2i_rn(f));
-                            }
+                        roundValid &= ~roundBit;
+                        metaEP[metaRound][subset][0] = metaEP[metaRound][subset][1] = metaEP[metaRound][subset][2] = 0;
+                        digest = bc6h_digest(0, 0, 0);
+                        live = false;
                     }
                     else
                     {
-                        // EndpointRefiner::GetRefinedEndpoints (EndpointRefiner.h:99-142) + GetRefinedEndpointsHDR (:160-175)
-                        float wN = contributed ? (float)n : 0.0f;
-                        safe_denominator(wN);
-                        const float wRcp = contributed ? P.rcpN[n] : P.rcpN[1];
-                        const float sv[3] = { contributed ? sumV[0] : 0.0f, contributed ? sumV[1] : 0.0f, contributed ? sumV[2] : 0.0f };
-                        float adenom = fmul(fsub(fmul(tt, wN), fmul(ts, ts)), wRcp);
-                        const bool adenomZero = (adenom == 0.0f);
-                        if (adenomZero)
-                            adenom = 1.0f;
-                        for (int ch = 0; ch < 3; ch++)
+                        if (refinePass == 0)
                         {
-                            const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sv[ch]), wRcp)), adenom);
-                            const float b = fmul(fsub(sv[ch], fmul(a, ts)), wRcp);
-                            float p1 = b, p2 = fadd(a, b);
+                            // UnfinishedEndpoints::FinishHDRSigned / Unsigned
+                            const float tf[2] = { P.tweak[RANGE == 16][tweak][0], P.tweak[RANGE == 16][tweak][1] };
+                            for (int ch = 0; ch < 3; ch++)
+                                for (int epi = 0; epi < 2; epi++)
+                                {
+                                    const float f = sse_clamp(fadd(ufepBase[subset * 3 + ch], fmul(ufepOffs[subset * 3 + ch], tf[epi])), SIGNED ? -31743.0f : 0.0f, 31743.0f);
+                                    ec[epi][ch] = packs_s16(f2i_rn(f));
+                                }
+                        }
+                        else
+                        {
+                            // EndpointRefiner::GetRefinedEndpoints (EndpointRefiner.h:99-142) + GetRefinedEndpointsHDR (:160-175)
+                            float wN = contributed ? (float)n : 0.0f;
+                            safe_denominator(wN);
+                            const float wRcp = contributed ? P.rcpN[n] : P.rcpN[1];
+                            const float sv[3] = { contributed ? sumV[0] : 0.0f, contributed ? sumV[1] : 0.0f, contributed ? sumV[2] : 0.0f };
+                            float adenom = fmul(fsub(fmul(tt, wN), fmul(ts, ts)), wRcp);
+                            const bool adenomZero = (adenom == 0.0f);
                             if (adenomZero)
-                                p1 = p2 = fmul(sv[ch], wRcp);
-                            const float f0 = fmul(p1, P.rcpW[ch]), f1 = fmul(p2, P.rcpW[ch]);
-                            ec[0][ch] = packs_s16(f2i_rn(sse_clamp(f0, SIGNED ? -31743.0f : 0.0f, 31743.0f)));
-                            ec[1][ch] = packs_s16(f2i_rn(sse_clamp(f1, SIGNED ? -31743.0f : 0.0f, 31743.0f)));
+                                adenom = 1.0f;
+                            for (int ch = 0; ch < 3; ch++)
+                            {
+                                const float a = fdiv(fsub(tv[ch], fmul(fmul(ts, sv[ch]), wRcp)), adenom);
+                                const float b = fmul(fsub(sv[ch], fmul(a, ts)), wRcp);
+                                float p1 = b, p2 = fadd(a, b);
+                                if (adenomZero)
+                                    p1 = p2 = fmul(sv[ch], wRcp);
+                                const float f0 = fmul(p1, P.rcpW[ch]), f1 = fmul(p2, P.rcpW[ch]);
+                                ec[0][ch] = packs_s16(f2i_rn(sse_clamp(f0, SIGNED ? -31743.0f : 0.0f, 31743.0f)));
+                                ec[1][ch] = packs_s16(f2i_rn(sse_clamp(f1, SIGNED ? -31743.0f : 0.0f, 31743.0f)));
+                            }
                         }
                     }
                     // refiners[subset].Init
@@ -499,246 +724,150 @@ namespace cvttb200
                     tt = ts = 0.0f;
                     contributed = false;
 
-                    // QuantizeEndpointsSigned / Unsigned (BC67.cpp:2503-2595)
-                    int q[2][3], unq[2][3], fin[2][3];
-                    for (int epi = 0; epi < 2; epi++)
-                        for (int ch = 0; ch < 3; ch++)
-                        {
-                            q[epi][ch] = bc6h_quantize_element<SIGNED>(ec[epi][ch], aPrec);
-                            bc6h_unquantize_element<SIGNED>(q[epi][ch], aPrec, unq[epi][ch], fin[epi][ch]);
-                        }
-
-                    // IndexSelector::Init (fast indexing only needs it) and IndexSelectorHDR::InitHDR
-                    float origin[3] = { 0, 0, 0 }, axis[3] = { 0, 0, 0 };
-                    float reconW[RANGE][3];       // m_reconstructedInterpolators
-                    float reconLin[RANGE][3];     // TwosCLHalfToFloat of the reconstructed colours (for the error)
-                    if (FAST)
+                    BC6HIndexer<SIGNED, FAST, RANGE, STRIDE> ix;
+                    int fixRaw = 0;
+                    float fixLin[3] = { 0.0f, 0.0f, 0.0f };
+                    bool invert = false;
+                    if (live)       // warp-uniform here: P.tweakRounds / P.refineRounds
                     {
-                        float dW[3];
-                        for (int ch = 0; ch < 3; ch++)
-                        {
-                            origin[ch] = (float)fin[0][ch];
-                            dW[ch] = fmul(fsub((float)fin[1][ch], origin[ch]), P.w[ch]);
-                        }
-                        float lenSq = fmul(dW[0], dW[0]);
-                        lenSq = fadd(lenSq, fmul(dW[1], dW[1]));
-                        lenSq = fadd(lenSq, fmul(dW[2], dW[2]));
-                        safe_denominator(lenSq);
-                        const float mdl = fdiv(maxV, lenSq);
-                        for (int ch = 0; ch < 3; ch++)
-                            axis[ch] = fmul(fmul(dW[ch], P.w[ch]), mdl);
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int i = 0; i < RANGE; i++)
-                        {
-                            const int weight = wrap_u16(weightRecip * i + 256) >> 9;
-#pragma unroll
+                        // QuantizeEndpointsSigned / Unsigned (BC67.cpp:2503-2595)
+                        int q[2][3];
+                        for (int epi = 0; epi < 2; epi++)
                             for (int ch = 0; ch < 3; ch++)
-                            {
-                                const float f = twoscl_half_to_float(bc6h_reconstruct<SIGNED>(weight, unq[0][ch], unq[1][ch]));
-                                reconLin[i][ch] = f;
-                                reconW[i][ch] = fmul(f, P.w[ch]);
-                            }
-                        }
-                    }
+                                q[epi][ch] = bc6h_quantize_element<SIGNED>(ec[epi][ch], aPrec);
+                        ix.init(P, L, q, aPrec);
 
-                    // index selection; returns the uninverted interpolator number
-                    auto selectIndex = [&](int px, float *linOut) -> int
-                    {
-                        const F4 lp = L.lin_at(px);
-                        if (FAST)
+                        // fix-up index and conditional inversion
+                        fixRaw = ix.select(P, L, fixW0, fixW1, fixPixelLin, fixLin);
+                        invert = (RANGE / 2 - 1) < fixRaw;
+                        const uint32_t qa[3] = { (uint32_t)wrap_u16(q[0][0]), (uint32_t)wrap_u16(q[0][1]), (uint32_t)wrap_u16(q[0][2]) };
+                        const uint32_t qb[3] = { (uint32_t)wrap_u16(q[1][0]), (uint32_t)wrap_u16(q[1][1]), (uint32_t)wrap_u16(q[1][2]) };
+                        uint32_t qp[3];
+                        for (int ch = 0; ch < 3; ch++)
+                            qp[ch] = invert ? (qb[ch] | (qa[ch] << 16)) : (qa[ch] | (qb[ch] << 16));
+                        metaEP[metaRound][subset][0] = qp[0];
+                        metaEP[metaRound][subset][1] = qp[1];
+                        metaEP[metaRound][subset][2] = qp[2];
+                        if (invert)
+                            roundInverted |= roundBit;
+                        digest = bc6h_digest(qp[0], qp[1], qp[2]);
+
+                        // A round that repeats an earlier round's endpoints on all eight lanes is dropped (BC67.cpp:2853-2877).
+                        // The digests of the earlier rounds are in registers; the exact comparison against the stored endpoints
+                        // only runs for a group whose eight lanes all have a digest match.
+                        if (metaRound > 0)
                         {
-                            const F4 pq = L.pw_at(px);
-                            const uint32_t w0 = as_uint(lp.w), w1 = as_uint(pq.w);
-                            const float c0 = (float)wrap_s16((int)(w0 & 0xffffu)), c1 = (float)wrap_s16((int)(w0 >> 16)), c2 = (float)wrap_s16((int)(w1 & 0xffffu));
-                            float dist = fmul(fsub(c0, origin[0]), axis[0]);
-                            dist = fadd(dist, fmul(fsub(c1, origin[1]), axis[1]));
-                            dist = fadd(dist, fmul(fsub(c2, origin[2]), axis[2]));
-                            return packs_s16(f2i_rn(sse_clamp(dist, 0.0f, maxV)));
-                        }
-                        else
-                        {
-                            // SelectIndexHDRSlow (IndexSelectorHDR.h:125-139)
-                            const float pl[3] = { fmul(lp.x, P.w[0]), fmul(lp.y, P.w[1]), fmul(lp.z, P.w[2]) };
-                            int index = 0;
-                            float bestError = 0.0f, l0 = reconLin[0][0], l1 = reconLin[0][1], l2 = reconLin[0][2];
-#pragma unroll
-                            for (int i = 0; i < RANGE; i++)
+                            const uint32_t x = digest * 0x01010101u;
+                            // bit r: round r's digest equals this one.  The zero-byte test can flag the byte above a true match
+                            // as well: harmless for an earlier round (it is compared exactly), masked off for rounds to come.
+                            uint32_t candidates = bc6h_byte_flags(bc6h_zero_byte(dg0 ^ x)) | (bc6h_byte_flags(bc6h_zero_byte(dg1 ^ x)) << 4) | (bc6h_byte_flags(bc6h_zero_byte(dg2 ^ x)) << 8);
+                            candidates &= (1u << metaRound) - 1u;
+                            const bool needExact = vote.all(candidates != 0);
+                            if (vote.warp_any(needExact))
                             {
-                                const float d0 = fsub(pl[0], reconW[i][0]), d1 = fsub(pl[1], reconW[i][1]), d2 = fsub(pl[2], reconW[i][2]);
-                                const float error = fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fmul(d2, d2));
-                                if (i == 0)
-                                    bestError = error;
-                                else
+                                bool anySame = false;
+                                if (needExact)
+                                    for (; candidates; candidates &= candidates - 1)
+                                    {
+                                        const int prev = ctz32(candidates);
+                                        const uint32_t p0 = metaEP[prev][subset][0], p1 = metaEP[prev][subset][1], p2 = metaEP[prev][subset][2];
+                                        anySame = anySame || (p0 == qp[0] && p1 == qp[1] && p2 == qp[2]);
+                                    }
+                                if (vote.all(needExact && anySame))
                                 {
-                                    const bool better = error < bestError;
-                                    index = better ? i : index;
-                                    l0 = better ? reconLin[i][0] : l0;      // selects, so the tables stay in registers
-                                    l1 = better ? reconLin[i][1] : l1;
-                                    l2 = better ? reconLin[i][2] : l2;
-                                    bestError = sse_min(bestError, error);
+                                    roundValid &= ~roundBit;
+                                    live = false;
                                 }
                             }
-                            linOut[0] = l0;
-                            linOut[1] = l1;
-                            linOut[2] = l2;
-                            return index;
-                        }
-                    };
-
-                    // fix-up index and conditional inversion
-                    float fixLin[3] = { 0, 0, 0 };
-                    int fixRaw = selectIndex(fixupIndex, fixLin);
-                    const bool invert = (RANGE / 2 - 1) < fixRaw;
-                    int fixIndexStored = invert ? (RANGE - 1 - fixRaw) : fixRaw;
-                    if (invert)
-                        for (int ch = 0; ch < 3; ch++)
-                        {
-                            const int t = q[0][ch];
-                            q[0][ch] = q[1][ch];
-                            q[1][ch] = t;
-                        }
-                    const uint32_t qp[3] = { (uint32_t)wrap_u16(q[0][0]) | ((uint32_t)wrap_u16(q[1][0]) << 16),
-                                             (uint32_t)wrap_u16(q[0][1]) | ((uint32_t)wrap_u16(q[1][1]) << 16),
-                                             (uint32_t)wrap_u16(q[0][2]) | ((uint32_t)wrap_u16(q[1][2]) << 16) };
-                    metaEP[metaRound][subset][0] = qp[0];
-                    metaEP[metaRound][subset][1] = qp[1];
-                    metaEP[metaRound][subset][2] = qp[2];
-                    // indexes[fixupIndex] = index (the array is shared by both subsets of the round)
-                    uint32_t roundIdx[2] = { 0, 0 }, roundMask[2] = { 0, 0 };
-                    {
-                        const int sh = 4 * (fixupIndex & 7);
-                        roundIdx[fixupIndex >> 3] = (uint32_t)fixIndexStored << sh;
-                        roundMask[fixupIndex >> 3] = 15u << sh;
-                    }
-
-                    // a round that repeats an earlier round's endpoints on all eight lanes is dropped (BC67.cpp:2853-2877)
-                    if (metaRound > 0)
-                    {
-                        bool anySame = false;
-                        for (int prev = 0; prev < metaRound; prev++)
-                            anySame = anySame || (metaEP[prev][subset][0] == qp[0] && metaEP[prev][subset][1] == qp[1] && metaEP[prev][subset][2] == qp[2]);
-                        if (vote.all(anySame))
-                        {
-                            roundValid &= ~(1u << (metaRound * 2 + subset));
-                            for (int h = 0; h < 2; h++)
-                                metaIdx[metaRound][h] = (metaIdx[metaRound][h] & ~roundMask[h]) | roundIdx[h];
-                            continue;
                         }
                     }
+                    {
+                        const uint32_t v = digest << dgShift;
+                        if (metaRound < 4) dg0 |= v;
+                        else if (metaRound < 8) dg1 |= v;
+                        else dg2 |= v;
+                    }
+                    if (!vote.warp_any(live))
+                        continue;
 
                     float subsetError = 0.0f;
                     const bool refineNext = (refinePass != P.refineRounds - 1);
+                    const bool pruneLoop = prune && !refineNext;
                     for (uint32_t m = mask; m; m &= m - 1)
                     {
                         const int px = ctz32(m);
-                        float rl[3] = { fixLin[0], fixLin[1], fixLin[2] };
-                        int raw, index;
-                        if (px == fixupIndex)
+                        if (live)
                         {
-                            raw = fixRaw;
-                            index = fixIndexStored;
-                        }
-                        else
-                        {
-                            raw = selectIndex(px, rl);
-                            index = invert ? (RANGE - 1 - raw) : raw;
-                            const int sh = 4 * (px & 7);
-                            if (px < 8)
-                            {
-                                roundIdx[0] |= (uint32_t)index << sh;
-                                roundMask[0] |= 15u << sh;
-                            }
-                            else
-                            {
-                                roundIdx[1] |= (uint32_t)index << sh;
-                                roundMask[1] |= 15u << sh;
-                            }
-                        }
+                            uint32_t w0, w1;
+                            L.raw_at(px, w0, w1);
+                            float lin[3] = { 0.0f, 0.0f, 0.0f };
+                            if (!FAST)
+                                bc6h_raw_to_lin<SIGNED>(w0, w1, lin);
+                            float rl[3] = { fixLin[0], fixLin[1], fixLin[2] };
+                            int raw = fixRaw;
+                            if (px != fixupIndex)
+                                raw = ix.select(P, L, w0, w1, lin, rl);
+                            subsetError = fadd(subsetError, ix.pixel_error(P, w0, w1, lin, raw, rl));
 
-                        const F4 lp = L.lin_at(px);
-                        float error = 0.0f;
-                        if (FAST)
-                        {
-                            // ReconstructHDR* + ComputeErrorHDRFast (BCCommon.h:45-61, SqDiffSInt16 ParallelMath.h:996-1010)
-                            const F4 pq = L.pw_at(px);
-                            const uint32_t w0 = as_uint(lp.w), w1 = as_uint(pq.w);
-                            const int orig[3] = { wrap_s16((int)(w0 & 0xffffu)), wrap_s16((int)(w0 >> 16)), wrap_s16((int)(w1 & 0xffffu)) };
-                            const int weight = wrap_u16(weightRecip * raw + 256) >> 9;
-                            for (int ch = 0; ch < 3; ch++)
+                            if (refineNext)
                             {
-                                const int rc = bc6h_reconstruct<SIGNED>(weight, unq[0][ch], unq[1][ch]);
-                                const int hi = rc > orig[ch] ? rc : orig[ch], lo = rc > orig[ch] ? orig[ch] : rc;
-                                const uint32_t diffU = (uint32_t)wrap_u16(hi - lo);
-                                const float sq = (float)(int32_t)(diffU * diffU);
-                                error = (P.flags & kFlag_Uniform) ? fadd(error, sq) : fadd(error, fmul(sq, P.wSq[ch]));
+                                // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92)
+                                const int index = invert ? (RANGE - 1 - raw) : raw;
+                                const F4 pq = L.pw_at(px);
+                                const float t = fmul((float)index, 1.0f / maxV);
+                                tv[0] = fadd(tv[0], fmul(t, pq.x));
+                                tv[1] = fadd(tv[1], fmul(t, pq.y));
+                                tv[2] = fadd(tv[2], fmul(t, pq.z));
+                                tt = fadd(tt, fmul(t, t));
+                                ts = fadd(ts, t);
+                                contributed = true;
                             }
                         }
-                        else
+                        if (pruneLoop)
                         {
-                            // ComputeErrorHDRSlow (BCCommon.h:63-79): SqDiff2CL(reconstructed, original)
-                            const float ol[3] = { lp.x, lp.y, lp.z };
-                            for (int ch = 0; ch < 3; ch++)
-                            {
-                                const float diff = fsub(rl[ch], ol[ch]);
-                                const float sq = fmul(diff, diff);
-                                error = (P.flags & kFlag_Uniform) ? fadd(error, sq) : fadd(error, fmul(sq, P.wSq[ch]));
-                            }
-                        }
-                        subsetError = fadd(subsetError, error);
-
-                        if (refineNext)
-                        {
-                            // EndpointRefiner::ContributeUnweightedPW (EndpointRefiner.h:78-92)
-                            const F4 pq = L.pw_at(px);
-                            const float t = fmul((float)index, 1.0f / maxV);
-                            tv[0] = fadd(tv[0], fmul(t, pq.x));
-                            tv[1] = fadd(tv[1], fmul(t, pq.y));
-                            tv[2] = fadd(tv[2], fmul(t, pq.z));
-                            tt = fadd(tt, fmul(t, t));
-                            ts = fadd(ts, t);
-                            contributed = true;
+                            const float bound = (subset == 0) ? subsetError : fadd(minErr0, subsetError);
+                            if (!vote.warp_any(live && bound < best.error))
+                                break;
                         }
                     }
-                    metaErr[metaRound][subset] = subsetError;
-                    for (int h = 0; h < 2; h++)
-                        metaIdx[metaRound][h] = (metaIdx[metaRound][h] & ~roundMask[h]) | roundIdx[h];
+                    if (live)
+                    {
+                        metaErr[metaRound][subset] = subsetError;
+                        minErrS = sse_min(minErrS, subsetError);
+                    }
                 }
             }
+            if (subset == 0)
+                minErr0 = minErrS;
+            else
+                minErr1 = minErrS;
         }
 
         // Combine the rounds of the two subsets; a combination that improves on the best so far is committed with the
         // modes of this (partitioned, precision) that can encode it (BC67.cpp:2915-2985).
+        if (prune && !vote.warp_any(fadd(minErr0, minErr1) < best.error))
+            return;
         const int numMeta1 = partitioned ? kMeta : 1;
-
-        // Most of the 12 x 12 combinations cannot improve on the best so far.  fl(a + b) is monotonic in b, so a subset-0 round
-        // whose error plus the SMALLEST valid subset-1 error is not below the lane's best has no partner that is; best.error
-        // only falls during the scan, which keeps the test conservative.  Rows that no lane of the warp can use are skipped
-        // with their twelve votes (combinations without a candidate lane are no-ops in the reference's loop as well).
-        float minErr1 = partitioned ? FLT_MAX : 0.0f;
-        if (partitioned)
-            for (int meta1 = 0; meta1 < kMeta; meta1++)
-                if ((roundValid >> (meta1 * 2 + 1)) & 1)
-                    minErr1 = sse_min(minErr1, metaErr[meta1][1]);
 
         for (int meta0 = 0; meta0 < kMeta; meta0++)
         {
             // roundValid is uniform over a group but not over the warp: only skip what every group of the warp skips, the
-            // votes below must be executed by all lanes
+            // votes below must be executed by all lanes.  A subset-0 round whose error plus the smallest subset-1 error is
+            // not below the lane's best has no partner that is.
             const bool valid0 = ((roundValid >> (meta0 * 2)) & 1) != 0;
-            const bool rowPossible = valid0 && ((partitioned ? fadd(metaErr[meta0][0], minErr1) : metaErr[meta0][0]) < best.error);
+            const float err0 = valid0 ? metaErr[meta0][0] : FLT_MAX;
+            const bool rowPossible = valid0 && (fadd(err0, minErr1) < best.error);
             if (!vote.warp_any(rowPossible))
                 continue;
             for (int meta1 = 0; meta1 < numMeta1; meta1++)
             {
-                float combinedError = metaErr[meta0][0];
+                float combinedError = err0;
                 bool valid = valid0;
                 if (partitioned)
                 {
-                    valid = valid && ((roundValid >> (meta1 * 2 + 1)) & 1) != 0;
-                    combinedError = fadd(combinedError, metaErr[meta1][1]);
+                    const bool valid1 = ((roundValid >> (meta1 * 2 + 1)) & 1) != 0;
+                    valid = valid && valid1;
+                    combinedError = fadd(combinedError, valid1 ? metaErr[meta1][1] : FLT_MAX);
                 }
                 const bool errorBetter = valid && (combinedError < best.error);
                 bool needsCommit = errorBetter;
@@ -751,8 +880,8 @@ namespace cvttb200
                 {
                     q[0][0][ch] = (int)(metaEP[meta0][0][ch] & 0xffffu);
                     q[0][1][ch] = (int)(metaEP[meta0][0][ch] >> 16);
-                    q[1][0][ch] = (int)(metaEP[meta1][1][ch] & 0xffffu);
-                    q[1][1][ch] = (int)(metaEP[meta1][1][ch] >> 16);
+                    q[1][0][ch] = partitioned ? (int)(metaEP[meta1][1][ch] & 0xffffu) : 0;
+                    q[1][1][ch] = partitioned ? (int)(metaEP[meta1][1][ch] >> 16) : 0;
                 }
 
                 for (int mode = 0; mode < 14; mode++)
@@ -773,22 +902,19 @@ namespace cvttb200
                             best.error = combinedError;
                             best.mode = mode;
                             best.partition = p;
+                            best.committed = true;
                             for (int s = 0; s < numSubsets; s++)
                                 for (int e = 0; e < 2; e++)
                                     for (int ch = 0; ch < 3; ch++)
                                         best.ep[s][e][ch] = enc[s][e][ch];
-                            // pixels of subset 0 take the indexes of meta0, pixels of subset 1 those of meta1
-                            uint32_t sel[2];
-                            for (int h = 0; h < 2; h++)
+                            // pixels of subset 0 take the indexes of meta0, pixels of subset 1 those of meta1: remembered as
+                            // the rounds' endpoints and inversion, from which bc6h_derive_indexes recomputes them
+                            for (int ch = 0; ch < 3; ch++)
                             {
-                                uint32_t nib = 0;
-                                const uint32_t pm = (partitionMask >> (8 * h)) & 0xffu;
-                                for (int k = 0; k < 8; k++)
-                                    if ((pm >> k) & 1)
-                                        nib |= 15u << (4 * k);
-                                sel[h] = nib;
-                                best.idx[h] = (metaIdx[meta0][h] & ~sel[h]) | (metaIdx[meta1][h] & sel[h]);
+                                best.q[0][ch] = metaEP[meta0][0][ch];
+                                best.q[1][ch] = partitioned ? metaEP[meta1][1][ch] : 0u;
                             }
+                            best.inverted = ((roundInverted >> (meta0 * 2)) & 1u) | (partitioned ? (((roundInverted >> (meta1 * 2 + 1)) & 1u) << 1) : 0u);
                         }
                     }
                     needsCommit = needsCommit && !legalAndBetter;
@@ -801,19 +927,62 @@ namespace cvttb200
         }
     }
 
+    // Indexes of the committed rounds: IndexSelectorHDR again on the winner's endpoints (the search keeps no indexes).
+    template<bool SIGNED, bool FAST, int RANGE, int STRIDE>
+    CVTT_HD void bc6h_derive_indexes(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, const BC6HBest &best, int aPrec, uint32_t idx[2])
+    {
+        const bool partitioned = (RANGE == 8);
+        const uint32_t partitionMask = partitioned ? T.partitionMask[best.partition] : 0u;
+        for (int subset = 0; subset < (partitioned ? 2 : 1); subset++)
+        {
+            const uint32_t mask = subset ? partitionMask : (~partitionMask & 0xffffu);
+            const bool inverted = ((best.inverted >> subset) & 1u) != 0;
+            int q[2][3];
+            for (int ch = 0; ch < 3; ch++)
+            {
+                // the stored pair is in block order; the round searched with the quantiser's order
+                const int a = (int)(best.q[subset][ch] & 0xffffu), b = (int)(best.q[subset][ch] >> 16);
+                q[0][ch] = inverted ? b : a;
+                q[1][ch] = inverted ? a : b;
+                if (SIGNED)
+                {
+                    q[0][ch] = wrap_s16(q[0][ch]);
+                    q[1][ch] = wrap_s16(q[1][ch]);
+                }
+            }
+            BC6HIndexer<SIGNED, FAST, RANGE, STRIDE> ix;
+            ix.init(P, L, q, aPrec);
+            for (uint32_t m = mask; m; m &= m - 1)
+            {
+                const int px = ctz32(m);
+                uint32_t w0, w1;
+                L.raw_at(px, w0, w1);
+                float lin[3] = { 0.0f, 0.0f, 0.0f }, rl[3];
+                if (!FAST)
+                    bc6h_raw_to_lin<SIGNED>(w0, w1, lin);
+                const int raw = ix.select(P, L, w0, w1, lin, rl);
+                const int index = inverted ? (RANGE - 1 - raw) : raw;
+                idx[px >> 3] |= (uint32_t)index << (4 * (px & 7));
+            }
+        }
+    }
+
     // ---------------------------------------------------------------------------------------------------------
     // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).
     template<bool SIGNED, bool FAST, int STRIDE, class Vote>
-    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE, FAST> &L, Vote &vote, uint32_t out[4])
+    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, uint32_t out[4])
     {
         BC6HBest best;
         best.error = FLT_MAX;
         best.mode = 0;
         best.partition = 0;
+        best.inverted = 0;
+        best.committed = false;
         for (int s = 0; s < 2; s++)
             for (int e = 0; e < 2; e++)
                 best.ep[s][e][0] = best.ep[s][e][1] = best.ep[s][e][2] = 0;
-        best.idx[0] = best.idx[1] = 0;
+        for (int s = 0; s < 2; s++)
+            best.q[s][0] = best.q[s][1] = best.q[s][2] = 0;
 
         // endpoint fits of the 32 partitions and of the whole block (BC67.cpp:2739-2774)
         float ufepBase[33][6], ufepOffs[33][6];
@@ -851,6 +1020,14 @@ namespace cvttb200
         // mask its argument; the fix-up indexes have their top bit clear by construction)
         const uint8_t *mi = T.modes[best.mode];
         const bool partitioned = mi[1] != 0;
+        uint32_t idx[2] = { 0, 0 };
+        if (best.committed)
+        {
+            if (partitioned)
+                bc6h_derive_indexes<SIGNED, FAST, 8, STRIDE>(P, T, L, best, (int)mi[3], idx);
+            else
+                bc6h_derive_indexes<SIGNED, FAST, 16, STRIDE>(P, T, L, best, (int)mi[3], idx);
+        }
         const int headerBits = partitioned ? 82 : 65;
         uint32_t fields[14];
         fields[0] = mi[0];
@@ -874,7 +1051,7 @@ namespace cvttb200
         const int indexBits = partitioned ? 3 : 4;
         for (int px = 0; px < 16; px++)
         {
-            const uint32_t index = (best.idx[px >> 3] >> (4 * (px & 7))) & 15u;
+            const uint32_t index = (idx[px >> 3] >> (4 * (px & 7))) & 15u;
             const int bits = (px == 0 || px == fixupIndex1) ? indexBits - 1 : indexBits;
             const int vOffset = offset >> 5, bitOffset = offset & 31;
             v[vOffset] |= index << bitOffset;

@@ -2,6 +2,7 @@
 #include "bc6h_host.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bc6h_tables.inc"
@@ -37,6 +38,8 @@ namespace cvttb200
         P.flags = options.flags;
         P.tweakRounds = std::min(4, std::max(1, options.seedPoints));
         P.refineRounds = std::min(3, std::max(1, options.refineRoundsBC6H));
+        const char *noPrune = getenv("CVTTB200_BC6H_NO_PRUNE");          // A/B timing only: results are identical either way
+        P.prune = (noPrune && noPrune[0] == '1') ? 0 : 1;
     }
 
     const BC6HTables &bc6h_tables()

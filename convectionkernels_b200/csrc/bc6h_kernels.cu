@@ -14,30 +14,30 @@ using namespace cvttb200;
 namespace
 {
     constexpr int kBC6HThreads = 128;
-    // per thread: 48 + 48 floats, plus 32 words of raw pixels for the fast-indexing kernels
-    constexpr size_t kBC6HSmemBytesSlow = (size_t)kBC6HThreads * 96 * 4, kBC6HSmemBytesFast = (size_t)kBC6HThreads * 128 * 4;
+    // per thread: 48 pre-weighted floats, 32 words of raw pixels, and the 24-word interpolator table of the slow index search
+    constexpr size_t kBC6HSmemBytesSlow = (size_t)kBC6HThreads * 104 * 4, kBC6HSmemBytesFast = (size_t)kBC6HThreads * 80 * 4;
 
     __constant__ BC6HTables c_bc6hTables;
 
     // One thread per block, warp = 4 reference groups.  Input: PixelBlockF16 = int16 [16][4] (128 B, alpha ignored), read
-    // with eight 128-bit loads per thread; converted once into [word][thread] planes in shared memory (384 B per thread, so
-    // that four CTAs = 16 warps fit an SM).
+    // with eight 128-bit loads per thread; converted once into [word][thread] planes in shared memory (416 B per thread with
+    // the interpolator table, so that four CTAs = 16 warps fit an SM).
     template<bool SIGNED, bool FAST>
     __global__ void __launch_bounds__(kBC6HThreads, 4)
     bc6h_encode_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks)
     {
         extern __shared__ __align__(16) unsigned char smem[];
-        float *sLin = reinterpret_cast<float *>(smem);
-        float *sPw = sLin + 48 * kBC6HThreads;
+        float *sPw = reinterpret_cast<float *>(smem);
+        uint32_t *sRaw = reinterpret_cast<uint32_t *>(sPw + 48 * kBC6HThreads);
 
         const uint32_t tid = threadIdx.x;
         const uint32_t block = blockIdx.x * kBC6HThreads + tid;
         const bool active = block < nBlocks;
 
-        BC6HLane<kBC6HThreads, FAST> L;
-        L.lin = sLin + tid;
+        BC6HLane<kBC6HThreads> L;
         L.pw = sPw + tid;
-        L.pix = reinterpret_cast<uint32_t *>(sPw + 48 * kBC6HThreads) + tid;
+        L.raw = sRaw + tid;
+        L.tab = sRaw + 32 * kBC6HThreads + tid;           // only touched with slow indexing
 #pragma unroll
         for (int q = 0; q < 8; q++)
         {

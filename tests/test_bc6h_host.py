@@ -20,6 +20,7 @@ def hostsim_bc6h():
                            os.path.join(ROOT, "tests", "hostsim", "hostsim_bc6h.cpp"), os.path.join(csrc, "bc6h_host.cpp")])
     H = ctypes.CDLL(out)
     H.hostsim_encode_bc6h.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    H.hostsim_encode_bc6h_warp.argtypes = H.hostsim_encode_bc6h.argtypes
     return H
 
 
@@ -42,6 +43,32 @@ def test_integer_quantiser_equals_directed_rounding_fp32(hostsim_bc6h):
     assert hostsim_bc6h.hostsim_bc6h_quantizer_mismatches() == 0
 
 
+def test_half_conversion_reproduces_the_reference_formula(hostsim_bc6h):
+    """TwosCLHalfToFloat is NOT the IEEE conversion for exponent 0 (it yields m * 2^-25); the kernels convert in hardware and
+    halve those values"""
+    assert hostsim_bc6h.hostsim_bc6h_half_conversion_mismatches() == 0
+
+
+def test_random_blocks_with_denormals_and_wrapping_errors(hostsim_bc6h, reference):
+    """Blocks of the GPU suite's random set that a plain IEEE half conversion gets wrong (half denormals) and that the exact
+    pruning must not touch (signed fast indexing: SqDiffSInt16 yields negative error terms), simulated warp of four groups."""
+    from convectionkernels_b200 import api, synth
+    rcp = np.ascontiguousarray(reference.rcp_table(), dtype=np.float32)
+    for fmt, signed, flags, picks in (("BC6HU", 0, None, (77, 203, 275, 491)), ("BC6HS", 1, None, (41, 401, 1216, 3262)),
+                                      ("BC6HS", 1, api.Flags.Default | 0x240, (299, 587, 701, 749))):
+        o = api.Options()
+        if flags is not None:
+            o.flags = flags
+        opt = np.frombuffer(bytes(memoryview(o)), np.uint8).copy()
+        all_blocks = synth.random_blocks_f16(4096 + 8, seed=77, signed=bool(signed))
+        idx = (np.array([b // 8 for b in picks])[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+        blocks = np.ascontiguousarray(all_blocks[idx])
+        want = reference.encode(fmt, blocks, opt)
+        out = np.zeros_like(want)
+        assert hostsim_bc6h.hostsim_encode_bc6h_warp(blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data) == 0
+        assert (out == want).all(), (fmt, flags, first_mismatch(want, out))
+
+
 def test_image_content_against_reference(hostsim_bc6h, reference):
     """The device code (compiled for the CPU) against the unmodified reference running in this process on an HDR ramp crop and
     on random halves, unsigned and signed: exercises the pruned commit scan (rows that cannot beat the lane's best are
@@ -58,3 +85,17 @@ def test_image_content_against_reference(hostsim_bc6h, reference):
         out = np.zeros_like(want)
         assert hostsim_bc6h.hostsim_encode_bc6h(blocks.ctypes.data, len(blocks), out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data) == 0
         assert (out == want).all(), (fmt, first_mismatch(want, out))
+
+
+def test_pruning_does_not_change_results(hostsim_bc6h, monkeypatch):
+    """bc6h_partition skips work that provably cannot change the result (P.prune); with the skipping switched off
+    (CVTTB200_BC6H_NO_PRUNE=1, the A/B timing knob) the bytes must be the same."""
+    g = load_golden("bc6hu_random")
+    blocks = np.ascontiguousarray(g["blocks"])
+    n = blocks.shape[0]
+    opt = np.ascontiguousarray(g["options"])
+    rcp = np.ascontiguousarray(g["rcp"], dtype=np.float32)
+    monkeypatch.setenv("CVTTB200_BC6H_NO_PRUNE", "1")
+    out = np.zeros((n, 16), np.uint8)
+    assert hostsim_bc6h.hostsim_encode_bc6h(blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data, 0, rcp.ctypes.data) == 0
+    assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# BC6H iteration pass on the GPU box: parity tests, timing with and without the exact pruning, one full ncu capture.
+mkdir -p gpurun_out
+python -m pytest tests/test_bc6h_gpu.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_bc6h.log
+python tools/time_format.py BC6HU 2>&1 | tail -1 | tee gpurun_out/time_bc6hu.json
+CVTTB200_BC6H_NO_PRUNE=1 python tools/time_format.py BC6HU 2>&1 | tail -1 | tee gpurun_out/time_bc6hu_noprune.json
+python tools/time_format.py BC6HS 2>&1 | tail -1 | tee gpurun_out/time_bc6hs.json
+if [ "$1" != "noprof" ]; then
+bash tools/prof_one.sh BC6HU bc6h_encode bc6hu_r2a
+fi

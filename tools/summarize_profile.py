@@ -47,8 +47,12 @@ def num(k):
 
 
 dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+sys.path.insert(0, ROOT)
+import bench
 summary = {
     "source": os.path.basename(rep), "captured_launch_blocks": blocks,
+    "kernel_source_hash": bench.kernel_source_hash(summary_name),
+    "kernel_source_hash_note": "sha256[:16] over bench.KERNEL_SOURCES[name] at capture time; bench.py only uses the instruction count while it still matches",
     "kernel_time_s_under_ncu": num("gpu__time_duration.sum"),
     "dram_bytes_per_block": dram / blocks,
     "dram_bytes_per_launch": dram / blocks * 1048576,
