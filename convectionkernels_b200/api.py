@@ -108,6 +108,7 @@ def _lib():
         L.cvttb200_input_block_bytes.restype = ctypes.c_size_t
         L.cvttb200_output_block_bytes.restype = ctypes.c_size_t
         L.cvttb200_encode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cvttb200_encode_ex.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.cvttb200_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.cvttb200_encode_multi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.cvttb200_set_rcp_table.argtypes = [ctypes.c_void_p]
@@ -178,13 +179,36 @@ def _as_struct_ptr(obj, ctype):
     return ctypes.cast(buf.ctypes.data, ctypes.c_void_p), buf
 
 
-def encode(fmt, pBlocks, options, encodingPlan=None, out=None):
+def _check_out(out, like_torch, need_bytes, device=None, dtype="uint8"):
+    """A caller-supplied output buffer must be contiguous, of the expected element type, with room for need_bytes, and of the
+    same kind (and device) as the input: the library writes through its raw pointer."""
+    if _is_torch(out):
+        import torch
+        if out.dtype != getattr(torch, dtype) or not out.is_contiguous() or out.numel() * out.element_size() < need_bytes:
+            raise ValueError("out must be a contiguous %s tensor of at least %d bytes" % (dtype, need_bytes))
+        if like_torch and device is not None and out.device != device:
+            raise ValueError("out is on %s, the input on %s" % (out.device, device))
+        if not like_torch and out.is_cuda:
+            raise ValueError("host input needs a host `out` (numpy array or CPU tensor)")
+    else:
+        if like_torch and device is not None and device.type == "cuda":
+            raise ValueError("a CUDA input needs a CUDA tensor as `out`")
+        if not isinstance(out, np.ndarray) or out.dtype != np.dtype(dtype) or not out.flags["C_CONTIGUOUS"] or out.nbytes < need_bytes:
+            raise ValueError("out must be a C-contiguous %s array of at least %d bytes" % (dtype, need_bytes))
+        if not out.flags["WRITEABLE"]:
+            raise ValueError("out is read-only")
+
+
+def encode(fmt, pBlocks, options, encodingPlan=None, out=None, etc2AllocOptions=None):
     """Encodes pBlocks (numpy array or torch CUDA tensor holding n PixelBlocks, n % 8 == 0) to `fmt`.
 
+    etc2AllocOptions: the Options the caller's AllocETC2Data received (ETC2 colour formats only; None = `options`).
     Returns a (n, outBytes) uint8 array of the same kind as the input (or `out` if given)."""
     L = _lib()
     f = FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
     inb, outb = L.cvttb200_input_block_bytes(f), L.cvttb200_output_block_bytes(f)
+    if not inb:
+        raise ValueError("unknown format %r" % (fmt,))
     keep = []
 
     def struct_arg(obj, ctype):
@@ -199,21 +223,29 @@ def encode(fmt, pBlocks, options, encodingPlan=None, out=None):
         src = pBlocks.contiguous()
         nbytes = src.numel() * src.element_size()
         n = nbytes // inb
+        if n * inb != nbytes:
+            raise ValueError("input size is not a whole number of blocks")
         if out is None:
             out = torch.empty((n, outb), dtype=torch.uint8, device=src.device)
+        else:
+            _check_out(out, True, n * outb, src.device)
         stream = torch.cuda.current_stream(src.device).cuda_stream if src.is_cuda else None
         with torch.cuda.device(src.device if src.is_cuda else torch.cuda.current_device()):
-            st = L.cvttb200_encode(f, src.data_ptr(), n, out.data_ptr(), struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan), stream)
+            st = L.cvttb200_encode_ex(f, src.data_ptr(), n, out.data_ptr(), struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan),
+                                      struct_arg(etc2AllocOptions, Options), stream)
     else:
         src = np.ascontiguousarray(pBlocks)
         nbytes = src.size * src.itemsize
         n = nbytes // inb
+        if n * inb != nbytes:
+            raise ValueError("input size is not a whole number of blocks")
         if out is None:
             out = np.empty((n, outb), dtype=np.uint8)
+        else:
+            _check_out(out, False, n * outb)
         optr = out.data_ptr() if _is_torch(out) else out.ctypes.data
-        st = L.cvttb200_encode(f, src.ctypes.data, n, optr, struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan), None)
-    if n * inb != nbytes:
-        raise ValueError("input size is not a whole number of blocks")
+        st = L.cvttb200_encode_ex(f, src.ctypes.data, n, optr, struct_arg(options, Options), struct_arg(encodingPlan, BC7EncodingPlan),
+                                  struct_arg(etc2AllocOptions, Options), None)
     _check(st)
     return out
 
@@ -274,21 +306,46 @@ def EncodeETC1(pBlocks, options, compressionData=None, out=None):
     return encode("ETC1", pBlocks, options, None, out)
 
 
+class ETC2CompressionData:
+    """What cvtt::Kernels::AllocETC2Data returns (ConvectionKernels.h:268).  The reference's object is CPU scratch plus the chroma
+    side axes derived from the allocation-time Options (ConvectionKernels_ETC.cpp:3117-3145); the device scratch is per call
+    here, so only the options are kept."""
+
+    def __init__(self, options):
+        self.options = Options()
+        ctypes.memmove(ctypes.byref(self.options), ctypes.byref(options), ctypes.sizeof(Options))
+
+
+def AllocETC2Data(options):
+    """cvtt::Kernels::AllocETC2Data (the allocator arguments of the reference have no meaning here)"""
+    return ETC2CompressionData(options)
+
+
+def ReleaseETC2Data(compressionData):
+    """cvtt::Kernels::ReleaseETC2Data"""
+    return None
+
+
+def _alloc_options(compressionData):
+    return None if compressionData is None else compressionData.options
+
+
 def EncodeETC2(pBlocks, options, compressionData=None, out=None):
-    """cvtt::Kernels::EncodeETC2, reference ConvectionKernels.h:254 / ConvectionKernels_API.cpp:215-228"""
-    return encode("ETC2", pBlocks, options, None, out)
+    """cvtt::Kernels::EncodeETC2, reference ConvectionKernels.h:254 / ConvectionKernels_API.cpp:215-228.  compressionData: what
+    AllocETC2Data returned (None = allocated with the same options)"""
+    return encode("ETC2", pBlocks, options, None, out, _alloc_options(compressionData))
 
 
 def EncodeETC2RGBA(pBlocks, options, compressionData=None, out=None):
     """cvtt::Kernels::EncodeETC2RGBA, reference ConvectionKernels.h:255 / ConvectionKernels_API.cpp:270-286: EAC alpha in bytes
     0-7, ETC2 colour in bytes 8-15"""
-    return encode("ETC2_RGBA", pBlocks, options, None, out)
+    return encode("ETC2_RGBA", pBlocks, options, None, out, _alloc_options(compressionData))
 
 
 def EncodeETC2PunchthroughAlpha(pBlocks, options, compressionData=None, out=None):
     """cvtt::Kernels::EncodeETC2PunchthroughAlpha, reference ConvectionKernels.h:255 / ConvectionKernels_API.cpp:231-244: pixels whose
     alpha is below options.threshold become the transparent index"""
-    return encode("ETC2_PUNCHTHROUGH", pBlocks, options, None, out)
+    return encode("ETC2_PUNCHTHROUGH", pBlocks, options, None, out, _alloc_options(compressionData))
 
 
 def EncodeETC2Alpha(pBlocks, options, out=None):
@@ -353,16 +410,24 @@ def decode(fmt, pBC, out=None):
         import torch
         src = pBC.contiguous()
         n = (src.numel() * src.element_size()) // 16
+        if n * 16 != src.numel() * src.element_size():
+            raise ValueError("input size is not a whole number of 16-byte blocks")
         if out is None:
             out = torch.empty((n, 16, 4), dtype=torch.uint8 if is_bc7 else torch.int16, device=src.device)
+        else:
+            _check_out(out, True, n * (64 if is_bc7 else 128), src.device, "uint8" if is_bc7 else "int16")
         stream = torch.cuda.current_stream(src.device).cuda_stream if src.is_cuda else None
         with torch.cuda.device(src.device if src.is_cuda else torch.cuda.current_device()):
             st = L.cvttb200_decode(f, src.data_ptr(), n, out.data_ptr(), stream)
     else:
         src = np.ascontiguousarray(pBC)
         n = (src.size * src.itemsize) // 16
+        if n * 16 != src.size * src.itemsize:
+            raise ValueError("input size is not a whole number of 16-byte blocks")
         if out is None:
             out = np.empty((n, 16, 4), dtype=np.uint8 if is_bc7 else np.int16)
+        else:
+            _check_out(out, False, n * (64 if is_bc7 else 128), None, "uint8" if is_bc7 else "int16")
         st = L.cvttb200_decode(f, src.ctypes.data, n, out.ctypes.data, None)
     _check(st)
     return out
@@ -394,6 +459,8 @@ def tile_image(image, out=None):
     n = tiled_block_count(w, h)
     if out is None:
         out = torch.empty((n, 16, 4), dtype=image.dtype, device=image.device)
+    else:
+        _check_out(out, True, n * 16 * pixel_bytes, image.device, str(image.dtype).replace("torch.", ""))
     L = _lib()
     L.cvttb200_tile_image.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     with torch.cuda.device(image.device):

@@ -230,7 +230,7 @@ namespace cvttb200
         return CVTTB200_OK;
     }
 
-    // caller holds g_mutex and has made ctx.device current
+    // caller holds ctx.planMutex and has made ctx.device current
     static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, const uint32_t **dCmds)
     {
         for (size_t i = 0; i < ctx.plans.size(); i++)
@@ -245,14 +245,29 @@ namespace cvttb200
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "BC7 plan needs more result slots than the kernel provides");
         if (ctx.plans.size() >= 16)
         {
+            // every launch that reads a cached plan was enqueued under planMutex, so after this synchronisation no kernel can
+            // still be reading the evicted command stream
+            CVTT_CUDA(cudaDeviceSynchronize());
             cudaFree(ctx.plans.front().dCmds);
             ctx.plans.erase(ctx.plans.begin());
         }
         PlanCacheEntry entry;
         entry.plan = plan;
         entry.dCmds = nullptr;
+        if (!ctx.setupStream)
+            CVTT_CUDA(cudaStreamCreateWithFlags(&ctx.setupStream, cudaStreamNonBlocking));
         CVTT_CUDA(cudaMalloc(&entry.dCmds, cmds.size() * sizeof(uint32_t)));
-        CVTT_CUDA(cudaMemcpy(entry.dCmds, cmds.data(), cmds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // The command stream must have LANDED in device memory before any stream may launch with it: a plain cudaMemcpy from
+        // pageable memory returns once the data is staged, and the caller's stream (possibly non-blocking) has no ordering
+        // with the copy.  `cmds` stays alive until the synchronisation.
+        cudaError_t e = cudaMemcpyAsync(entry.dCmds, cmds.data(), cmds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx.setupStream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(ctx.setupStream);
+        if (e != cudaSuccess)
+        {
+            cudaFree(entry.dCmds);
+            return fail_cuda(e, "upload of the compiled BC7 plan");
+        }
         ctx.plans.push_back(entry);
         *dCmds = entry.dCmds;
         return CVTTB200_OK;
@@ -265,6 +280,7 @@ namespace cvttb200
 
         BC7Params P;
         bc7_fill_params(P, options, plan, rcpN);
+        std::lock_guard<std::mutex> planLock(ctx.planMutex);      // until the launches below are enqueued (see the eviction above)
         const uint32_t *dCmds = nullptr;
         int rc = get_plan_commands(ctx, plan, &dCmds);
         if (rc != CVTTB200_OK)
@@ -274,7 +290,9 @@ namespace cvttb200
         // stream-ordered scratch for the group classification: counts[4] then lists[3][nGroups]
         const uint32_t nGroups = (uint32_t)(nBlocks / 8);
         uint32_t *dScratch = nullptr;
-        CVTT_CUDA(cudaMallocAsync((void **)&dScratch, (4 + 3 * (size_t)nGroups) * sizeof(uint32_t), stream));
+        rc = pool_alloc(ctx, (void **)&dScratch, (4 + 3 * (size_t)nGroups) * sizeof(uint32_t), stream);
+        if (rc != CVTTB200_OK)
+            return rc;
         CVTT_CUDA(cudaMemsetAsync(dScratch, 0, 4 * sizeof(uint32_t), stream));
         bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
         g_launches++;

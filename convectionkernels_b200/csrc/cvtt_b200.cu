@@ -178,14 +178,31 @@ namespace
 
 // =========================================================================================================
 // Host state
+//
+// Like the reference (README.md:57) the library may be called from any number of host threads at once.  What is shared:
+//   * the registry of per-device contexts and the reciprocal table        -> g_mutex, held for look-ups only
+//   * a context's BC7 plan cache                                           -> DeviceContext::planMutex (bc7_kernels.cu)
+//   * a context's pair of pipeline streams / its encode_multi stream       -> DeviceContext::pipeMutex / g_multiMutex
+// Everything a call needs on the device (staging buffers of host-pointer calls, kernel scratch) is allocated per call,
+// stream-ordered, from the context's private memory pool, so that calls on different streams overlap on the device and no
+// lock is held across a copy, a launch or a synchronisation.
 
 namespace
-{    thread_local std::string t_lastError;
+{
+    thread_local std::string t_lastError;
 
-    std::mutex g_mutex;
+    std::mutex g_mutex;                               // registry of contexts, reciprocal table
+    std::mutex g_multiMutex;                          // cvttb200_encode_multi calls take turns (each uses every listed device)
     std::deque<DeviceContext> g_contexts;             // references stay valid while contexts are added
     float g_rcpN[17];
     bool g_rcpOverridden = false, g_rcpReady = false;
+
+    // restores the calling thread's current device on every exit path
+    struct DeviceRestore
+    {
+        int prev = -1;
+        ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+    };
 }
 
 namespace cvttb200
@@ -203,6 +220,13 @@ namespace cvttb200
         return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? CVTTB200_ERR_NO_DEVICE : CVTTB200_ERR_CUDA,
                     std::string(what) + ": " + cudaGetErrorString(e));
     }
+
+    int pool_alloc(DeviceContext &ctx, void **p, size_t bytes, cudaStream_t stream)
+    {
+        *p = nullptr;
+        CVTT_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 16, ctx.pool, stream));
+        return CVTTB200_OK;
+    }
 }
 
 namespace
@@ -214,20 +238,8 @@ namespace
     }
 
     // caller holds g_mutex
-    int get_context(int device, DeviceContext **out)
+    int create_context(int device, DeviceContext **out)
     {
-        if (!g_rcpReady)
-        {
-            host_rcp_table(g_rcpN);
-            g_rcpReady = true;
-        }
-        for (size_t i = 0; i < g_contexts.size(); i++)
-            if (g_contexts[i].device == device && g_contexts[i].ready)
-            {
-                *out = &g_contexts[i];
-                return CVTTB200_OK;
-            }
-
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)
@@ -239,26 +251,33 @@ namespace
         if (prop.major != 10)
             return fail(CVTTB200_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100; this library contains sm_100a code only");
 
-        int prev = 0;
-        CVTT_CUDA(cudaGetDevice(&prev));
+        DeviceRestore restore;
+        CVTT_CUDA(cudaGetDevice(&restore.prev));
         CVTT_CUDA(cudaSetDevice(device));
+
+        // The library's own stream-ordered pool: staging buffers and kernel scratch are cached here between calls (release
+        // threshold = never) without changing the behaviour of the device's default pool, which the rest of the process uses.
+        cudaMemPool_t pool = nullptr;
         {
-            // scratch of the BC7 / ETC launches comes from the stream-ordered pool; keep it cached between calls instead of
-            // returning it to the driver at every synchronisation
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-            {
-                uint64_t threshold = ~(uint64_t)0;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-            }
-            cudaGetLastError();
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            CVTT_CUDA(cudaMemPoolCreate(&pool, &props));
+            uint64_t threshold = ~(uint64_t)0;
+            CVTT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
         }
         {
             int rc = bc7_device_setup();
             if (rc == CVTTB200_OK) rc = bc6h_device_setup();
             if (rc == CVTTB200_OK) rc = etc_device_setup();
             if (rc != CVTTB200_OK)
+            {
+                cudaMemPoolDestroy(pool);
                 return rc;
+            }
         }
         {
             DecodeTables dt;
@@ -267,14 +286,44 @@ namespace
             CVTT_CUDA(cudaMemcpyToSymbol(g_decodeTables, &dt, sizeof(dt)));
         }
         CVTT_CUDA(cudaDeviceSynchronize());
-        CVTT_CUDA(cudaSetDevice(prev));
 
         g_contexts.emplace_back();
-        g_contexts.back().numSMs = prop.multiProcessorCount;
-        g_contexts.back().device = device;
-        g_contexts.back().ready = true;
-        *out = &g_contexts.back();
+        DeviceContext &c = g_contexts.back();
+        c.numSMs = prop.multiProcessorCount;
+        c.device = device;
+        c.pool = pool;
+        c.ready = true;
+        *out = &c;
         return CVTTB200_OK;
+    }
+
+    // the context of `device`, created on first use; rcpN (may be null) receives a snapshot of the reciprocal table
+    int get_context(int device, DeviceContext **out, float *rcpN = nullptr)
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if (!g_rcpReady)
+        {
+            host_rcp_table(g_rcpN);
+            g_rcpReady = true;
+        }
+        if (rcpN)
+            memcpy(rcpN, g_rcpN, sizeof(g_rcpN));
+        for (size_t i = 0; i < g_contexts.size(); i++)
+            if (g_contexts[i].device == device && g_contexts[i].ready)
+            {
+                *out = &g_contexts[i];
+                return CVTTB200_OK;
+            }
+        return create_context(device, out);
+    }
+
+    int current_context(DeviceContext **out, float *rcpN = nullptr)
+    {
+        int device = 0;
+        const cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "cudaGetDevice");
+        return get_context(device, out, rcpN);
     }
 
     bool is_device_pointer(const void *p)
@@ -288,24 +337,51 @@ namespace
         return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
     }
 
-    int ensure_stage(void **buf, size_t *have, size_t need)
+    // a stream-ordered allocation from the context's pool that is returned (stream-ordered) when the scope ends
+    struct PoolBuffer
     {
-        if (*have >= need)
+        void *p = nullptr;
+        cudaStream_t stream = nullptr;
+        int alloc(DeviceContext &ctx, size_t bytes, cudaStream_t s)
+        {
+            stream = s;
+            return pool_alloc(ctx, &p, bytes, s);
+        }
+        ~PoolBuffer() { if (p) cudaFreeAsync(p, stream); }
+    };
+
+    // A call whose buffers are both host memory and that names no stream is complete when it returns and has no ordering
+    // with any device work of the caller, so it does not have to queue behind the legacy default stream: it borrows one of the
+    // context's non-blocking streams.  Unmodified multi-threaded callers of the reference interface then overlap on the device.
+    struct StreamLease
+    {
+        DeviceContext *ctx = nullptr;
+        cudaStream_t stream = nullptr;
+        int acquire(DeviceContext &c)
+        {
+            ctx = &c;
+            {
+                std::lock_guard<std::mutex> lock(c.streamMutex);
+                if (!c.idleStreams.empty())
+                {
+                    stream = c.idleStreams.back();
+                    c.idleStreams.pop_back();
+                    return CVTTB200_OK;
+                }
+            }
+            CVTT_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
             return CVTTB200_OK;
-        if (*buf)
-            cudaFree(*buf);
-        *buf = nullptr;
-        *have = 0;
-        CVTT_CUDA(cudaMalloc(buf, need));
-        *have = need;
-        return CVTTB200_OK;
-    }
+        }
+        ~StreamLease()
+        {
+            if (stream)
+            {
+                std::lock_guard<std::mutex> lock(ctx->streamMutex);
+                ctx->idleStreams.push_back(stream);
+            }
+        }
+    };
 
-}
-
-
-namespace
-{
     int launch_decode(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, cudaStream_t stream)
     {
         if (nBlocks > 0xffffff00u)
@@ -323,26 +399,52 @@ namespace
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
     }
-}
 
-namespace
-{
-    // format -> kernel launch; caller holds g_mutex and has made ctx.device current
-    int dispatch_encode(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const cvttb200_options *options, const cvttb200_bc7_plan *plan, cudaStream_t stream)
+    // what an encode call needs besides its buffers
+    struct EncodeRequest
     {
-        OptionsPOD opt;
-        memcpy(&opt, options, sizeof(opt));
+        int format;
+        OptionsPOD options;
+        OptionsPOD etc2AllocOptions;          // the Options AllocETC2Data was called with (chroma side axes, ETC.cpp:3117-3145)
+        BC7PlanPOD plan;
+        float rcpN[17];
+    };
+
+    // format -> kernel launch; the context's device is current
+    int dispatch_encode(DeviceContext &ctx, const EncodeRequest &rq, const void *dIn, size_t nBlocks, void *dOut, cudaStream_t stream)
+    {
+        const int format = rq.format;
         if (format == CVTTB200_BC7)
-        {
-            BC7PlanPOD planPOD;
-            memcpy(&planPOD, plan, sizeof(planPOD));
-            return launch_bc7(ctx, dIn, nBlocks, dOut, opt, planPOD, g_rcpN, stream);
-        }
+            return launch_bc7(ctx, dIn, nBlocks, dOut, rq.options, rq.plan, rq.rcpN, stream);
         if (format <= CVTTB200_BC5S)
-            return launch_s3tc(format, dIn, nBlocks, dOut, opt, g_rcpN, stream);
+            return launch_s3tc(format, dIn, nBlocks, dOut, rq.options, rq.rcpN, stream);
         if (format == CVTTB200_BC6HU || format == CVTTB200_BC6HS)
-            return launch_bc6h(dIn, nBlocks, dOut, opt, format == CVTTB200_BC6HS, g_rcpN, stream);
-        return launch_etc(ctx, format, dIn, nBlocks, dOut, opt, stream);
+            return launch_bc6h(dIn, nBlocks, dOut, rq.options, format == CVTTB200_BC6HS, rq.rcpN, stream);
+        return launch_etc(ctx, format, dIn, nBlocks, dOut, rq.options, rq.etc2AllocOptions, stream);
+    }
+
+    int check_encode_arguments(int format, const void *blocks, size_t nBlocks, const void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan)
+    {
+        if (!blocks || !out || !options)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
+        if (nBlocks % 8 != 0)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "nBlocks must be a multiple of 8 (cvtt::NumParallelBlocks)");
+        if (!cvttb200_input_block_bytes(format))
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
+        if (format == CVTTB200_BC7 && !plan)
+            return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
+        return CVTTB200_OK;
+    }
+
+    void fill_request(EncodeRequest &rq, int format, const cvttb200_options *options, const cvttb200_bc7_plan *plan, const cvttb200_options *etc2AllocOptions)
+    {
+        rq.format = format;
+        memcpy(&rq.options, options, sizeof(rq.options));
+        memcpy(&rq.etc2AllocOptions, etc2AllocOptions ? etc2AllocOptions : options, sizeof(rq.etc2AllocOptions));
+        if (plan)
+            memcpy(&rq.plan, plan, sizeof(rq.plan));
+        else
+            memset(&rq.plan, 0, sizeof(rq.plan));
     }
 }
 
@@ -354,18 +456,19 @@ extern "C"
 
 int cvttb200_init(int device)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
     DeviceContext *ctx = nullptr;
     return get_context(device, &ctx);
 }
 
 void cvttb200_shutdown(void)
 {
+    std::lock_guard<std::mutex> multi(g_multiMutex);
     std::lock_guard<std::mutex> lock(g_mutex);
-    int prev = 0;
-    if (cudaGetDevice(&prev) != cudaSuccess)
+    DeviceRestore restore;
+    if (cudaGetDevice(&restore.prev) != cudaSuccess)
     {
         cudaGetLastError();
+        restore.prev = -1;
         g_contexts.clear();
         return;
     }
@@ -374,16 +477,18 @@ void cvttb200_shutdown(void)
         DeviceContext &c = g_contexts[i];
         if (cudaSetDevice(c.device) != cudaSuccess)
             continue;
+        cudaDeviceSynchronize();
         for (size_t k = 0; k < c.plans.size(); k++)
             cudaFree(c.plans[k].dCmds);
-        if (c.stageIn) cudaFree(c.stageIn);
-        if (c.stageOut) cudaFree(c.stageOut);
+        if (c.setupStream) cudaStreamDestroy(c.setupStream);
         if (c.multiStream) cudaStreamDestroy(c.multiStream);
         for (int k = 0; k < 2; k++)
             if (c.pipeStream[k]) cudaStreamDestroy(c.pipeStream[k]);
+        for (size_t k = 0; k < c.idleStreams.size(); k++)
+            cudaStreamDestroy(c.idleStreams[k]);
+        if (c.pool) cudaMemPoolDestroy(c.pool);
     }
     g_contexts.clear();
-    cudaSetDevice(prev);
 }
 
 int cvttb200_set_rcp_table(const float *rcp17)
@@ -432,15 +537,8 @@ int cvttb200_tile_image(int pixelBytes, const void *image, int width, int height
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "bad image description");
     if (!is_device_pointer(image) || !is_device_pointer(blocks))
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_tile_image works on device memory");
-    std::lock_guard<std::mutex> lock(g_mutex);
-    int device = 0;
-    {
-        cudaError_t e = cudaGetDevice(&device);
-        if (e != cudaSuccess)
-            return fail_cuda(e, "cudaGetDevice");
-    }
     DeviceContext *ctx = nullptr;
-    int rc = get_context(device, &ctx);
+    int rc = current_context(&ctx);
     if (rc != CVTTB200_OK)
         return rc;
     const int blocksPerRow = ((width + 31) / 32) * 8;
@@ -465,7 +563,6 @@ int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t bl
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "bad arguments");
     if (!is_device_pointer(encoded) || !is_device_pointer(out))
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_untile_blocks works on device memory");
-    std::lock_guard<std::mutex> lock(g_mutex);
     const int blocksPerRow = ((width + 31) / 32) * 8, realBlocksPerRow = (width + 3) / 4;
     const int wordsPerBlock = (int)(blockBytes / 8);
     const uint64_t nWords = (uint64_t)((height + 3) / 4) * (uint64_t)realBlocksPerRow * (uint64_t)wordsPerBlock;
@@ -480,15 +577,8 @@ int cvttb200_selftest(uint64_t samples, uint64_t seed, uint64_t *mismatches)
 {
     if (!mismatches)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
-    std::lock_guard<std::mutex> lock(g_mutex);
-    int device = 0;
-    {
-        cudaError_t e = cudaGetDevice(&device);
-        if (e != cudaSuccess)
-            return fail_cuda(e, "cudaGetDevice");
-    }
     DeviceContext *ctx = nullptr;
-    int rc = get_context(device, &ctx);
+    int rc = current_context(&ctx);
     if (rc != CVTTB200_OK)
         return rc;
     return bc7_selftest_div(samples, seed, mismatches);
@@ -548,56 +638,31 @@ size_t cvttb200_output_block_bytes(int format)
     }
 }
 
-int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *streamPtr)
+int cvttb200_encode_ex(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan,
+                       const cvttb200_options *etc2AllocOptions, void *streamPtr)
 {
-    if (!blocks || !out || !options)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
-    if (nBlocks % 8 != 0)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "nBlocks must be a multiple of 8 (cvtt::NumParallelBlocks)");
-    const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
-    if (!inBytes)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
-    if (format == CVTTB200_BC7 && !plan)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
+    int rc = check_encode_arguments(format, blocks, nBlocks, out, options, plan);
+    if (rc != CVTTB200_OK)
+        return rc;
     if (nBlocks == 0)
         return CVTTB200_OK;
+    const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
 
-    std::lock_guard<std::mutex> lock(g_mutex);
-
-    int device = 0;
-    {
-        cudaError_t e = cudaGetDevice(&device);
-        if (e != cudaSuccess)
-            return fail_cuda(e, "cudaGetDevice");
-    }
+    EncodeRequest rq;
+    fill_request(rq, format, options, plan, etc2AllocOptions);
     DeviceContext *ctx = nullptr;
-    int rc = get_context(device, &ctx);
+    rc = current_context(&ctx, rq.rcpN);
     if (rc != CVTTB200_OK)
         return rc;
 
     cudaStream_t stream = (cudaStream_t)streamPtr;
     const bool inOnDevice = is_device_pointer(blocks), outOnDevice = is_device_pointer(out);
-    const void *dIn = blocks;
-    void *dOut = out;
+    if (inOnDevice && outOnDevice)
+        return dispatch_encode(*ctx, rq, blocks, nBlocks, out, stream);       // enqueued; no synchronisation
+
     const bool fastFormat = format <= CVTTB200_BC5S || format == CVTTB200_ETC2_ALPHA || format == CVTTB200_EAC_R11U || format == CVTTB200_EAC_R11S;
     const size_t kChunkBlocks = 131072;
     const bool pipelined = !inOnDevice && !outOnDevice && fastFormat && nBlocks >= 2 * kChunkBlocks;
-    if (!inOnDevice)
-    {
-        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, nBlocks * inBytes);
-        if (rc != CVTTB200_OK)
-            return rc;
-        if (!pipelined)
-            CVTT_CUDA(cudaMemcpyAsync(ctx->stageIn, blocks, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
-        dIn = ctx->stageIn;
-    }
-    if (!outOnDevice)
-    {
-        rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, nBlocks * outBytes);
-        if (rc != CVTTB200_OK)
-            return rc;
-        dOut = ctx->stageOut;
-    }
 
     // Host buffers in and out, and a format whose kernel is shorter than its PCIe transfers (BC1-BC5, EAC: >= 100 Mblocks/s on
     // the device): chunks of whole groups alternate between two streams, so that the copy-in of one chunk, the kernel of the
@@ -606,21 +671,38 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
     // chunked launches than the overlap returns, so they stay one launch.
     if (pipelined)
     {
+        std::lock_guard<std::mutex> pipe(ctx->pipeMutex);         // one pipelined call per device at a time: they are PCIe-bound
         for (int k = 0; k < 2; k++)
             if (!ctx->pipeStream[k])
                 CVTT_CUDA(cudaStreamCreateWithFlags(&ctx->pipeStream[k], cudaStreamNonBlocking));
-        CVTT_CUDA(cudaStreamSynchronize(stream));          // the staging buffers may still be in use by an earlier call on `stream`
+        PoolBuffer stageIn, stageOut;
+        rc = stageIn.alloc(*ctx, nBlocks * inBytes, ctx->pipeStream[0]);
+        if (rc == CVTTB200_OK)
+            rc = stageOut.alloc(*ctx, nBlocks * outBytes, ctx->pipeStream[0]);
+        if (rc != CVTTB200_OK)
+            return rc;
+        CVTT_CUDA(cudaStreamSynchronize(ctx->pipeStream[0]));     // the allocations are usable from the second stream as well
         int chunk = 0;
         for (size_t first = 0; first < nBlocks; first += kChunkBlocks, chunk++)
         {
             const size_t n = std::min(kChunkBlocks, nBlocks - first);
             cudaStream_t s = ctx->pipeStream[chunk & 1];
-            unsigned char *cIn = (unsigned char *)ctx->stageIn + first * inBytes, *cOut = (unsigned char *)ctx->stageOut + first * outBytes;
-            CVTT_CUDA(cudaMemcpyAsync(cIn, (const unsigned char *)blocks + first * inBytes, n * inBytes, cudaMemcpyHostToDevice, s));
-            rc = dispatch_encode(*ctx, format, cIn, n, cOut, options, plan, s);
+            unsigned char *cIn = (unsigned char *)stageIn.p + first * inBytes, *cOut = (unsigned char *)stageOut.p + first * outBytes;
+            cudaError_t e = cudaMemcpyAsync(cIn, (const unsigned char *)blocks + first * inBytes, n * inBytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess)
+            {
+                rc = fail_cuda(e, "cudaMemcpyAsync (host to device)");
+                break;
+            }
+            rc = dispatch_encode(*ctx, rq, cIn, n, cOut, s);
             if (rc != CVTTB200_OK)
                 break;
-            CVTT_CUDA(cudaMemcpyAsync((unsigned char *)out + first * outBytes, cOut, n * outBytes, cudaMemcpyDeviceToHost, s));
+            e = cudaMemcpyAsync((unsigned char *)out + first * outBytes, cOut, n * outBytes, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess)
+            {
+                rc = fail_cuda(e, "cudaMemcpyAsync (device to host)");
+                break;
+            }
         }
         for (int k = 0; k < 2; k++)
         {
@@ -628,36 +710,59 @@ int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, c
             if (e != cudaSuccess && rc == CVTTB200_OK)
                 rc = fail_cuda(e, "cudaStreamSynchronize");
         }
-        return rc;
+        return rc;          // the staging buffers go back to the pool on pipeStream[0], which is idle now
     }
 
-    rc = dispatch_encode(*ctx, format, dIn, nBlocks, dOut, options, plan, stream);
+    StreamLease lease;              // declared before the buffers: they are returned to the pool on this stream first
+    if (!inOnDevice && !outOnDevice && !stream)
+    {
+        rc = lease.acquire(*ctx);
+        if (rc != CVTTB200_OK)
+            return rc;
+        stream = lease.stream;
+    }
+    PoolBuffer stageIn, stageOut;
+    const void *dIn = blocks;
+    void *dOut = out;
+    if (!inOnDevice)
+    {
+        rc = stageIn.alloc(*ctx, nBlocks * inBytes, stream);
+        if (rc != CVTTB200_OK)
+            return rc;
+        CVTT_CUDA(cudaMemcpyAsync(stageIn.p, blocks, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
+        dIn = stageIn.p;
+    }
+    if (!outOnDevice)
+    {
+        rc = stageOut.alloc(*ctx, nBlocks * outBytes, stream);
+        if (rc != CVTTB200_OK)
+            return rc;
+        dOut = stageOut.p;
+    }
+    rc = dispatch_encode(*ctx, rq, dIn, nBlocks, dOut, stream);
     if (rc != CVTTB200_OK)
         return rc;
-
     if (!outOnDevice)
         CVTT_CUDA(cudaMemcpyAsync(out, dOut, nBlocks * outBytes, cudaMemcpyDeviceToHost, stream));
-    if (!inOnDevice || !outOnDevice)
-        CVTT_CUDA(cudaStreamSynchronize(stream));
+    CVTT_CUDA(cudaStreamSynchronize(stream));
     return CVTTB200_OK;
+}
+
+int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *streamPtr)
+{
+    return cvttb200_encode_ex(format, blocks, nBlocks, out, options, plan, nullptr, streamPtr);
 }
 
 int cvttb200_encode_multi(int format, const void *blocks, size_t nBlocks, void *out, const cvttb200_options *options, const cvttb200_bc7_plan *plan,
                           const int *devices, int nDevices)
 {
-    if (!blocks || !out || !options)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "null argument");
-    if (nBlocks % 8 != 0)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "nBlocks must be a multiple of 8 (cvtt::NumParallelBlocks)");
+    int rc = check_encode_arguments(format, blocks, nBlocks, out, options, plan);
+    if (rc != CVTTB200_OK)
+        return rc;
     const size_t inBytes = cvttb200_input_block_bytes(format), outBytes = cvttb200_output_block_bytes(format);
-    if (!inBytes)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "unknown format");
-    if (format == CVTTB200_BC7 && !plan)
-        return fail(CVTTB200_ERR_BAD_ARGUMENT, "CVTTB200_BC7 needs an encoding plan");
     if (is_device_pointer(blocks) || is_device_pointer(out))
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_encode_multi takes host buffers (use cvttb200_encode per device for device memory)");
 
-    std::lock_guard<std::mutex> lock(g_mutex);
     int count = 0;
     {
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -679,18 +784,33 @@ int cvttb200_encode_multi(int format, const void *blocks, size_t nBlocks, void *
     if (nBlocks == 0)
         return CVTTB200_OK;
 
-    int prev = 0;
-    CVTT_CUDA(cudaGetDevice(&prev));
+    std::lock_guard<std::mutex> multi(g_multiMutex);
+    DeviceRestore restore;
+    CVTT_CUDA(cudaGetDevice(&restore.prev));
 
-    // Contiguous ranges of whole 8-block groups (a group is one reference call and is never split); every device copies its
-    // range in, encodes it and copies the result back on its own stream, then all streams are joined.
+    EncodeRequest rq;
+    fill_request(rq, format, options, plan, nullptr);
+
+    // Contiguous ranges of whole 8-block groups (a group is one reference call and is never split).  Two passes, so that the
+    // devices work at the same time whatever kind of host memory the caller has: a copy to or from PAGEABLE memory only
+    // returns when its data has moved, so a copy-out issued right behind a device's kernel would hold the loop until that
+    // kernel is done, and the next device would not even have started.  Pass 1 gives every device its input and its kernel;
+    // pass 2 collects the results (the copy-out of device i waits for kernel i while the other kernels keep running).
+    struct Part
+    {
+        DeviceContext *ctx;
+        size_t first, n;
+        void *dIn, *dOut;
+    };
+    std::vector<Part> parts;
     const size_t nGroups = nBlocks / 8;
-    std::vector<DeviceContext *> used;
-    int rc = CVTTB200_OK;
     for (int i = 0; i < nDevices && rc == CVTTB200_OK; i++)
     {
-        const size_t first = nGroups * (size_t)i / (size_t)nDevices * 8, end = nGroups * (size_t)(i + 1) / (size_t)nDevices * 8, n = end - first;
-        if (n == 0)
+        Part part;
+        part.first = nGroups * (size_t)i / (size_t)nDevices * 8;
+        part.n = nGroups * (size_t)(i + 1) / (size_t)nDevices * 8 - part.first;
+        part.dIn = part.dOut = nullptr;
+        if (part.n == 0)
             continue;
         cudaError_t e = cudaSetDevice(ids[(size_t)i]);
         if (e != cudaSuccess)
@@ -698,40 +818,44 @@ int cvttb200_encode_multi(int format, const void *blocks, size_t nBlocks, void *
             rc = fail_cuda(e, "cudaSetDevice");
             break;
         }
-        DeviceContext *ctx = nullptr;
-        rc = get_context(ids[(size_t)i], &ctx);
+        rc = get_context(ids[(size_t)i], &part.ctx, rq.rcpN);
         if (rc != CVTTB200_OK)
             break;
+        DeviceContext *ctx = part.ctx;
         if (!ctx->multiStream && (e = cudaStreamCreateWithFlags(&ctx->multiStream, cudaStreamNonBlocking)) != cudaSuccess)
         {
             rc = fail_cuda(e, "cudaStreamCreateWithFlags");
             break;
         }
-        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, n * inBytes);
+        rc = pool_alloc(*ctx, &part.dIn, part.n * inBytes, ctx->multiStream);
         if (rc == CVTTB200_OK)
-            rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, n * outBytes);
+            rc = pool_alloc(*ctx, &part.dOut, part.n * outBytes, ctx->multiStream);
+        parts.push_back(part);                  // from here on the buffers are released below
         if (rc != CVTTB200_OK)
             break;
-        used.push_back(ctx);
-        if ((e = cudaMemcpyAsync(ctx->stageIn, (const unsigned char *)blocks + first * inBytes, n * inBytes, cudaMemcpyHostToDevice, ctx->multiStream)) != cudaSuccess)
+        if ((e = cudaMemcpyAsync(part.dIn, (const unsigned char *)blocks + part.first * inBytes, part.n * inBytes, cudaMemcpyHostToDevice, ctx->multiStream)) != cudaSuccess)
         {
             rc = fail_cuda(e, "cudaMemcpyAsync (host to device)");
             break;
         }
-        rc = dispatch_encode(*ctx, format, ctx->stageIn, n, ctx->stageOut, options, plan, ctx->multiStream);
-        if (rc != CVTTB200_OK)
-            break;
-        if ((e = cudaMemcpyAsync((unsigned char *)out + first * outBytes, ctx->stageOut, n * outBytes, cudaMemcpyDeviceToHost, ctx->multiStream)) != cudaSuccess)
+        rc = dispatch_encode(*ctx, rq, part.dIn, part.n, part.dOut, ctx->multiStream);
+    }
+    for (size_t k = 0; k < parts.size() && rc == CVTTB200_OK; k++)
+    {
+        cudaSetDevice(parts[k].ctx->device);
+        const cudaError_t e = cudaMemcpyAsync((unsigned char *)out + parts[k].first * outBytes, parts[k].dOut, parts[k].n * outBytes, cudaMemcpyDeviceToHost, parts[k].ctx->multiStream);
+        if (e != cudaSuccess)
             rc = fail_cuda(e, "cudaMemcpyAsync (device to host)");
     }
-    for (size_t k = 0; k < used.size(); k++)
+    for (size_t k = 0; k < parts.size(); k++)
     {
-        cudaSetDevice(used[k]->device);
-        const cudaError_t e = cudaStreamSynchronize(used[k]->multiStream);
+        cudaSetDevice(parts[k].ctx->device);
+        const cudaError_t e = cudaStreamSynchronize(parts[k].ctx->multiStream);
         if (e != cudaSuccess && rc == CVTTB200_OK)
             rc = fail_cuda(e, "cudaStreamSynchronize");
+        if (parts[k].dIn) cudaFreeAsync(parts[k].dIn, parts[k].ctx->multiStream);
+        if (parts[k].dOut) cudaFreeAsync(parts[k].dOut, parts[k].ctx->multiStream);
     }
-    cudaSetDevice(prev);
     return rc;
 }
 
@@ -745,36 +869,38 @@ int cvttb200_decode(int format, const void *encoded, size_t nBlocks, void *pixel
         return CVTTB200_OK;
     const size_t inBytes = 16, outBytes = cvttb200_input_block_bytes(format);      // a decoded block is the encoder's input block
 
-    std::lock_guard<std::mutex> lock(g_mutex);
-    int device = 0;
-    {
-        cudaError_t e = cudaGetDevice(&device);
-        if (e != cudaSuccess)
-            return fail_cuda(e, "cudaGetDevice");
-    }
     DeviceContext *ctx = nullptr;
-    int rc = get_context(device, &ctx);
+    int rc = current_context(&ctx);
     if (rc != CVTTB200_OK)
         return rc;
 
     cudaStream_t stream = (cudaStream_t)streamPtr;
     const bool inOnDevice = is_device_pointer(encoded), outOnDevice = is_device_pointer(pixelBlocks);
+    StreamLease lease;
+    if (!inOnDevice && !outOnDevice && !stream)
+    {
+        rc = lease.acquire(*ctx);
+        if (rc != CVTTB200_OK)
+            return rc;
+        stream = lease.stream;
+    }
+    PoolBuffer stageIn, stageOut;
     const void *dIn = encoded;
     void *dOut = pixelBlocks;
     if (!inOnDevice)
     {
-        rc = ensure_stage(&ctx->stageIn, &ctx->stageInBytes, nBlocks * inBytes);
+        rc = stageIn.alloc(*ctx, nBlocks * inBytes, stream);
         if (rc != CVTTB200_OK)
             return rc;
-        CVTT_CUDA(cudaMemcpyAsync(ctx->stageIn, encoded, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
-        dIn = ctx->stageIn;
+        CVTT_CUDA(cudaMemcpyAsync(stageIn.p, encoded, nBlocks * inBytes, cudaMemcpyHostToDevice, stream));
+        dIn = stageIn.p;
     }
     if (!outOnDevice)
     {
-        rc = ensure_stage(&ctx->stageOut, &ctx->stageOutBytes, nBlocks * outBytes);
+        rc = stageOut.alloc(*ctx, nBlocks * outBytes, stream);
         if (rc != CVTTB200_OK)
             return rc;
-        dOut = ctx->stageOut;
+        dOut = stageOut.p;
     }
     rc = launch_decode(*ctx, format, dIn, nBlocks, dOut, stream);
     if (rc != CVTTB200_OK)

@@ -9,7 +9,7 @@
 
 namespace cvttb200
 {
-    void etc_fill_params(ETCParams &P, const OptionsPOD &options)
+    void etc_fill_params(ETCParams &P, const OptionsPOD &options, const OptionsPOD &allocOptions)
     {
         memset(&P, 0, sizeof(P));
         P.flags = options.flags;
@@ -25,8 +25,9 @@ namespace cvttb200
             P.wSq[ch] = cd[ch] * cd[ch];
         }
 
-        // ETC2CompressionDataInternal::ETC2CompressionDataInternal, ETC.cpp:3117-3145
+        // ETC2CompressionDataInternal::ETC2CompressionDataInternal, ETC.cpp:3117-3145: from the allocation-time weights
         {
+            const float cd[3] = { allocOptions.redWeight, allocOptions.greenWeight, allocOptions.blueWeight };
             const float rotCD[3] = { cd[1], cd[2], cd[0] };
             const float offs = -(rotCD[0] * cd[0] + rotCD[1] * cd[1] + rotCD[2] * cd[2]) / (cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2]);
             const float chromaAxis0[3] = { rotCD[0] + cd[0] * offs, rotCD[1] + cd[1] * offs, rotCD[2] + cd[2] * offs };

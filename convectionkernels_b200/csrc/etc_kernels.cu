@@ -196,7 +196,11 @@ namespace cvttb200
         const unsigned grid = (unsigned)std::min(maxCtas, (nBlocks + kETCThreads - 1) / kETCThreads);
         const size_t threads = (size_t)grid * kETCThreads;
         void *dScratch = nullptr;
-        CVTT_CUDA(cudaMallocAsync(&dScratch, etc_scratch_bytes(threads), stream));
+        {
+            const int rc = pool_alloc(ctx, &dScratch, etc_scratch_bytes(threads), stream);
+            if (rc != CVTTB200_OK)
+                return rc;
+        }
         ETCScratch S;
         etc_scratch_layout(S, dScratch, threads);
         const uint4 *in = (const uint4 *)dIn;
@@ -218,7 +222,7 @@ namespace cvttb200
         return CVTTB200_OK;
     }
 
-    int launch_etc(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, cudaStream_t stream)
+    int launch_etc(DeviceContext &ctx, int format, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, const OptionsPOD &allocOptions, cudaStream_t stream)
     {
         if (nBlocks > 0xffffff00u)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "too many blocks for one call");
@@ -236,7 +240,7 @@ namespace cvttb200
             return CVTTB200_OK;
         }
         ETCParams P;
-        etc_fill_params(P, options);
+        etc_fill_params(P, options, allocOptions);
         const bool uniform = (options.flags & kFlag_Uniform) != 0, bt709 = (options.flags & kFlag_ETC_UseFakeBT709) != 0;
         switch (format)
         {

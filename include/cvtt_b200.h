@@ -176,10 +176,23 @@ int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t bl
  * device memory of the current CUDA device; the kind is detected per pointer.  With device pointers the work is
  * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns without synchronising; if
  * either pointer is host memory the call copies through device staging buffers and returns when `out` is
- * complete.  `plan` is required for CVTTB200_BC7 and ignored otherwise.
+ * complete (both pointers host memory and stream == NULL: the work runs on a stream of the library's own instead of
+ * queueing behind the default stream, so that such calls from several host threads overlap on the device).  `plan` is required for CVTTB200_BC7 and ignored otherwise.
+ * Thread safety: like the reference (README.md:57) every entry point may be called from any number of host threads at once;
+ * calls on different streams overlap on the device (staging buffers and kernel scratch are per call).
  * Returns a cvttb200_status. */
 int cvttb200_encode(int format, const void *blocks, size_t nBlocks, void *out,
                     const cvttb200_options *options, const cvttb200_bc7_plan *plan, void *stream);
+
+/* cvttb200_encode with the second Options object the reference's ETC2 entry points see: cvtt::Kernels::AllocETC2Data(alloc,
+ * context, options) (ConvectionKernels.h:268, ConvectionKernels_ETC.cpp:3117-3145) derives the chroma side axes of the T/H-mode
+ * search from THOSE options once, and EncodeETC2 / EncodeETC2RGBA / EncodeETC2PunchthroughAlpha read them from the
+ * ETC2CompressionData (ETC.cpp:1773) while taking flags and error weights from their own `options` argument.
+ * etc2AllocOptions = the Options given to AllocETC2Data; NULL means "the same as options" (what cvttb200_encode does).  Ignored
+ * by every other format. */
+int cvttb200_encode_ex(int format, const void *blocks, size_t nBlocks, void *out,
+                       const cvttb200_options *options, const cvttb200_bc7_plan *plan,
+                       const cvttb200_options *etc2AllocOptions, void *stream);
 
 /* The same call over several GPUs of this process (the reference itself is single threaded and leaves
  * parallelism to its caller, README.md:57).  `blocks` and `out` are HOST buffers.  The blocks are split into nDevices contiguous

@@ -62,6 +62,8 @@ namespace cvtt
     // The reference's ETC compression data is CPU scratch memory (ConvectionKernels_ETC.h:36-78).  The device equivalent is
     // allocated by the library per call, so these objects only keep the reference's allocation protocol alive: Alloc* calls
     // allocFunc(context, size) once and returns the pointer, Release* hands it back to freeFunc(context, ptr, size).
+    // ETC2CompressionData also carries the Options given to AllocETC2Data: the reference derives the chroma side axes of the
+    // T / H search from them at allocation time (ConvectionKernels_ETC.cpp:3117-3145), not from the per-call options.
     class ETC2CompressionData
     {
     public:
@@ -98,6 +100,17 @@ namespace cvtt
                 Check(cvttb200_encode(format, pBlocks, numBlocks, pBC, &options, encodingPlan, cudaStream), "Encode");
             }
 
+            // ETC2 colour formats: compressionData carries the allocation-time options (must not be NULL, as in the reference)
+            inline void EncodeETC2Family(int format, uint8_t *pBC, const void *pBlocks, size_t numBlocks, const Options &options, const ETC2CompressionData *compressionData, void *cudaStream = NULL)
+            {
+                if (!compressionData)
+                {
+                    fprintf(stderr, "cvtt (B200): ETC2 encode called without ETC2CompressionData (AllocETC2Data)\n");
+                    abort();
+                }
+                Check(cvttb200_encode_ex(format, pBlocks, numBlocks, pBC, &options, NULL, &compressionData->m_options, cudaStream), "EncodeETC2");
+            }
+
             inline void EncodeBC7(uint8_t *pBC, const PixelBlockU8 *pBlocks, size_t numBlocks, const Options &options, const BC7EncodingPlan &encodingPlan, void *cudaStream = NULL)
             {
                 Check(cvttb200_encode(CVTTB200_BC7, pBlocks, numBlocks, pBC, &options, &encodingPlan, cudaStream), "EncodeBC7");
@@ -125,9 +138,9 @@ namespace cvtt
             B200::EncodeBC7(pBC, pBlocks, NumParallelBlocks, options, encodingPlan);
         }
         inline void EncodeETC1(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC1CompressionData *) { B200::Encode(CVTTB200_ETC1, pBC, pBlocks, NumParallelBlocks, options); }
-        inline void EncodeETC2(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2, pBC, pBlocks, NumParallelBlocks, options); }
-        inline void EncodeETC2RGBA(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2_RGBA, pBC, pBlocks, NumParallelBlocks, options); }
-        inline void EncodeETC2PunchthroughAlpha(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *) { B200::Encode(CVTTB200_ETC2_PUNCHTHROUGH, pBC, pBlocks, NumParallelBlocks, options); }
+        inline void EncodeETC2(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *compressionData) { B200::EncodeETC2Family(CVTTB200_ETC2, pBC, pBlocks, NumParallelBlocks, options, compressionData); }
+        inline void EncodeETC2RGBA(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *compressionData) { B200::EncodeETC2Family(CVTTB200_ETC2_RGBA, pBC, pBlocks, NumParallelBlocks, options, compressionData); }
+        inline void EncodeETC2PunchthroughAlpha(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options, ETC2CompressionData *compressionData) { B200::EncodeETC2Family(CVTTB200_ETC2_PUNCHTHROUGH, pBC, pBlocks, NumParallelBlocks, options, compressionData); }
         inline void EncodeETC2Alpha(uint8_t *pBC, const PixelBlockU8 *pBlocks, const Options &options) { B200::Encode(CVTTB200_ETC2_ALPHA, pBC, pBlocks, NumParallelBlocks, options); }
         inline void EncodeETC2Alpha11(uint8_t *pBC, const PixelBlockScalarS16 *pBlocks, bool isSigned, const Options &options)
         {

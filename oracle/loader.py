@@ -45,6 +45,7 @@ class Reference:
         for f in ("cvttref_sizeof_options", "cvttref_sizeof_plan", "cvttref_sizeof_finetune"):
             getattr(L, f).restype = ctypes.c_size_t
         L.cvttref_encode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.cvttref_encode_alloc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.cvttref_decode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.cvttref_rcp.restype = ctypes.c_float
         L.cvttref_rcp.argtypes = [ctypes.c_float]
@@ -73,15 +74,17 @@ class Reference:
         self.lib.cvttref_plan_from_finetune(buf.ctypes.data_as(ctypes.c_void_p), ft.ctypes.data_as(ctypes.c_void_p))
         return buf
 
-    def encode(self, fmt, blocks, options, plan=None, threads=1):
+    def encode(self, fmt, blocks, options, plan=None, threads=1, etc2_alloc_options=None):
+        """etc2_alloc_options: the Options AllocETC2Data is called with (default: the same as `options`)"""
         src = _as_u8(blocks)
         n = src.size // IN_BYTES[fmt]
         assert n * IN_BYTES[fmt] == src.size and n % 8 == 0
         out = np.zeros((n, OUT_BYTES[fmt]), dtype=np.uint8)
         options = np.ascontiguousarray(options, dtype=np.uint8)
         pp = None if plan is None else np.ascontiguousarray(plan, dtype=np.uint8).ctypes.data_as(ctypes.c_void_p)
-        rc = self.lib.cvttref_encode(FMT[fmt], src.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p),
-                                     options.ctypes.data_as(ctypes.c_void_p), pp, int(threads))
+        alloc = options if etc2_alloc_options is None else np.ascontiguousarray(etc2_alloc_options, dtype=np.uint8)
+        rc = self.lib.cvttref_encode_alloc(FMT[fmt], src.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p),
+                                           options.ctypes.data_as(ctypes.c_void_p), pp, alloc.ctypes.data_as(ctypes.c_void_p), int(threads))
         if rc != 0:
             raise ValueError("cvttref_encode rc=%d" % rc)
         return out

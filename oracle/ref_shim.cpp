@@ -60,7 +60,8 @@ namespace
 
     void FreeShim(void *, void *ptr, size_t) { free(ptr); }
 
-    void EncodeRange(int fmt, const uint8_t *in, size_t firstGroup, size_t lastGroup, uint8_t *out, const cvtt::Options &opt, const cvtt::BC7EncodingPlan *plan)
+    // allocOpt: the Options handed to AllocETC2Data (the reference keeps the chroma side axes derived from them)
+    void EncodeRange(int fmt, const uint8_t *in, size_t firstGroup, size_t lastGroup, uint8_t *out, const cvtt::Options &opt, const cvtt::BC7EncodingPlan *plan, const cvtt::Options &allocOpt)
     {
         using namespace cvtt;
         const size_t ib = InBytes(fmt) * 8, ob = OutBytes(fmt) * 8;
@@ -69,7 +70,7 @@ namespace
         if (fmt == F_ETC1)
             etc1 = Kernels::AllocETC1Data(AllocShim, NULL);
         if (fmt == F_ETC2 || fmt == F_ETC2_RGBA || fmt == F_ETC2_PUNCHTHROUGH)
-            etc2 = Kernels::AllocETC2Data(AllocShim, NULL, opt);
+            etc2 = Kernels::AllocETC2Data(AllocShim, NULL, allocOpt);
 
         for (size_t g = firstGroup; g < lastGroup; g++)
         {
@@ -127,17 +128,26 @@ extern "C"
 
     // Encodes nBlocks (multiple of 8) blocks with nThreads host threads; each thread owns a
     // contiguous range of 8-block groups.  Returns 0, or -1 on a bad argument.
+    int cvttref_encode_alloc(int fmt, const void *blocks, size_t nBlocks, void *out, const void *options, const void *plan, const void *etc2AllocOptions, int nThreads);
+
     int cvttref_encode(int fmt, const void *blocks, size_t nBlocks, void *out, const void *options, const void *plan, int nThreads)
     {
-        if (!blocks || !out || !options || (nBlocks % cvtt::NumParallelBlocks) != 0)
+        return cvttref_encode_alloc(fmt, blocks, nBlocks, out, options, plan, options, nThreads);
+    }
+
+    // The same with AllocETC2Data receiving its own Options (etc2AllocOptions), as a caller of the reference may do.
+    int cvttref_encode_alloc(int fmt, const void *blocks, size_t nBlocks, void *out, const void *options, const void *plan, const void *etc2AllocOptions, int nThreads)
+    {
+        if (!blocks || !out || !options || !etc2AllocOptions || (nBlocks % cvtt::NumParallelBlocks) != 0)
             return -1;
         if (fmt == F_BC7 && !plan)
             return -1;
         if (fmt < F_BC1 || fmt > F_EAC_R11S)
             return -1;
 
-        cvtt::Options opt;
+        cvtt::Options opt, allocOpt;
         memcpy(&opt, options, sizeof(opt));
+        memcpy(&allocOpt, etc2AllocOptions, sizeof(allocOpt));
         const cvtt::BC7EncodingPlan *p = static_cast<const cvtt::BC7EncodingPlan*>(plan);
 
         const size_t nGroups = nBlocks / cvtt::NumParallelBlocks;
@@ -151,7 +161,7 @@ extern "C"
 
         if (nThreads == 1)
         {
-            EncodeRange(fmt, in, 0, nGroups, dst, opt, p);
+            EncodeRange(fmt, in, 0, nGroups, dst, opt, p, allocOpt);
             return 0;
         }
 
@@ -160,7 +170,7 @@ extern "C"
         {
             size_t first = nGroups * t / nThreads;
             size_t last = nGroups * (t + 1) / nThreads;
-            threads.emplace_back(EncodeRange, fmt, in, first, last, dst, opt, p);
+            threads.emplace_back(EncodeRange, fmt, in, first, last, dst, opt, p, allocOpt);
         }
         for (size_t t = 0; t < threads.size(); t++)
             threads[t].join();

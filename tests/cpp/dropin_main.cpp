@@ -2,6 +2,7 @@
 // call and encodes them with cvtt::Kernels::EncodeBC7, then encodes the same image with the whole-image entry point and
 // checks both agree.  Prints a 64-bit FNV hash of the output so a harness can compare it with the oracle's.
 // usage: dropin_main <width> <height> <quality>
+#include <thread>
 #include <vector>
 #include <stdint.h>
 #include <string.h>
@@ -66,6 +67,40 @@ int main(int argc, char **argv)
         for (size_t i = 0; i < b.size(); i++)
             h2 = (h2 ^ b[i]) * 1099511628211ull;
         printf("BC3 fnv64 %016llx\n", (unsigned long long)h2);
+
+        // AllocETC2Data with options of its own (the chroma side axes come from these), EncodeETC2 with others
+        cvtt::Options encOptions, allocOptions;
+        encOptions.redWeight = 1.0f; encOptions.greenWeight = 0.5f; encOptions.blueWeight = 0.25f;
+        allocOptions.redWeight = 0.1f; allocOptions.greenWeight = 1.0f; allocOptions.blueWeight = 0.7f;
+        cvtt::ETC2CompressionData *etc2b = cvtt::Kernels::AllocETC2Data(*allocShim, NULL, allocOptions);
+        std::vector<uint8_t> c(blocks.size() * 8);
+        for (size_t i = 0; i < blocks.size(); i += cvtt::NumParallelBlocks)
+            cvtt::Kernels::EncodeETC2(&c[i * 8], &blocks[i], encOptions, etc2b);
+        cvtt::Kernels::ReleaseETC2Data(etc2b, *freeShim);
+        uint64_t h3 = 1469598103934665603ull;
+        for (size_t i = 0; i < c.size(); i++)
+            h3 = (h3 ^ c[i]) * 1099511628211ull;
+        printf("ETC2 alloc-options fnv64 %016llx\n", (unsigned long long)h3);
+    }
+    // the reference may be called from any number of threads (README.md:57): four threads encode quarters of the image with
+    // 8-block calls at the same time
+    {
+        std::vector<uint8_t> threaded(blocks.size() * 16);
+        std::vector<std::thread> pool;
+        const size_t groups = blocks.size() / cvtt::NumParallelBlocks;
+        for (int t = 0; t < 4; t++)
+            pool.emplace_back([&, t]() {
+                for (size_t g = groups * t / 4; g < groups * (t + 1) / 4; g++)
+                    cvtt::Kernels::EncodeBC7(&threaded[g * 8 * 16], &blocks[g * 8], options, plan);
+            });
+        for (size_t t = 0; t < pool.size(); t++)
+            pool[t].join();
+        if (memcmp(threaded.data(), whole.data(), whole.size()) != 0)
+        {
+            fprintf(stderr, "four caller threads disagree with the whole-image call\n");
+            return 5;
+        }
+        printf("4 caller threads OK\n");
     }
 
     uint64_t hash = 1469598103934665603ull;

@@ -117,12 +117,20 @@ namespace
     }
 }
 
+extern "C" int hostsim_encode_etc_alloc(int kind, const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const OptionsPOD *allocOptions);
+
 extern "C" int hostsim_encode_etc(int kind, const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options)
+{
+    return hostsim_encode_etc_alloc(kind, blocks, nBlocks, out, options, options);
+}
+
+// allocOptions: what the caller's AllocETC2Data received (chroma side axes)
+extern "C" int hostsim_encode_etc_alloc(int kind, const uint8_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, const OptionsPOD *allocOptions)
 {
     if (nBlocks % 8)
         return -1;
     ETCParams P;
-    etc_fill_params(P, *options);
+    etc_fill_params(P, *options, *allocOptions);
     GroupShared shared;
     std::vector<std::thread> threads;
     for (int lane = 0; lane < 8; lane++)

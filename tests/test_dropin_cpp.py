@@ -16,7 +16,7 @@ def _build():
     os.makedirs(os.path.dirname(out), exist_ok=True)
     libdir = os.path.dirname(api.library_path())
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"),
-                           "-o", out, "-L", libdir, "-lcvtt_b200", "-Wl,-rpath," + libdir])
+                           "-o", out, "-L", libdir, "-lcvtt_b200", "-Wl,-rpath," + libdir, "-pthread"])
     return out
 
 
@@ -53,5 +53,12 @@ def test_dropin_matches_oracle(oracle):
     assert "%d blocks, fnv64 %016x" % (len(blocks), _fnv64(want)) in r.stdout, r.stdout
     from oracle import loader
     if os.path.exists(loader.REF_SO):
-        ref = loader.Reference().encode("BC3", blocks, opt)
+        R = loader.Reference()
+        ref = R.encode("BC3", blocks, opt)
         assert "BC3 fnv64 %016x" % _fnv64(ref) in r.stdout, r.stdout
+        enc, alloc = api.Options(), api.Options()
+        enc.redWeight, enc.greenWeight, enc.blueWeight = 1.0, 0.5, 0.25
+        alloc.redWeight, alloc.greenWeight, alloc.blueWeight = 0.1, 1.0, 0.7
+        ref = R.encode("ETC2", blocks, np.frombuffer(bytes(memoryview(enc)), np.uint8), etc2_alloc_options=np.frombuffer(bytes(memoryview(alloc)), np.uint8))
+        assert "ETC2 alloc-options fnv64 %016x" % _fnv64(ref) in r.stdout, r.stdout
+    assert "4 caller threads OK" in r.stdout, r.stdout

@@ -55,6 +55,24 @@ def test_weights_and_image_content_against_reference(reference):
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("fmt", ["ETC2", "ETC2_RGBA", "ETC2_PUNCHTHROUGH"])
+def test_alloc_time_options(reference, fmt):
+    """cvtt::Kernels::AllocETC2Data fixes the chroma side axes from ITS options (ETC.cpp:3117-3145); the encode call's options
+    give flags and error weights.  Different options at the two places, through the reference-name mirror."""
+    blocks = synth.random_blocks_rgba8(2048, seed=41) if fmt != "ETC2_PUNCHTHROUGH" else synth.punchthrough_blocks_rgba8(2048, seed=5)
+    enc, alloc = api.Options(), api.Options()
+    enc.redWeight, enc.greenWeight, enc.blueWeight = 1.0, 0.5, 0.25
+    alloc.redWeight, alloc.greenWeight, alloc.blueWeight = 0.1, 1.0, 0.7
+    want = reference.encode(fmt, blocks, _opt_bytes(enc), threads=0, etc2_alloc_options=_opt_bytes(alloc))
+    data = api.AllocETC2Data(alloc)
+    call = {"ETC2": api.EncodeETC2, "ETC2_RGBA": api.EncodeETC2RGBA, "ETC2_PUNCHTHROUGH": api.EncodeETC2PunchthroughAlpha}[fmt]
+    got = call(blocks, enc, data)
+    api.ReleaseETC2Data(data)
+    assert (got == want).all(), first_mismatch(want, got)
+    if fmt == "ETC2":
+        assert (want != reference.encode(fmt, blocks, _opt_bytes(enc), threads=0)).any()       # the test has teeth
+
+
 def test_ultra_preset_is_accepted(reference):
     """Flags::Ultra carries ETC_FakeBT709Accurate without ETC_UseFakeBT709: the bit has no effect on its own"""
     blocks = synth.random_blocks_rgba8(1024, seed=3)

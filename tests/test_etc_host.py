@@ -22,6 +22,7 @@ def hostsim_etc():
                            os.path.join(ROOT, "tests", "hostsim", "hostsim_etc.cpp"), os.path.join(csrc, "etc_host.cpp")])
     H = ctypes.CDLL(out)
     H.hostsim_encode_etc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    H.hostsim_encode_etc_alloc.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return H
 
 
@@ -35,6 +36,23 @@ def test_etc_device_logic_on_cpu_matches_golden(hostsim_etc, name):
     rc = hostsim_etc.hostsim_encode_etc(KIND[str(g["fmt"])], blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data)
     assert rc == 0
     assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)
+
+
+def test_alloc_time_options_fix_the_chroma_axes(hostsim_etc, reference):
+    """AllocETC2Data(options) derives the chroma side axes of the T / H search (ETC.cpp:3117-3145); EncodeETC2 takes flags and
+    error weights from its own options (ETC.cpp:1773).  A caller that passes different weights to the two must get the
+    reference's bytes -- which differ from both 'same options' encodings."""
+    from convectionkernels_b200 import api, synth
+    blocks = synth.random_blocks_rgba8(256, seed=41)
+    enc, alloc = api.Options(), api.Options()
+    enc.redWeight, enc.greenWeight, enc.blueWeight = 1.0, 0.5, 0.25
+    alloc.redWeight, alloc.greenWeight, alloc.blueWeight = 0.1, 1.0, 0.7
+    eb, ab = (np.frombuffer(bytes(memoryview(o)), np.uint8).copy() for o in (enc, alloc))
+    want = reference.encode("ETC2", blocks, eb, etc2_alloc_options=ab)
+    assert (want != reference.encode("ETC2", blocks, eb)).any() and (want != reference.encode("ETC2", blocks, ab)).any()
+    out = np.zeros_like(want)
+    assert hostsim_etc.hostsim_encode_etc_alloc(1, blocks.ctypes.data, len(blocks), out.ctypes.data, eb.ctypes.data, ab.ctypes.data) == 0
+    assert (out == want).all(), first_mismatch(want, out)
 
 
 def test_t_mode_group_coupling(hostsim_etc, reference):

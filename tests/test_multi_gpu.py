@@ -44,3 +44,32 @@ def test_encode_multi_argument_errors():
     with pytest.raises(Exception):
         api.encode_multi("BC7", blocks, opt, None, devices=[0])        # BC7 needs a plan
     assert api.encode_multi("BC1", blocks[:0], opt).shape == (0, 8)
+
+
+def test_encode_multi_overlaps_devices_with_pageable_buffers():
+    """Ordinary (pageable) numpy buffers: a copy from or to pageable memory only returns when its data has moved, so the call
+    enqueues every device's input and kernel before it collects any result.  With two devices the call must take clearly less
+    than the one-device call."""
+    import time
+    count = _device_count()
+    if count < 2:
+        pytest.skip("needs two GPUs")
+    for d in range(2):
+        api.init(d)
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(2048, 2048, seed=8))          # 262144 blocks, ~35 ms of kernel on one B200
+    opt, plan = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(plan, 100)
+    out1, out2 = np.empty((len(blocks), 16), np.uint8), np.empty((len(blocks), 16), np.uint8)
+
+    def timed(devices, out):
+        api.encode_multi("BC7", blocks, opt, plan, devices=devices, out=out)       # warm-up: plan upload, pools
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            api.encode_multi("BC7", blocks, opt, plan, devices=devices, out=out)
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    t1, t2 = timed([0], out1), timed([0, 1], out2)
+    assert (out1 == out2).all()
+    assert t2 < 0.75 * t1, "one device %.1f ms, two devices %.1f ms: the devices did not overlap" % (t1 * 1e3, t2 * 1e3)
