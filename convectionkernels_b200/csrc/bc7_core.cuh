@@ -76,7 +76,7 @@ namespace cvttb200
     };
 
     // Command stream opcodes (built by bc7_plan.cpp)
-    enum { kCmdEnd = 0, kCmdShape = 1, kCmdEval = 2, kCmdDual = 3 };
+    enum { kCmdEnd = 0, kCmdShape = 1, kCmdEval = 2, kCmdDual = 3, kCmdPair2 = 4 };
     enum { kBC7MaxSlots = 184 };
 
     // lexicographic order of the reference's commit sequence: modes 0,1,2,3,6,7 (TrySinglePlane) then 4,5 (TryDualPlane)
@@ -1421,6 +1421,151 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
+    // Endpoint fits of one gathered pixel subset (the first half of a SHAPE command).  Shapes the plan does not list keep the
+    // all-zero "unfinished" endpoints the zero-initialised reference build has (SinglePlaneTemporaries, BC67.cpp:803-811).
+    // allowRGBModes / usePCA4 are the votes of the block the pixels belong to; anyRGB / anyPCA4 only say whether some lane of
+    // the warp needs the fit at all (pure work skipping).
+    template<int STRIDE>
+    CVTT_HD void bc7_shape_fits(const BC7Params &P, const F4 *gw, int n, bool listedRGB, bool listedRGBA, bool needRGBA,
+        bool allowRGBModes, bool usePCA4, bool anyRGB, bool anyPCA4, float *baseRGB, float *offsRGB, float *baseRGBA, float *offsRGBA)
+    {
+        for (int ch = 0; ch < 3; ch++)
+            baseRGB[ch] = offsRGB[ch] = 0.0f;
+        if (listedRGB && anyRGB)
+        {
+            float b3[3], o3[3];
+            bc7_endpoint_selector<3, STRIDE>(gw, n, P.w, b3, o3);
+            if (allowRGBModes)                                       // BC67.cpp:1085
+                for (int ch = 0; ch < 3; ch++)
+                {
+                    baseRGB[ch] = b3[ch];
+                    offsRGB[ch] = o3[ch];
+                }
+        }
+        for (int ch = 0; ch < 4; ch++)
+            baseRGBA[ch] = offsRGBA[ch] = 0.0f;
+        if (needRGBA && listedRGBA)
+        {
+            // ExpandTo<4>(255), UnfinishedEndpoints.h:93-114
+            for (int ch = 0; ch < 3; ch++)
+            {
+                baseRGBA[ch] = baseRGB[ch];
+                offsRGBA[ch] = offsRGB[ch];
+            }
+            baseRGBA[3] = 255.0f;
+            offsRGBA[3] = 0.0f;
+            if (anyPCA4)
+            {
+                float b4[4], o4[4];
+                bc7_endpoint_selector<4, STRIDE>(gw, n, P.w, b4, o4);
+                if (usePCA4)
+                    for (int ch = 0; ch < 4; ch++)
+                    {
+                        baseRGBA[ch] = b4[ch];
+                        offsRGBA[ch] = o4[ch];
+                    }
+            }
+        }
+    }
+
+    // the trials of one (mode, gathered subset) of the two-subset modes, without the punch-through and single-colour variants
+    template<bool FAST, int STRIDE>
+    CVTT_HD void bc7_run_pair_mode(const BC7Params &P, int mode, const F4 *gv, const F4 *gw, int n, int seeds, const float *baseRGB, const float *offsRGB,
+        const float *baseRGBA, const float *offsRGBA, const float *sumV, float staticAlphaError, BC7ShapeBest &best)
+    {
+        if (mode == 1)
+            bc7_shape_trials<1, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
+        else if (mode == 3)
+            bc7_shape_trials<3, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
+        else
+            bc7_shape_trials<7, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // PAIR2 commands (two-subset modes 1 / 3 / 7, one partition): the second subset is only searched for the blocks that can
+    // still use it, and those blocks are handed to the first threads of the CTA so that the remaining warps do not walk the
+    // trials at all.  The exchange between a block's owner thread and the thread that searches its second subset goes through
+    // this interface: the kernel implements it with shared memory (bc7_kernels.cu), a single lane (tests/hostsim, and kernels
+    // whose command streams hold no PAIR2) searches its own second subset.
+    struct BC7SoloExchange
+    {
+        F4 data, posted;
+        uint32_t flags;
+        const uint32_t *raw;
+        CVTT_HD void publish(const F4 &d, uint32_t f) { data = d; flags = f; }
+        CVTT_HD int compact(bool need, bool &warpHasTasks) { warpHasTasks = need; return need ? 0 : -1; }
+        CVTT_HD F4 owner_data(int) const { return data; }
+        CVTT_HD uint32_t owner_flags(int) const { return flags; }
+        CVTT_HD const uint32_t *owner_raw(int) const { return raw; }
+        CVTT_HD bool task_any(bool x) const { return x; }
+        CVTT_HD void post(int, const F4 &r) { posted = r; }
+        CVTT_HD void sync() {}
+        CVTT_HD F4 result() const { return posted; }
+    };
+
+    // Second half of a PAIR2 command, executed by the warps that received tasks: searches subset B of the block owned by thread
+    // `owner` (owner < 0: a lane of a task warp without a task; it walks along) and posts the best (total, run, endpoints)
+    // among the runs the owner can still use.  pc points at the command.
+    template<bool FAST, int STRIDE, class Exchange>
+    CVTT_HD void bc7_pair2_second(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *pc, int owner)
+    {
+        const uint32_t w0 = pc[0], w2 = pc[2];
+        const int nRuns = (w0 >> 8) & 0xff;
+        const bool listedRGB = (w0 >> 19) & 1, listedRGBA = (w0 >> 20) & 1, needRGBA = (w0 >> 18) & 1;
+        const uint32_t maskB = w2 & 0xffffu;
+        const int nB = (w2 >> 16) & 0xff;
+        const bool hasTask = owner >= 0;
+        const int o = hasTask ? owner : 0;
+        const F4 od = ex.owner_data(o);
+        const uint32_t of = hasTask ? ex.owner_flags(o) : 0u;
+        const float ownerBest = od.x;
+        const float errA[3] = { od.y, od.z, od.w };
+
+        BC7Lane<STRIDE> LB = L;
+        LB.raw = ex.owner_raw(o);
+        float sumV[4], accA;
+        bc7_gather<STRIDE>(LB, maskB, 0, P.w, sumV, accA);
+        const float staticAlphaError = (P.flags & kFlag_Uniform) ? accA : fmul(accA, P.wSq[3]);
+        const bool allowRGBModes = (of & 1u) != 0, usePCA4 = (of & 2u) != 0;
+        float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+        bc7_shape_fits<STRIDE>(P, L.gw, nB, listedRGB, listedRGBA, needRGBA, allowRGBModes, usePCA4, ex.task_any(hasTask && allowRGBModes), ex.task_any(hasTask && usePCA4),
+                               baseRGB, offsRGB, baseRGBA, offsRGBA);
+
+        float candTotal = FLT_MAX;
+        int candRun = -1, candOrder = 0;
+        uint32_t candE0 = 0, candE1 = 0;
+        for (int r = 0; r < nRuns; r++)
+        {
+            const uint32_t rw = pc[3 + r];
+            const int mode = rw & 0xf, seeds = (rw >> 8) & 0xf;
+            const bool wanted = hasTask && errA[r] != FLT_MAX && !(errA[r] > ownerBest);
+            if (!ex.task_any(wanted))
+                continue;
+            BC7ShapeBest best;
+            bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nB, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best);
+            const float total = fadd(errA[r], best.err);          // = err(subset 0) + err(subset 1), whichever of them is A
+            const int order = bc7_mode_order(mode);
+            if (wanted && (candRun < 0 || total < candTotal || (total == candTotal && order < candOrder)))
+            {
+                candTotal = total;
+                candRun = r;
+                candOrder = order;
+                candE0 = best.e0;
+                candE1 = best.e1;
+            }
+        }
+        if (hasTask)
+        {
+            F4 res;
+            res.x = candTotal;
+            res.y = as_float(candRun >= 0 ? (0x80000000u | (uint32_t)candRun) : 0u);
+            res.z = as_float(candE0);
+            res.w = as_float(candE1);
+            ex.post(owner, res);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
     // The whole search for one block.
     struct BC7NoVote      // the search without Flags::BC7_RespectPunchThrough has no per-trial group votes
     {
@@ -1430,8 +1575,8 @@ namespace cvttb200
     };
 
     // PUNCH: Flags::BC7_RespectPunchThrough; vote = the reference's AnySet / AllSet over the 8 blocks of one call
-    template<bool FAST, int STRIDE, bool PUNCH, class Vote>
-    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, uint32_t out[4])
+    template<bool FAST, int STRIDE, bool PUNCH, class Vote, class Exchange>
+    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, Exchange &ex, uint32_t out[4])
     {
         BC7Work work;
         work.error = FLT_MAX;
@@ -1468,6 +1613,20 @@ namespace cvttb200
             if (!lf.warpHasWork)
             {
                 // a warp without blocks (the dealt-out tail of a CTA) only walks the stream for the barriers
+                if (op == kCmdPair2)
+                {
+                    // no block, no task to offer, but the exchange's barriers and the task warps need every warp of the CTA
+                    F4 none;
+                    none.x = none.y = none.z = none.w = FLT_MAX;
+                    ex.publish(none, 0u);
+                    bool warpHasTasks;
+                    const int owner = ex.compact(false, warpHasTasks);
+                    if (warpHasTasks)
+                        bc7_pair2_second<FAST, STRIDE>(P, L, ex, pc, owner);
+                    ex.sync();
+                    pc += 3 + (int)((w0 >> 8) & 0xff);
+                    continue;
+                }
                 pc += (op == kCmdShape) ? 2 + (int)((w0 >> 8) & 0xff) : (op == kCmdEval ? 2 : 1);
                 continue;
             }
@@ -1484,43 +1643,8 @@ namespace cvttb200
                 bc7_gather<STRIDE>(L, mask, 0, P.w, sumV, accA);
                 const float staticAlphaError = uniform ? accA : fmul(accA, P.wSq[3]);
 
-                // endpoint fits.  Shapes the plan does not list keep the all-zero "unfinished" endpoints the
-                // zero-initialised reference build has (SinglePlaneTemporaries, BC67.cpp:803-811).
-                float baseRGB[3] = { 0, 0, 0 }, offsRGB[3] = { 0, 0, 0 };
-                if (listedRGB && lf.warpAnyRGB)
-                {
-                    float b3[3], o3[3];
-                    bc7_endpoint_selector<3, STRIDE>(L.gw, n, P.w, b3, o3);
-                    if (lf.allowRGBModes)                                       // BC67.cpp:1085
-                        for (int ch = 0; ch < 3; ch++)
-                        {
-                            baseRGB[ch] = b3[ch];
-                            offsRGB[ch] = o3[ch];
-                        }
-                }
-                float baseRGBA[4] = { 0, 0, 0, 0 }, offsRGBA[4] = { 0, 0, 0, 0 };
-                if (needRGBA && listedRGBA)
-                {
-                    // ExpandTo<4>(255), UnfinishedEndpoints.h:93-114
-                    for (int ch = 0; ch < 3; ch++)
-                    {
-                        baseRGBA[ch] = baseRGB[ch];
-                        offsRGBA[ch] = offsRGB[ch];
-                    }
-                    baseRGBA[3] = 255.0f;
-                    offsRGBA[3] = 0.0f;
-                    if (lf.warpAnyPCA4)
-                    {
-                        float b4[4], o4[4];
-                        bc7_endpoint_selector<4, STRIDE>(L.gw, n, P.w, b4, o4);
-                        if (usePCA4)
-                            for (int ch = 0; ch < 4; ch++)
-                            {
-                                baseRGBA[ch] = b4[ch];
-                                offsRGBA[ch] = o4[ch];
-                            }
-                    }
-                }
+                float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+                bc7_shape_fits<STRIDE>(P, L.gw, n, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
 
                 for (int r = 0; r < nRuns; r++)
                 {
@@ -1614,6 +1738,93 @@ namespace cvttb200
                         work.sc[s] = res[slots[s]][3];
                     }
                 }
+            }
+            else if (op == kCmdPair2)
+            {
+                // Two-subset modes, one partition: subset A (the larger one) for every block, subset B only where A's error
+                // leaves room below the block's best.  total = err(A) + err(B) >= err(A) (errors are sums of non-negative
+                // terms and fl(a + b) is monotonic), so a block whose err(A) already exceeds its best cannot take this
+                // (mode, partition) whatever B gives -- the reference evaluates it and rejects it.
+                const int nRuns = (w0 >> 8) & 0xff, partition = (w0 >> 24) & 0x3f;
+                const bool listedRGB = (w0 >> 16) & 1, listedRGBA = (w0 >> 17) & 1, needRGBA = (w0 >> 18) & 1, aIsSubset1 = (w0 >> 21) & 1;
+                const uint32_t w1 = pc[1];
+                const uint32_t maskA = w1 & 0xffffu;
+                const int nA = (w1 >> 16) & 0xff;
+
+                float sumV[4], accA;
+                bc7_gather<STRIDE>(L, maskA, 0, P.w, sumV, accA);
+                const float staticAlphaError = uniform ? accA : fmul(accA, P.wSq[3]);
+                float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+                bc7_shape_fits<STRIDE>(P, L.gw, nA, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
+
+                float errA[3] = { FLT_MAX, FLT_MAX, FLT_MAX };       // FLT_MAX: this block cannot use the run
+                uint32_t epA[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+                bool need = false;
+                for (int r = 0; r < nRuns; r++)
+                {
+                    const uint32_t rw = pc[3 + r];
+                    const int mode = rw & 0xf, seeds = (rw >> 4) & 0xf;
+                    if ((mode < 4 && !lf.warpAnyRGB) || (mode == 7 && !lf.warpAnyMode7))
+                        continue;
+                    BC7ShapeBest best;
+                    bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nA, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best);
+                    bool eligible = true;                              // the lane conditions of the partition scan, BC67.cpp:1602-1634
+                    if (mode < 4 && !lf.allowRGBModes)
+                        eligible = false;
+                    if (mode == 7)
+                    {
+                        if (!allowMode7)
+                            eligible = false;
+                        if (lf.anyBlockHasAlpha && ((P.mode7RGBPartitionEnabled >> partition) & 1) == 0 && !lf.blockHasNonMaxAlpha)
+                            eligible = false;
+                    }
+                    if (eligible)
+                    {
+                        errA[r] = best.err;
+                        epA[r][0] = best.e0;
+                        epA[r][1] = best.e1;
+                        need = need || !(best.err > work.error);
+                    }
+                }
+                {
+                    F4 d;
+                    d.x = work.error;
+                    d.y = errA[0];
+                    d.z = errA[1];
+                    d.w = errA[2];
+                    ex.publish(d, (lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
+                }
+                bool warpHasTasks;
+                const int owner = ex.compact(need, warpHasTasks);
+                if (warpHasTasks)
+                    bc7_pair2_second<FAST, STRIDE>(P, L, ex, pc, owner);
+                ex.sync();
+                if (need)
+                {
+                    const F4 got = ex.result();
+                    const uint32_t tag = as_uint(got.y);
+                    if (tag & 0x80000000u)
+                    {
+                        const int r = (int)(tag & 3u);
+                        const int mode = pc[3 + r] & 0xf;
+                        const float totalError = got.x;
+                        const int key = bc7_mode_order(mode) * 64 + partition;
+                        if (totalError < work.error || (totalError == work.error && key < work.key))
+                        {
+                            work.error = totalError;
+                            work.key = key;
+                            work.mode = mode;
+                            work.sub = partition;
+                            const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
+                            work.ep[sA][0] = epA[r][0];
+                            work.ep[sA][1] = epA[r][1];
+                            work.ep[sB][0] = as_uint(got.z);
+                            work.ep[sB][1] = as_uint(got.w);
+                            work.sc[0] = work.sc[1] = work.sc[2] = 0;
+                        }
+                    }
+                }
+                pc += 3 + nRuns;
             }
             else // kCmdDual
             {

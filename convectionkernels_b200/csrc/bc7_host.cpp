@@ -184,39 +184,36 @@ namespace cvttb200
         }
     }
 
-    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds)
+    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, bool pairCommands)
     {
         cmds.clear();
         const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
         int maxSlot = 0;
 
-        // Two-subset modes 1, 3, 7, partition-major: every two-subset shape belongs to exactly one partition, so
-        // six recycled slots are enough.  A (mode, partition) whose subsets are not all searched can never win in
-        // the reference (its total is >= FLT_MAX), so it is not emitted at all.  Mode 7 scans all 64 partitions
-        // whatever mode7RGBAPartitionEnabled says (the reference assigns a misspelt variable, BC67.cpp:1593-1596).
-        for (int p = 0; p < 64; p++)
+        // The one-subset candidates go first (mode 6, then modes 4 and 5), then the three-subset modes: they are the cheap part
+        // of the search and give every block a good error to beat, which is what lets the PAIR2 commands of the two-subset
+        // modes drop most second subsets.  The order of commands is free: the winner is the lexicographic (error, reference
+        // sequence) minimum.  Slots 0-5 are recycled (mode 6, then the two-subset partitions), the rest belong to modes 0 / 2.
+
+        // Mode 6: the whole block (shape 0)
+        if (plan.mode6Enabled && spRGBA[0])
         {
-            const int shapes[2] = { kBC7Shapes2[p * 2], kBC7Shapes2[p * 2 + 1] };
-            const bool rgbSearched = spRGB[shapes[0]] && spRGB[shapes[1]];
-            const bool m1 = ((plan.mode1PartitionEnabled >> p) & 1) && rgbSearched;
-            const bool m3 = ((plan.mode3PartitionEnabled >> p) & 1) && rgbSearched;
-            const bool m7 = spRGBA[shapes[0]] && spRGBA[shapes[1]];
-            if (!m1 && !m3 && !m7)
-                continue;
-            for (int s = 0; s < 2; s++)
-            {
-                std::vector<Run> runs;
-                if (m1) runs.push_back(Run{ 1, spRGB[shapes[s]], 0 + s });
-                if (m3) runs.push_back(Run{ 3, spRGB[shapes[s]], 2 + s });
-                if (m7) runs.push_back(Run{ 7, spRGBA[shapes[s]], 4 + s });
-                emit_shape(cmds, plan, shapes[s], runs);
-            }
-            const int s1[2] = { 0, 1 }, s3[2] = { 2, 3 }, s7[2] = { 4, 5 };
-            if (m1) emit_eval(cmds, 1, p, 2, s1);
-            if (m3) emit_eval(cmds, 3, p, 2, s3);
-            if (m7) emit_eval(cmds, 7, p, 2, s7);
-            maxSlot = 6;
+            std::vector<Run> runs(1, Run{ 6, spRGBA[0], 0 });
+            emit_shape(cmds, plan, 0, runs);
+            const int slots[1] = { 0 };
+            emit_eval(cmds, 6, 0, 1, slots);
+            maxSlot = std::max(maxSlot, 1);
         }
+
+        // Modes 4 and 5 (BC67.cpp:1675-1683, 1735-1742)
+        for (int mode = 4; mode <= 5; mode++)
+            for (int rotation = 0; rotation < 4; rotation++)
+                for (int isel = 0; isel < (mode == 4 ? 2 : 1); isel++)
+                {
+                    const int seeds = std::min<int>(4, mode == 4 ? plan.mode4SP[rotation][isel] : plan.mode5SP[rotation]);
+                    if (seeds > 0)
+                        cmds.push_back(kCmdDual | ((uint32_t)mode << 8) | ((uint32_t)rotation << 16) | ((uint32_t)isel << 20) | ((uint32_t)seeds << 24));
+                }
 
         // Three-subset modes 0 and 2: shapes are shared between partitions, so each needed shape is searched once
         // and kept in its own slot until the partitions are scanned.
@@ -257,25 +254,60 @@ namespace cvttb200
             maxSlot = std::max(maxSlot, nextSlot);
         }
 
-        // Mode 6: the whole block (shape 0)
-        if (plan.mode6Enabled && spRGBA[0])
+        // Two-subset modes 1, 3, 7, partition-major: every two-subset shape belongs to exactly one partition.  A (mode,
+        // partition) whose subsets are not all searched can never win in the reference (its total is >= FLT_MAX), so it is not
+        // emitted at all.  Mode 7 scans all 64 partitions whatever mode7RGBAPartitionEnabled says (the reference assigns a
+        // misspelt variable, BC67.cpp:1593-1596).
+        //   pairCommands: one PAIR2 command per partition -- the larger subset (A) is searched for every block, the other one
+        //   (B) only for the blocks whose err(A) leaves room below their best (bc7_core.cuh);
+        //   otherwise SHAPE, SHAPE, EVAL... through six recycled slots (the kernels with per-trial group votes and the
+        //   single-colour candidates need every block's own thread to walk both subsets).
+        for (int p = 0; p < 64; p++)
         {
-            std::vector<Run> runs(1, Run{ 6, spRGBA[0], 0 });
-            emit_shape(cmds, plan, 0, runs);
-            const int slots[1] = { 0 };
-            emit_eval(cmds, 6, 0, 1, slots);
-            maxSlot = std::max(maxSlot, 1);
-        }
-
-        // Modes 4 and 5 (BC67.cpp:1675-1683, 1735-1742)
-        for (int mode = 4; mode <= 5; mode++)
-            for (int rotation = 0; rotation < 4; rotation++)
-                for (int isel = 0; isel < (mode == 4 ? 2 : 1); isel++)
+            const int shapes[2] = { kBC7Shapes2[p * 2], kBC7Shapes2[p * 2 + 1] };
+            const bool rgbSearched = spRGB[shapes[0]] && spRGB[shapes[1]];
+            const bool m1 = ((plan.mode1PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m3 = ((plan.mode3PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m7 = spRGBA[shapes[0]] && spRGBA[shapes[1]];
+            if (!m1 && !m3 && !m7)
+                continue;
+            if (pairCommands)
+            {
+                const unsigned masks[2] = { kBC7ShapeMask[shapes[0]], kBC7ShapeMask[shapes[1]] };
+                const int a = popcount16(masks[1]) > popcount16(masks[0]) ? 1 : 0, b = 1 - a;
+                bool listedRGB[2] = { false, false }, listedRGBA[2] = { false, false };
+                for (int k = 0; k < 2; k++)
                 {
-                    const int seeds = std::min<int>(4, mode == 4 ? plan.mode4SP[rotation][isel] : plan.mode5SP[rotation]);
-                    if (seeds > 0)
-                        cmds.push_back(kCmdDual | ((uint32_t)mode << 8) | ((uint32_t)rotation << 16) | ((uint32_t)isel << 20) | ((uint32_t)seeds << 24));
+                    for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
+                        listedRGB[k] |= (plan.rgbShapeList[i] == shapes[k]);
+                    for (int i = 0; i < plan.rgbaNumShapesToEvaluate; i++)
+                        listedRGBA[k] |= (plan.rgbaShapeList[i] == shapes[k]);
                 }
+                const int nRuns = (m1 ? 1 : 0) + (m3 ? 1 : 0) + (m7 ? 1 : 0);
+                cmds.push_back(kCmdPair2 | ((uint32_t)nRuns << 8) | ((uint32_t)listedRGB[a] << 16) | ((uint32_t)listedRGBA[a] << 17) | ((uint32_t)m7 << 18) |
+                               ((uint32_t)listedRGB[b] << 19) | ((uint32_t)listedRGBA[b] << 20) | ((uint32_t)a << 21) | ((uint32_t)p << 24));
+                cmds.push_back(masks[a] | ((uint32_t)popcount16(masks[a]) << 16));
+                cmds.push_back(masks[b] | ((uint32_t)popcount16(masks[b]) << 16));
+                // run word: mode | seeds of subset A << 4 | seeds of subset B << 8
+                if (m1) cmds.push_back(1u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
+                if (m3) cmds.push_back(3u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
+                if (m7) cmds.push_back(7u | ((uint32_t)std::min<int>(spRGBA[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGBA[shapes[b]], 4) << 8));
+                continue;
+            }
+            for (int s = 0; s < 2; s++)
+            {
+                std::vector<Run> runs;
+                if (m1) runs.push_back(Run{ 1, spRGB[shapes[s]], 0 + s });
+                if (m3) runs.push_back(Run{ 3, spRGB[shapes[s]], 2 + s });
+                if (m7) runs.push_back(Run{ 7, spRGBA[shapes[s]], 4 + s });
+                emit_shape(cmds, plan, shapes[s], runs);
+            }
+            const int s1[2] = { 0, 1 }, s3[2] = { 2, 3 }, s7[2] = { 4, 5 };
+            if (m1) emit_eval(cmds, 1, p, 2, s1);
+            if (m3) emit_eval(cmds, 3, p, 2, s3);
+            if (m7) emit_eval(cmds, 7, p, 2, s7);
+            maxSlot = std::max(maxSlot, 6);
+        }
 
         cmds.push_back(kCmdEnd);
         return maxSlot;

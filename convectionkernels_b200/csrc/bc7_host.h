@@ -15,7 +15,7 @@ namespace cvttb200
     void bc7_plan_default(BC7PlanPOD &plan);
 
     // Flattens a plan into SHAPE / EVAL / DUAL commands (see bc7_core.cuh).  Returns the number of result slots used.
-    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds);
+    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, bool pairCommands);
 
     // Fills everything of BC7Params except `cmds`.  rcpN[n] must hold the host's _mm_rcp_ps((float)n), n = 0..16.
     void bc7_fill_params(BC7Params &P, const OptionsPOD &options, const BC7PlanPOD &plan, const float rcpN[17]);

@@ -21,6 +21,55 @@ namespace
 
     __constant__ BC7PackTables c_bc7PackTables;
 
+    // The exchange of the PAIR2 commands (bc7_core.cuh) inside one CTA.  A block's owner thread publishes (best error, err(A) of
+    // each run) in entry 15 of its own gathered-pixel array gv -- a two-subset shape has at most 15 pixels, so that entry is
+    // never used by the gathers of these commands -- and the thread that searched subset B answers in entry 15 of the owner's gw.
+    // compact() turns the per-thread "needs subset B" flags into a dense list of owner threads: the first `count` threads of
+    // the CTA take one each, so only ceil(count / 32) warps walk the second subset's trials.
+    struct BC7CtaExchange
+    {
+        F4 *gvBase, *gwBase;
+        const uint32_t *rawBase;
+        uint16_t *list;             // [kBC7Threads]
+        uint32_t *warpCounts;       // [kBC7Threads / 32]
+        uint8_t *flags;             // [kBC7Threads]
+        uint32_t tid;
+
+        __device__ __forceinline__ void publish(const F4 &d, uint32_t f)
+        {
+            gvBase[15 * kBC7Threads + tid] = d;
+            flags[tid] = (uint8_t)f;
+        }
+        __device__ __forceinline__ int compact(bool need, bool &warpHasTasks)
+        {
+            const uint32_t lane = tid & 31, warp = tid >> 5;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, need);
+            if (lane == 0)
+                warpCounts[warp] = __popc(ballot);
+            __syncthreads();
+            uint32_t base = 0, total = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < kBC7Threads / 32; k++)
+            {
+                const uint32_t c = warpCounts[k];
+                base += (k < warp) ? c : 0u;
+                total += c;
+            }
+            if (need)
+                list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)tid;
+            __syncthreads();
+            warpHasTasks = warp * 32 < total;
+            return tid < total ? (int)list[tid] : -1;
+        }
+        __device__ __forceinline__ F4 owner_data(int owner) const { return gvBase[15 * kBC7Threads + owner]; }
+        __device__ __forceinline__ uint32_t owner_flags(int owner) const { return flags[owner]; }
+        __device__ __forceinline__ const uint32_t *owner_raw(int owner) const { return rawBase + owner; }
+        __device__ __forceinline__ bool task_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
+        __device__ __forceinline__ void post(int owner, const F4 &r) { gwBase[15 * kBC7Threads + owner] = r; }
+        __device__ __forceinline__ void sync() { __syncthreads(); }
+        __device__ __forceinline__ F4 result() const { return gwBase[15 * kBC7Threads + tid]; }
+    };
+
     // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
     // group-wide votes of BC7Computer::TrySinglePlane (BC67.cpp:1069-1072), so that every warp of the encode kernel
     // holds four groups that walk the same set of modes.  Pure scheduling: the encode kernel recomputes the votes.
@@ -132,6 +181,18 @@ namespace
         L.gv = sGv + tid;
         L.gw = sGw + tid;
 
+        __shared__ uint16_t sTaskList[kBC7Threads];
+        __shared__ uint32_t sWarpCounts[kBC7Threads / 32];
+        __shared__ uint8_t sOwnerFlags[kBC7Threads];
+        BC7CtaExchange ex;
+        ex.gvBase = sGv;
+        ex.gwBase = sGw;
+        ex.rawBase = sRaw;
+        ex.list = sTaskList;
+        ex.warpCounts = sWarpCounts;
+        ex.flags = sOwnerFlags;
+        ex.tid = tid;
+
         uint32_t minAlpha = 255, maxAlpha = 0;
         bool isPunchThrough = true;
         if (active)
@@ -184,12 +245,12 @@ namespace
         {
             SegmentVote vote;
             vote.segMask = segMask;
-            bc7_encode_block<FAST, kBC7Threads, true>(P, c_bc7PackTables, L, lf, vote, o);
+            bc7_encode_block<FAST, kBC7Threads, true>(P, c_bc7PackTables, L, lf, vote, ex, o);
         }
         else
         {
             BC7NoVote vote;
-            bc7_encode_block<FAST, kBC7Threads, false>(P, c_bc7PackTables, L, lf, vote, o);
+            bc7_encode_block<FAST, kBC7Threads, false>(P, c_bc7PackTables, L, lf, vote, ex, o);
         }
 
         if (active)
@@ -231,16 +292,16 @@ namespace cvttb200
     }
 
     // caller holds ctx.planMutex and has made ctx.device current
-    static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, const uint32_t **dCmds)
+    static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, bool pairCommands, const uint32_t **dCmds)
     {
         for (size_t i = 0; i < ctx.plans.size(); i++)
-            if (memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
+            if (ctx.plans[i].pairCommands == pairCommands && memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
             {
                 *dCmds = ctx.plans[i].dCmds;
                 return CVTTB200_OK;
             }
         std::vector<uint32_t> cmds;
-        const int slots = bc7_compile_plan(plan, cmds);
+        const int slots = bc7_compile_plan(plan, cmds, pairCommands);
         if (slots > kBC7MaxSlots)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "BC7 plan needs more result slots than the kernel provides");
         if (ctx.plans.size() >= 16)
@@ -253,6 +314,7 @@ namespace cvttb200
         }
         PlanCacheEntry entry;
         entry.plan = plan;
+        entry.pairCommands = pairCommands;
         entry.dCmds = nullptr;
         if (!ctx.setupStream)
             CVTT_CUDA(cudaStreamCreateWithFlags(&ctx.setupStream, cudaStreamNonBlocking));
@@ -281,8 +343,11 @@ namespace cvttb200
         BC7Params P;
         bc7_fill_params(P, options, plan, rcpN);
         std::lock_guard<std::mutex> planLock(ctx.planMutex);      // until the launches below are enqueued (see the eviction above)
+        // PAIR2 commands hand a block's second subset to another thread; the variants whose trials vote inside the block's
+        // group (BC7_RespectPunchThrough) or return more than endpoints (BC7_TrySingleColor) keep the plain command stream
+        const bool pairCommands = (options.flags & (kFlag_BC7_RespectPunchThrough | kFlag_BC7_TrySingleColor)) == 0;
         const uint32_t *dCmds = nullptr;
-        int rc = get_plan_commands(ctx, plan, &dCmds);
+        int rc = get_plan_commands(ctx, plan, pairCommands, &dCmds);
         if (rc != CVTTB200_OK)
             return rc;
         P.cmds = dCmds;

@@ -27,6 +27,7 @@ namespace cvttb200
     struct PlanCacheEntry
     {
         BC7PlanPOD plan;
+        bool pairCommands;                            // which of the two command-stream forms (bc7_compile_plan)
         uint32_t *dCmds;
     };
 

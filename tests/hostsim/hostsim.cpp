@@ -24,10 +24,12 @@ namespace
         L.gv = gv;
         L.gw = gw;
         uint32_t o[4];
+        BC7SoloExchange ex;                 // PAIR2 commands: the lane searches its own second subsets
+        ex.raw = raw;
         if (fast)
-            bc7_encode_block<true, 1, PUNCH>(P, T, L, lf, vote, o);
+            bc7_encode_block<true, 1, PUNCH>(P, T, L, lf, vote, ex, o);
         else
-            bc7_encode_block<false, 1, PUNCH>(P, T, L, lf, vote, o);
+            bc7_encode_block<false, 1, PUNCH>(P, T, L, lf, vote, ex, o);
         memcpy(out, o, 16);
     }
 }
@@ -40,7 +42,9 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
     for (int n = 0; n < 17; n++)
         rcpN[n] = rcpTable ? rcpTable[n] : _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
     std::vector<uint32_t> cmds;
-    int slots = bc7_compile_plan(*plan, cmds);
+    // the same choice of command stream as launch_bc7 makes
+    const bool pairCommands = (options->flags & (kFlag_BC7_RespectPunchThrough | kFlag_BC7_TrySingleColor)) == 0;
+    int slots = bc7_compile_plan(*plan, cmds, pairCommands);
     if (slots > kBC7MaxSlots)
         return -2;
     BC7Params P;
