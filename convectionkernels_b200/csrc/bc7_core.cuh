@@ -479,6 +479,7 @@ namespace cvttb200
     {
         float err;
         uint32_t e0, e1;      // packed endpoint bytes
+        int seq;              // reference sequence number of the winning trial (bc7_shape_trials), for merging partial searches
     };
 
     template<int NCH>
@@ -657,9 +658,11 @@ namespace cvttb200
         }
     }
 
+    // ppFirst / ppEnd restrict the search to the parity-pair iterations [ppFirst, ppEnd) (modes with four parity combinations:
+    // 0 .. 2); the results of disjoint parts merge by (err, seq).
     template<int MODE, bool FAST, int STRIDE>
     CVTT_HD void bc7_shape_trials(const BC7Params &P, const F4 *gv, const F4 *gw, int n, int seeds, const float *base, const float *offs,
-        const float *sumV, float staticAlphaError, BC7ShapeBest &out)
+        const float *sumV, float staticAlphaError, BC7ShapeBest &out, int ppFirst = 0, int ppEnd = 2)
     {
         typedef BC7ModeT<MODE> M;
         enum { NCH = M::NCH };
@@ -688,7 +691,7 @@ namespace cvttb200
                     u1[ch] = f2_splat(rne(clamp_for_round(fadd(base[ch], fmul(offs[ch], tf1)), 0.0f, 255.0f)));
                 }
 #pragma unroll 1
-                for (int pp = 0; pp < M::PMAX / 2; pp++)
+                for (int pp = ppFirst; pp < imin(ppEnd, M::PMAX / 2); pp++)
                 {
                     // lanes: pIter = 2 pp and 2 pp + 1, i.e. first parity bit 0 and 1
                     const int p1 = M::SHAREDP ? 0 : pp;
@@ -719,6 +722,7 @@ namespace cvttb200
 
         const bool takeY = best.err.y < best.err.x || (best.err.y == best.err.x && best.seqY < best.seqX);
         out.err = takeY ? best.err.y : best.err.x;
+        out.seq = takeY ? best.seqY : best.seqX;
         uint32_t r0 = 0, r1 = 0;
 #pragma unroll
         for (int ch = 0; ch < NCH; ch++)
@@ -1471,97 +1475,99 @@ namespace cvttb200
     // the trials of one (mode, gathered subset) of the two-subset modes, without the punch-through and single-colour variants
     template<bool FAST, int STRIDE>
     CVTT_HD void bc7_run_pair_mode(const BC7Params &P, int mode, const F4 *gv, const F4 *gw, int n, int seeds, const float *baseRGB, const float *offsRGB,
-        const float *baseRGBA, const float *offsRGBA, const float *sumV, float staticAlphaError, BC7ShapeBest &best)
+        const float *baseRGBA, const float *offsRGBA, const float *sumV, float staticAlphaError, BC7ShapeBest &best, int ppFirst = 0, int ppEnd = 2)
     {
         if (mode == 1)
-            bc7_shape_trials<1, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
+            bc7_shape_trials<1, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best, ppFirst, ppEnd);
         else if (mode == 3)
-            bc7_shape_trials<3, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best);
+            bc7_shape_trials<3, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, best, ppFirst, ppEnd);
         else
-            bc7_shape_trials<7, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best);
+            bc7_shape_trials<7, FAST, STRIDE>(P, gv, gw, n, seeds, baseRGBA, offsRGBA, sumV, 0.0f, best, ppFirst, ppEnd);
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // PAIR2 commands (two-subset modes 1 / 3 / 7, one partition): the second subset is only searched for the blocks that can
-    // still use it, and those blocks are handed to the first threads of the CTA so that the remaining warps do not walk the
-    // trials at all.  The exchange between a block's owner thread and the thread that searches its second subset goes through
-    // this interface: the kernel implements it with shared memory (bc7_kernels.cu), a single lane (tests/hostsim, and kernels
-    // whose command streams hold no PAIR2) searches its own second subset.
+    // PAIR2 commands (two-subset modes 1 / 3 / 7, one partition): subset A is searched by every block's own thread; subset B
+    // only for the (block, run) pairs that can still win, as TASKS that are dealt out to the warps of the CTA, so that the
+    // warps without a task do not walk those trials at all.  A task is one class of work for one block: class = run * 2 +
+    // unit, where a run with four parity combinations may be split into two units (its two parity-pair iterations).  All
+    // tasks of a 32-slot chunk have the same class, so a warp executes one mode's trials at a time.
+    //
+    // The exchange between a block's owner thread and the threads that run its tasks goes through this interface.  The
+    // kernel implements it with shared memory (bc7_kernels.cu); a single lane (tests/hostsim, and kernels whose command
+    // streams hold no PAIR2) runs its own tasks one after the other.
+    enum { kBC7PairClasses = 6 };
+
     struct BC7SoloExchange
     {
-        F4 data, posted;
-        uint32_t flags;
+        F4 posted[kBC7PairClasses];
+        uint32_t flags, want;
         const uint32_t *raw;
-        CVTT_HD void publish(const F4 &d, uint32_t f) { data = d; flags = f; }
-        CVTT_HD int compact(bool need, bool &warpHasTasks) { warpHasTasks = need; return need ? 0 : -1; }
-        CVTT_HD F4 owner_data(int) const { return data; }
+        // the owner's group votes, for whoever fits its pixels: bit 0 allowRGBModes, bit 1 usePCA4
+        CVTT_HD void publish(uint32_t f) { flags = f; }
+        // wantMask: bit c = this block wants class c searched.  Returns the number of task slots (padded to whole chunks).
+        CVTT_HD int compact(uint32_t wantMask) { want = wantMask; return kBC7PairClasses; }
+        CVTT_HD int first_slot() const { return 0; }
+        CVTT_HD int slot_stride() const { return 1; }
+        CVTT_HD bool chunk_in_range(int slot, int total) const { return slot < total; }
+        // the task in `slot`: its class (the same for the whole chunk) and the owner thread, -1 for a padding slot
+        CVTT_HD void task(int slot, int &cls, int &owner) const { cls = slot; owner = ((want >> slot) & 1u) ? 0 : -1; }
         CVTT_HD uint32_t owner_flags(int) const { return flags; }
         CVTT_HD const uint32_t *owner_raw(int) const { return raw; }
         CVTT_HD bool task_any(bool x) const { return x; }
-        CVTT_HD void post(int, const F4 &r) { posted = r; }
+        CVTT_HD void post(int, int cls, const F4 &r) { posted[cls] = r; }
         CVTT_HD void sync() {}
-        CVTT_HD F4 result() const { return posted; }
+        CVTT_HD F4 result(int cls) const { return posted[cls]; }
     };
 
-    // Second half of a PAIR2 command, executed by the warps that received tasks: searches subset B of the block owned by thread
-    // `owner` (owner < 0: a lane of a task warp without a task; it walks along) and posts the best (total, run, endpoints)
-    // among the runs the owner can still use.  pc points at the command.
+    // Second half of a PAIR2 command: runs the task slots dealt to this thread.  pc points at the command.
     template<bool FAST, int STRIDE, class Exchange>
-    CVTT_HD void bc7_pair2_second(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *pc, int owner)
+    CVTT_HD void bc7_pair2_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *pc, int total)
     {
         const uint32_t w0 = pc[0], w2 = pc[2];
-        const int nRuns = (w0 >> 8) & 0xff;
-        const bool listedRGB = (w0 >> 19) & 1, listedRGBA = (w0 >> 20) & 1, needRGBA = (w0 >> 18) & 1;
+        const bool listedRGB = (w0 >> 19) & 1, listedRGBA = (w0 >> 20) & 1, split = (w0 >> 22) & 1;
         const uint32_t maskB = w2 & 0xffffu;
         const int nB = (w2 >> 16) & 0xff;
-        const bool hasTask = owner >= 0;
-        const int o = hasTask ? owner : 0;
-        const F4 od = ex.owner_data(o);
-        const uint32_t of = hasTask ? ex.owner_flags(o) : 0u;
-        const float ownerBest = od.x;
-        const float errA[3] = { od.y, od.z, od.w };
 
-        BC7Lane<STRIDE> LB = L;
-        LB.raw = ex.owner_raw(o);
-        float sumV[4], accA;
-        bc7_gather<STRIDE>(LB, maskB, 0, P.w, sumV, accA);
-        const float staticAlphaError = (P.flags & kFlag_Uniform) ? accA : fmul(accA, P.wSq[3]);
-        const bool allowRGBModes = (of & 1u) != 0, usePCA4 = (of & 2u) != 0;
-        float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
-        bc7_shape_fits<STRIDE>(P, L.gw, nB, listedRGB, listedRGBA, needRGBA, allowRGBModes, usePCA4, ex.task_any(hasTask && allowRGBModes), ex.task_any(hasTask && usePCA4),
-                               baseRGB, offsRGB, baseRGBA, offsRGBA);
-
-        float candTotal = FLT_MAX;
-        int candRun = -1, candOrder = 0;
-        uint32_t candE0 = 0, candE1 = 0;
-        for (int r = 0; r < nRuns; r++)
+        for (int slot = ex.first_slot(); ex.chunk_in_range(slot, total); slot += ex.slot_stride())
         {
+            int cls, owner;
+            ex.task(slot, cls, owner);
+            const bool hasTask = owner >= 0;
+            if (!ex.task_any(hasTask))
+                continue;
+            const int r = cls >> 1, unit = cls & 1;
             const uint32_t rw = pc[3 + r];
             const int mode = rw & 0xf, seeds = (rw >> 8) & 0xf;
-            const bool wanted = hasTask && errA[r] != FLT_MAX && !(errA[r] > ownerBest);
-            if (!ex.task_any(wanted))
-                continue;
+            const int o = hasTask ? owner : 0;
+            const uint32_t of = hasTask ? ex.owner_flags(o) : 0u;
+            const bool allowRGBModes = (of & 1u) != 0, usePCA4 = (of & 2u) != 0;
+
+            BC7Lane<STRIDE> LB = L;
+            LB.raw = ex.owner_raw(o);
+            float sumV[4], accA;
+            bc7_gather<STRIDE>(LB, maskB, 0, P.w, sumV, accA);
+            const float staticAlphaError = (P.flags & kFlag_Uniform) ? accA : fmul(accA, P.wSq[3]);
+            // the fits this mode reads: RGB modes the 3-channel one; mode 7 the 4-channel one, or the expanded 3-channel one
+            // for a block whose group has no alpha (bc7_shape_fits)
+            const bool rgba = (mode == 7);
+            const bool anyRGB = ex.task_any(hasTask && (rgba ? !usePCA4 : allowRGBModes));
+            const bool anyPCA4 = rgba && ex.task_any(hasTask && usePCA4);
+            float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+            bc7_shape_fits<STRIDE>(P, L.gw, nB, listedRGB, listedRGBA, rgba, allowRGBModes, usePCA4, anyRGB, anyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
+
             BC7ShapeBest best;
-            bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nB, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best);
-            const float total = fadd(errA[r], best.err);          // = err(subset 0) + err(subset 1), whichever of them is A
-            const int order = bc7_mode_order(mode);
-            if (wanted && (candRun < 0 || total < candTotal || (total == candTotal && order < candOrder)))
+            const bool wide = (mode != 1) && split;          // four parity combinations, searched as two units
+            bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nB, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best,
+                                            wide ? unit : 0, wide ? unit + 1 : 2);
+            if (hasTask)
             {
-                candTotal = total;
-                candRun = r;
-                candOrder = order;
-                candE0 = best.e0;
-                candE1 = best.e1;
+                F4 res;
+                res.x = best.err;
+                res.y = as_float((uint32_t)best.seq);
+                res.z = as_float(best.e0);
+                res.w = as_float(best.e1);
+                ex.post(owner, cls, res);
             }
-        }
-        if (hasTask)
-        {
-            F4 res;
-            res.x = candTotal;
-            res.y = as_float(candRun >= 0 ? (0x80000000u | (uint32_t)candRun) : 0u);
-            res.z = as_float(candE0);
-            res.w = as_float(candE1);
-            ex.post(owner, res);
         }
     }
 
@@ -1616,13 +1622,9 @@ namespace cvttb200
                 if (op == kCmdPair2)
                 {
                     // no block, no task to offer, but the exchange's barriers and the task warps need every warp of the CTA
-                    F4 none;
-                    none.x = none.y = none.z = none.w = FLT_MAX;
-                    ex.publish(none, 0u);
-                    bool warpHasTasks;
-                    const int owner = ex.compact(false, warpHasTasks);
-                    if (warpHasTasks)
-                        bc7_pair2_second<FAST, STRIDE>(P, L, ex, pc, owner);
+                    ex.publish(0u);
+                    const int total = ex.compact(0u);
+                    bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pc, total);
                     ex.sync();
                     pc += 3 + (int)((w0 >> 8) & 0xff);
                     continue;
@@ -1757,9 +1759,10 @@ namespace cvttb200
                 float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
                 bc7_shape_fits<STRIDE>(P, L.gw, nA, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
 
-                float errA[3] = { FLT_MAX, FLT_MAX, FLT_MAX };       // FLT_MAX: this block cannot use the run
+                const bool split = (w0 >> 22) & 1;
+                float errA[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
                 uint32_t epA[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
-                bool need = false;
+                uint32_t wantMask = 0;                              // bit (run * 2 + unit)
                 for (int r = 0; r < nRuns; r++)
                 {
                     const uint32_t rw = pc[3 + r];
@@ -1778,50 +1781,45 @@ namespace cvttb200
                         if (lf.anyBlockHasAlpha && ((P.mode7RGBPartitionEnabled >> partition) & 1) == 0 && !lf.blockHasNonMaxAlpha)
                             eligible = false;
                     }
-                    if (eligible)
+                    if (eligible && !(best.err > work.error))
                     {
                         errA[r] = best.err;
                         epA[r][0] = best.e0;
                         epA[r][1] = best.e1;
-                        need = need || !(best.err > work.error);
+                        wantMask |= ((mode != 1 && split) ? 3u : 1u) << (2 * r);
                     }
                 }
-                {
-                    F4 d;
-                    d.x = work.error;
-                    d.y = errA[0];
-                    d.z = errA[1];
-                    d.w = errA[2];
-                    ex.publish(d, (lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
-                }
-                bool warpHasTasks;
-                const int owner = ex.compact(need, warpHasTasks);
-                if (warpHasTasks)
-                    bc7_pair2_second<FAST, STRIDE>(P, L, ex, pc, owner);
+                ex.publish((lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
+                const int total = ex.compact(wantMask);
+                bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pc, total);
                 ex.sync();
-                if (need)
+                for (int r = 0; r < nRuns; r++)
                 {
-                    const F4 got = ex.result();
-                    const uint32_t tag = as_uint(got.y);
-                    if (tag & 0x80000000u)
+                    if (!((wantMask >> (2 * r)) & 1u))
+                        continue;
+                    const int mode = pc[3 + r] & 0xf;
+                    F4 got = ex.result(2 * r);
+                    if ((wantMask >> (2 * r + 1)) & 1u)
                     {
-                        const int r = (int)(tag & 3u);
-                        const int mode = pc[3 + r] & 0xf;
-                        const float totalError = got.x;
-                        const int key = bc7_mode_order(mode) * 64 + partition;
-                        if (totalError < work.error || (totalError == work.error && key < work.key))
-                        {
-                            work.error = totalError;
-                            work.key = key;
-                            work.mode = mode;
-                            work.sub = partition;
-                            const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
-                            work.ep[sA][0] = epA[r][0];
-                            work.ep[sA][1] = epA[r][1];
-                            work.ep[sB][0] = as_uint(got.z);
-                            work.ep[sB][1] = as_uint(got.w);
-                            work.sc[0] = work.sc[1] = work.sc[2] = 0;
-                        }
+                        // the run was searched as two units: "first strictly better in sequence order" over both
+                        const F4 other = ex.result(2 * r + 1);
+                        if (other.x < got.x || (other.x == got.x && (int)as_uint(other.y) < (int)as_uint(got.y)))
+                            got = other;
+                    }
+                    const float totalError = aIsSubset1 ? fadd(got.x, errA[r]) : fadd(errA[r], got.x);       // subset 0 + subset 1
+                    const int key = bc7_mode_order(mode) * 64 + partition;
+                    if (totalError < work.error || (totalError == work.error && key < work.key))
+                    {
+                        work.error = totalError;
+                        work.key = key;
+                        work.mode = mode;
+                        work.sub = partition;
+                        const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
+                        work.ep[sA][0] = epA[r][0];
+                        work.ep[sA][1] = epA[r][1];
+                        work.ep[sB][0] = as_uint(got.z);
+                        work.ep[sB][1] = as_uint(got.w);
+                        work.sc[0] = work.sc[1] = work.sc[2] = 0;
                     }
                 }
                 pc += 3 + nRuns;

@@ -155,6 +155,10 @@ namespace cvttb200
     {
         struct Run { int mode, seeds, slot; };
 
+        // PAIR2: search subset B of the modes with four parity combinations (3, 7) as two tasks of one parity pair each
+        // (shorter task phases, the subset's fit is repeated) or as one
+        const bool kBC7SplitWideRuns = true;
+
         void emit_shape(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, int shape, const std::vector<Run> &runs)
         {
             bool inRGBList = false, inRGBAList = false, anyRGB = false, anyRGBA = false;
@@ -285,7 +289,7 @@ namespace cvttb200
                 }
                 const int nRuns = (m1 ? 1 : 0) + (m3 ? 1 : 0) + (m7 ? 1 : 0);
                 cmds.push_back(kCmdPair2 | ((uint32_t)nRuns << 8) | ((uint32_t)listedRGB[a] << 16) | ((uint32_t)listedRGBA[a] << 17) | ((uint32_t)m7 << 18) |
-                               ((uint32_t)listedRGB[b] << 19) | ((uint32_t)listedRGBA[b] << 20) | ((uint32_t)a << 21) | ((uint32_t)p << 24));
+                               ((uint32_t)listedRGB[b] << 19) | ((uint32_t)listedRGBA[b] << 20) | ((uint32_t)a << 21) | ((uint32_t)(kBC7SplitWideRuns ? 1 : 0) << 22) | ((uint32_t)p << 24));
                 cmds.push_back(masks[a] | ((uint32_t)popcount16(masks[a]) << 16));
                 cmds.push_back(masks[b] | ((uint32_t)popcount16(masks[b]) << 16));
                 // run word: mode | seeds of subset A << 4 | seeds of subset B << 8

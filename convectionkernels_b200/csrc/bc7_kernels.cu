@@ -21,53 +21,82 @@ namespace
 
     __constant__ BC7PackTables c_bc7PackTables;
 
-    // The exchange of the PAIR2 commands (bc7_core.cuh) inside one CTA.  A block's owner thread publishes (best error, err(A) of
-    // each run) in entry 15 of its own gathered-pixel array gv -- a two-subset shape has at most 15 pixels, so that entry is
-    // never used by the gathers of these commands -- and the thread that searched subset B answers in entry 15 of the owner's gw.
-    // compact() turns the per-thread "needs subset B" flags into a dense list of owner threads: the first `count` threads of
-    // the CTA take one each, so only ceil(count / 32) warps walk the second subset's trials.
+    // The exchange of the PAIR2 commands (bc7_core.cuh) inside one CTA.  compact() turns the per-thread "wanted classes" masks
+    // into one dense list of owner threads per class, each padded to whole 32-slot chunks; chunk k goes to warp k mod 12, so
+    // only as many warps as there are chunks walk the second subset's trials.  Results travel through entries 8 + class of the
+    // owner's gathered-pixel array gv: subset B is the smaller subset of its partition (at most 8 pixels), so during the task
+    // phase no gather touches entries 8..15 of anybody's array.
     struct BC7CtaExchange
     {
-        F4 *gvBase, *gwBase;
+        enum { kWarps = kBC7Threads / 32, kListSlots = kBC7Threads * 5 + kBC7PairClasses * 32 };
+        F4 *gvBase;
         const uint32_t *rawBase;
-        uint16_t *list;             // [kBC7Threads]
-        uint32_t *warpCounts;       // [kBC7Threads / 32]
+        uint16_t *list;             // [kListSlots]
+        uint16_t *warpCounts;       // [kWarps][kBC7PairClasses]
         uint8_t *flags;             // [kBC7Threads]
         uint32_t tid;
+        int classBase[kBC7PairClasses + 1], classCount[kBC7PairClasses];
 
-        __device__ __forceinline__ void publish(const F4 &d, uint32_t f)
-        {
-            gvBase[15 * kBC7Threads + tid] = d;
-            flags[tid] = (uint8_t)f;
-        }
-        __device__ __forceinline__ int compact(bool need, bool &warpHasTasks)
+        __device__ __forceinline__ void publish(uint32_t f) { flags[tid] = (uint8_t)f; }
+        __device__ __forceinline__ int compact(uint32_t wantMask)
         {
             const uint32_t lane = tid & 31, warp = tid >> 5;
-            const uint32_t ballot = __ballot_sync(0xffffffffu, need);
-            if (lane == 0)
-                warpCounts[warp] = __popc(ballot);
-            __syncthreads();
-            uint32_t base = 0, total = 0;
+            uint32_t ballots[kBC7PairClasses];
 #pragma unroll
-            for (uint32_t k = 0; k < kBC7Threads / 32; k++)
+            for (int c = 0; c < kBC7PairClasses; c++)
             {
-                const uint32_t c = warpCounts[k];
-                base += (k < warp) ? c : 0u;
-                total += c;
+                ballots[c] = __ballot_sync(0xffffffffu, (wantMask >> c) & 1u);
+                if (lane == 0)
+                    warpCounts[warp * kBC7PairClasses + c] = (uint16_t)__popc(ballots[c]);
             }
-            if (need)
-                list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)tid;
             __syncthreads();
-            warpHasTasks = warp * 32 < total;
-            return tid < total ? (int)list[tid] : -1;
+            int pos = 0;
+#pragma unroll
+            for (int c = 0; c < kBC7PairClasses; c++)
+            {
+                uint32_t before = 0, total = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < kWarps; k++)
+                {
+                    const uint32_t n = warpCounts[k * kBC7PairClasses + c];
+                    before += (k < warp) ? n : 0u;
+                    total += n;
+                }
+                classBase[c] = pos;
+                classCount[c] = (int)total;
+                if ((wantMask >> c) & 1u)
+                    list[pos + before + __popc(ballots[c] & ((1u << lane) - 1u))] = (uint16_t)tid;
+                pos += (int)((total + 31u) & ~31u);
+            }
+            classBase[kBC7PairClasses] = pos;
+            __syncthreads();
+            return pos;
         }
-        __device__ __forceinline__ F4 owner_data(int owner) const { return gvBase[15 * kBC7Threads + owner]; }
+        __device__ __forceinline__ int first_slot() const { return (int)tid; }
+        __device__ __forceinline__ int slot_stride() const { return kBC7Threads; }
+        __device__ __forceinline__ bool chunk_in_range(int slot, int total) const { return slot - (int)(tid & 31) < total; }
+        __device__ __forceinline__ void task(int slot, int &cls, int &owner) const
+        {
+            const int chunk = slot - (int)(tid & 31);        // warp-uniform
+            cls = 0;
+#pragma unroll
+            for (int c = 1; c < kBC7PairClasses; c++)
+                cls = (chunk >= classBase[c]) ? c : cls;
+            int base = classBase[0], count = classCount[0];
+#pragma unroll
+            for (int c = 1; c < kBC7PairClasses; c++)
+            {
+                base = (cls == c) ? classBase[c] : base;
+                count = (cls == c) ? classCount[c] : count;
+            }
+            owner = (slot - base < count) ? (int)list[slot] : -1;
+        }
         __device__ __forceinline__ uint32_t owner_flags(int owner) const { return flags[owner]; }
         __device__ __forceinline__ const uint32_t *owner_raw(int owner) const { return rawBase + owner; }
         __device__ __forceinline__ bool task_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
-        __device__ __forceinline__ void post(int owner, const F4 &r) { gwBase[15 * kBC7Threads + owner] = r; }
+        __device__ __forceinline__ void post(int owner, int cls, const F4 &r) { gvBase[(8 + cls) * kBC7Threads + owner] = r; }
         __device__ __forceinline__ void sync() { __syncthreads(); }
-        __device__ __forceinline__ F4 result() const { return gwBase[15 * kBC7Threads + tid]; }
+        __device__ __forceinline__ F4 result(int cls) const { return gvBase[(8 + cls) * kBC7Threads + tid]; }
     };
 
     // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
@@ -181,12 +210,11 @@ namespace
         L.gv = sGv + tid;
         L.gw = sGw + tid;
 
-        __shared__ uint16_t sTaskList[kBC7Threads];
-        __shared__ uint32_t sWarpCounts[kBC7Threads / 32];
+        __shared__ uint16_t sTaskList[BC7CtaExchange::kListSlots];
+        __shared__ uint16_t sWarpCounts[BC7CtaExchange::kWarps * kBC7PairClasses];
         __shared__ uint8_t sOwnerFlags[kBC7Threads];
         BC7CtaExchange ex;
         ex.gvBase = sGv;
-        ex.gwBase = sGw;
         ex.rawBase = sRaw;
         ex.list = sTaskList;
         ex.warpCounts = sWarpCounts;
