@@ -549,8 +549,9 @@ namespace cvttb200
 
     // ---------------------------------------------------------------------------------------------------------
     // EncodeTMode, ETC.cpp:396-647.  isolatedMask: bit px set = pixel is in the isolated cluster.
+    // rendezvous: whether the CTA's warps meet before the table loop (see etc2_encode_block)
     template<bool UNIFORM, bool BT709, int STRIDE, class Vote>
-    CVTT_HD void etc_t_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, Vote &vote, uint32_t isolatedMask, ETCBest &best)
+    CVTT_HD void etc_t_mode(const ETCParams &P, const ETCTables &T, const ETCLane<STRIDE> &L, Vote &vote, uint32_t isolatedMask, ETCBest &best, bool rendezvous = true)
     {
         int isolatedTotal[3] = { 0, 0, 0 }, lineTotal[3] = { 0, 0, 0 }, numIsolated = 0;
         for (int px = 0; px < 16; px++)
@@ -610,7 +611,8 @@ namespace cvttb200
         uint32_t bestSelectors = 0;
         int bestTable = 0, bestLineColor = 0;
 
-        cta_sync();     // keeps the warps of the CTA in the same code region (instruction cache), see DESIGN.md
+        if (rendezvous)
+            cta_sync();     // keeps the warps of the CTA in the same code region (instruction cache), see DESIGN.md
         for (int table = 0; table < 8; table++)
         {
             const int modifier = T.thModifier[table];
@@ -973,19 +975,90 @@ namespace cvttb200
         return true;
     }
 
-    // FindBestDifferentialCombination, ETC.cpp:219-362, for one lane.  winMeta receives the pair to encode (colour | table << 15
-    // per sector), selMeta the attempts whose selectors go with it (they differ only when a transparent sector 0 borrows
-    // sector 1's colour); both stay -1 when no legal pair beats bestErrorIn.
+    // ---- warp-cooperative helpers: in the kernel the 32 lanes of a warp, on the CPU (tests/hostsim) one lane on its own ----
+    CVTT_HD int coop_lane()
+    {
+#if defined(__CUDA_ARCH__)
+        return (int)(threadIdx.x & 31u);
+#else
+        return 0;
+#endif
+    }
+    CVTT_HD int coop_width()
+    {
+#if defined(__CUDA_ARCH__)
+        return 32;
+#else
+        return 1;
+#endif
+    }
+    CVTT_HD uint32_t coop_ballot(bool x)
+    {
+#if defined(__CUDA_ARCH__)
+        return __ballot_sync(0xffffffffu, x);
+#else
+        return x ? 1u : 0u;
+#endif
+    }
+    CVTT_HD float coop_bcast(float v, int src)
+    {
+#if defined(__CUDA_ARCH__)
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        (void)src;
+        return v;
+#endif
+    }
+    CVTT_HD int coop_bcast(int v, int src)
+    {
+#if defined(__CUDA_ARCH__)
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        (void)src;
+        return v;
+#endif
+    }
+    // lexicographic minimum of (e, i) over the lanes; i < 0 marks "no entry" and loses against everything
+    CVTT_HD void coop_min_entry(float &e, int &i)
+    {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+        {
+            const float oe = __shfl_xor_sync(0xffffffffu, e, step);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, step);
+            const bool take = oi >= 0 && (i < 0 || oe < e || (oe == e && oi < i));
+            e = take ? oe : e;
+            i = take ? oi : i;
+        }
+#else
+        (void)e;
+        (void)i;
+#endif
+    }
+
+    // FindBestDifferentialCombination, ETC.cpp:219-362.  winMeta receives the pair to encode (colour | table << 15 per
+    // sector), selMeta the attempts whose selectors go with it (they differ only when a transparent sector 0 borrows sector
+    // 1's colour); both stay -1 when no legal pair beats bestErrorIn.
     //
     // The attempts arrive already filtered: per sector the smallest error of ALL attempts with its colour / table (the first
     // one on ties, in generation order) and, in the scratch arrays, only the kept[sector] attempts with error < bestErrorIn,
     // in generation order -- the only ones the pair search can use.  The differential stages filter while they generate (the
     // block's best error cannot change during that stage), which leaves a fraction of the reference's
     // DifferentialResolveStorage stores and no second pass over them.
+    //
+    // Most blocks are settled by their two best attempts.  The rest -- a few per cent, but with up to 624 attempts per sector
+    // -- need the reference's pair scan: its lists sorted by (error, index), sector 0 walked in that order, the partner of an
+    // entry being the first legal one of sector 1 below the error still allowed.  Done by one lane that is a chain of tens of
+    // thousands of dependent scratch loads on which the whole CTA waits at its next rendezvous, so the warp does it TOGETHER,
+    // one such block after the other: each step of the walk is a "next larger key" selection over sector 0 and a "smallest
+    // legal key" selection over sector 1, both as strided scans with a lexicographic shuffle reduction.  Every lane of the
+    // warp must call this function (the control flow around it is warp-uniform).
     CVTT_HD void etc_find_best_differential_kept(const ETCScratch &S, const int *kept, const float *bestDiffErrors, const uint32_t *bestDiffMeta, bool canIgnore0,
         float bestErrorIn, int *winMeta, int *selMeta, float &winTotal)
     {
         const float blockBestTotalError = bestErrorIn;
+        bool needScan = false;
         if (fadd(bestDiffErrors[0], bestDiffErrors[1]) < blockBestTotalError)
         {
             // with punch-through a fully transparent sector 0 takes the colour of sector 1 and makes any pair legal (ETC.cpp:251-260)
@@ -1001,66 +1074,75 @@ namespace cvttb200
                 winTotal = fadd(bestDiffErrors[0], bestDiffErrors[1]);
             }
             else
+                needScan = true;
+        }
+
+        const int lane = coop_lane(), width = coop_width();
+        for (uint32_t todo = coop_ballot(needScan); todo; todo &= todo - 1)
+        {
+            // the block of lane `owner`: its scratch entries sit (owner - lane) elements from this lane's
+            const int owner = ctz32(todo);
+            const ptrdiff_t shift = (ptrdiff_t)owner - (ptrdiff_t)lane;
+            const float *err = S.drsErr + shift;
+            const uint32_t *meta = S.drsMeta + shift;
+            const int kept0 = coop_bcast(kept[0], owner), kept1 = coop_bcast(kept[1], owner);
+            const float bestDiff1 = coop_bcast(bestDiffErrors[1], owner);
+            float current = coop_bcast(blockBestTotalError, owner);
+            int found0 = -1, found1 = -1;           // metas of the pair found so far (identical on every lane)
+            float lastErr = -1.0f;
+            int lastIdx = -1;
+            for (;;)
             {
-                // The reference sorts both lists by (error, index) and scans pairs.  Equivalent without a sort:
-                // walk sector 0 in that order by repeated "next larger key" selection; for each entry the partner
-                // is the smallest-key entry of sector 1 whose colour makes a legal differential pair.
-                float current = blockBestTotalError;
-                float lastErr = -1.0f;
-                int lastIdx = -1;
-                for (;;)
+                // next entry of sector 0 in (error, index) order
+                float e0 = 0.0f;
+                int i0 = -1;
+                for (int i = lane; i < kept0; i += width)
                 {
-                    int i0 = -1;
-                    float e0 = 0.0f;
-                    uint32_t m0 = 0;
-                    for (int i = 0; i < kept[0]; i++)
+                    const float e = err[(size_t)i * S.stride];
+                    const bool after = (e > lastErr) || (e == lastErr && i > lastIdx);
+                    if (after && (i0 < 0 || e < e0))
                     {
-                        const size_t slot = (size_t)i * S.stride;
-                        const float e = S.drsErr[slot];
-                        const bool after = (e > lastErr) || (e == lastErr && i > lastIdx);
-                        if (after && (i0 < 0 || e < e0))
-                        {
-                            i0 = i;
-                            e0 = e;
-                            m0 = S.drsMeta[slot];
-                        }
-                    }
-                    if (i0 < 0)
-                        break;
-                    lastErr = e0;
-                    lastIdx = i0;
-                    if (e0 >= current)
-                        break;
-                    const float maxError1 = fsub(current, e0);
-                    if (maxError1 < bestDiffErrors[1])
-                        break;
-                    // the scan of sector 1 stops at the first entry with error >= maxError1; before that the first legal one wins
-                    int j1 = -1;
-                    float e1 = 0.0f;
-                    uint32_t m1 = 0;
-                    for (int j = 0; j < kept[1]; j++)
-                    {
-                        const size_t slot = (size_t)(kETCMaxAttempts + j) * S.stride;
-                        const float e = S.drsErr[slot];
-                        if (e < maxError1 && (j1 < 0 || e < e1))
-                        {
-                            const uint32_t m = S.drsMeta[slot];
-                            if (etc_differential_legal((int)(m0 & 0x7fffu), (int)(m & 0x7fffu)))
-                            {
-                                j1 = j;
-                                e1 = e;
-                                m1 = m;
-                            }
-                        }
-                    }
-                    if (j1 >= 0)
-                    {
-                        current = fadd(e0, e1);
-                        winMeta[0] = selMeta[0] = (int)m0;
-                        winMeta[1] = selMeta[1] = (int)m1;
-                        winTotal = current;
+                        i0 = i;
+                        e0 = e;
                     }
                 }
+                coop_min_entry(e0, i0);
+                if (i0 < 0)
+                    break;
+                lastErr = e0;
+                lastIdx = i0;
+                if (e0 >= current)
+                    break;
+                const float maxError1 = fsub(current, e0);
+                if (maxError1 < bestDiff1)
+                    break;
+                const uint32_t m0 = meta[(size_t)i0 * S.stride];
+                // its partner: the smallest (error, index) of sector 1 below maxError1 whose colour makes a legal pair
+                float e1 = 0.0f;
+                int j1 = -1;
+                for (int j = lane; j < kept1; j += width)
+                {
+                    const size_t slot = (size_t)(kETCMaxAttempts + j) * S.stride;
+                    const float e = err[slot];
+                    if (e < maxError1 && (j1 < 0 || e < e1) && etc_differential_legal((int)(m0 & 0x7fffu), (int)(meta[slot] & 0x7fffu)))
+                    {
+                        j1 = j;
+                        e1 = e;
+                    }
+                }
+                coop_min_entry(e1, j1);
+                if (j1 >= 0)
+                {
+                    current = fadd(e0, e1);
+                    found0 = (int)m0;
+                    found1 = (int)meta[(size_t)(kETCMaxAttempts + j1) * S.stride];
+                }
+            }
+            if (lane == owner && found0 >= 0)
+            {
+                winMeta[0] = selMeta[0] = found0;
+                winMeta[1] = selMeta[1] = found1;
+                winTotal = current;
             }
         }
     }
@@ -1073,6 +1155,9 @@ namespace cvttb200
         int bestColors[2] = { 0, 0 }, bestTables[2] = { 0, 0 }, bestFlip = 0, bestD = 0;
         uint32_t bestSelectors[2] = { 0, 0 };
 
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
         for (int flip = 0; flip < 2; flip++)
         {
             int cumulative[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
@@ -1096,7 +1181,11 @@ namespace cvttb200
                 for (int sector = 0; sector < 2; sector++)
                 {
                     const int16_t *potentialOffsets = T.potentialOffsets;
-                    cta_sync();         // one rendezvous per (flip, d, sector): the eight tables run the same code
+                    // One rendezvous where the CTA enters this stage: flips and sectors run the same loop body (the flip loop is
+                    // not unrolled), so the warps stay in the same code without meeting again; measured +1 % against a
+                    // rendezvous per (flip, sector) and before the pair search.
+                    if (flip == 0 && sector == 0 && d == MIN_D)
+                        cta_sync();
                     for (int table = 0; table < 8; table++)
                     {
                         const int numOffsets = *potentialOffsets++;
@@ -1176,7 +1265,6 @@ namespace cvttb200
                 }
                 else
                 {
-                    cta_sync();
                     int winMeta[2] = { -1, -1 }, selMeta[2] = { -1, -1 };
                     float winTotal = 0.0f;
                     etc_find_best_differential_kept(S, kept, bestDiffErrors, bestDiffMeta, false, best.error, winMeta, selMeta, winTotal);
@@ -1644,10 +1732,19 @@ namespace cvttb200
         cta_sync();
         etc_planar<UNIFORM, BT709, STRIDE>(P, L, best);
 
+        // The two T-mode passes (isolated colour = one chroma sector, then the other) are ONE loop body: the warps of the CTA
+        // then need no rendezvous between them to stay in the same code, and a pass's cost grows with its number of line
+        // pixels, which the two passes split between them -- per warp the sum varies far less than either pass.
         uint32_t sectorMask = etc2_chroma_split<UNIFORM, STRIDE>(P, L, 16);
-        etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
-        sectorMask ^= 0xffffu;
-        etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int pass = 0; pass < 2; pass++)
+        {
+            if (pass)
+                sectorMask ^= 0xffffu;
+            etc_t_mode<UNIFORM, BT709, STRIDE>(P, T, L, vote, sectorMask, best, pass == 0);
+        }
         etc_h_mode<UNIFORM, BT709, STRIDE>(P, T, L, S, sectorMask, best);
         etc_etc1<UNIFORM, BT709, 1, STRIDE>(P, T, L, S, best);
 

@@ -4,7 +4,7 @@ import torch, numpy as np
 from convectionkernels_b200 import api, synth
 fmt = sys.argv[1]
 api.init(0)
-n = 151552
+n = 151552 if not fmt.startswith("ETC") else 303104      # ETC: persistent grid of 75776 threads, four tiles per CTA
 if fmt.startswith("BC6H"):
     blocks = synth.image_to_blocks(synth.hdr_ramp_f16(4096, 4096))[:n]
 else:
