@@ -39,34 +39,65 @@ static_assert(sizeof(cvttb200_bc7_fine_tuning) == 285 && sizeof(BC7FineTuningPOD
 
 namespace
 {
-    // One thread per block row (4 pixels).  PIXEL_BYTES = 4 (RGBA8 -> PixelBlockU8) or 8 (RGBA16F -> PixelBlockF16).  Blocks are
-    // laid out like the sample packer does: rows of ceil(width / 32) groups of 8 blocks; coordinates past the edge are clamped,
-    // so the padding blocks of the last group of a row repeat the last column (they take part in the group semantics of the
-    // encoders).  Thread t of a warp handles row (t & 3) of block (t >> 2): the warp's stores are one contiguous 512 B (1 KB)
-    // run of the block array, its loads are four 128 B (256 B) row segments -- whole 32-byte sectors on both sides.
+    // One thread per block row (4 pixels), kTileUnroll rows in flight per thread.  PIXEL_BYTES = 4 (RGBA8 -> PixelBlockU8) or 8
+    // (RGBA16F -> PixelBlockF16).  Blocks are laid out like the sample packer does: rows of ceil(width / 32) groups of 8 blocks;
+    // coordinates past the edge are clamped, so the padding blocks of the last group of a row repeat the last column (they take
+    // part in the group semantics of the encoders).  Thread t of a warp handles row (t & 3) of block (t >> 2): the warp's
+    // stores are one contiguous 512 B (1 KB) run of the block array, its loads are four 128 B (256 B) row segments -- whole
+    // 32-byte sectors on both sides.  A thread issues the loads of all its rows (one CTA-width apart, so every access keeps
+    // that shape) before the first store: with a single 16-byte load in flight per thread the RGBA8 case stayed at 88 % of
+    // the copy bandwidth (long_scoreboard, profiles/r02_misc_kernels.csv).
+    constexpr int kTileUnroll = 4;
+
     template<int PIXEL_BYTES>
     __global__ void __launch_bounds__(256)
     tile_image_kernel(const unsigned char *__restrict__ image, int width, int height, size_t pitch, int blocksPerRow, uint32_t nBlocks, uint4 *__restrict__ blocks, int vectorOK)
     {
-        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const uint32_t b = (uint32_t)(i >> 2);
-        const int r = (int)(i & 3);
-        if (b >= nBlocks)
-            return;
-        const int by = (int)(b / (uint32_t)blocksPerRow), bx = (int)(b % (uint32_t)blocksPerRow);
-        const int x0 = bx * 4, y = min(by * 4 + r, height - 1);
         constexpr int kRowVec = PIXEL_BYTES / 4;      // uint4 per block row
-        uint4 *dst = blocks + ((size_t)b * 4 + r) * kRowVec;
-        const unsigned char *rowPtr = image + (size_t)y * pitch;
-        if (vectorOK && x0 + 4 <= width)
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(rowPtr + (size_t)x0 * PIXEL_BYTES);
+        const uint64_t first = (uint64_t)blockIdx.x * (blockDim.x * kTileUnroll) + threadIdx.x;
+        uint4 v[kTileUnroll][kRowVec];
+        bool fast[kTileUnroll];
 #pragma unroll
-            for (int k = 0; k < kRowVec; k++)
-                dst[k] = __ldg(src + k);
-        }
-        else
+        for (int u = 0; u < kTileUnroll; u++)
         {
+            const uint64_t i = first + (uint64_t)u * blockDim.x;
+            const uint32_t b = (uint32_t)(i >> 2);
+            const int r = (int)(i & 3);
+            fast[u] = false;
+            if (b >= nBlocks)
+                continue;
+            const int by = (int)(b / (uint32_t)blocksPerRow), bx = (int)(b % (uint32_t)blocksPerRow);
+            const int x0 = bx * 4, y = min(by * 4 + r, height - 1);
+            const unsigned char *rowPtr = image + (size_t)y * pitch;
+            if (vectorOK && x0 + 4 <= width)
+            {
+                fast[u] = true;
+                const uint4 *src = reinterpret_cast<const uint4 *>(rowPtr + (size_t)x0 * PIXEL_BYTES);
+#pragma unroll
+                for (int k = 0; k < kRowVec; k++)
+                    v[u][k] = __ldg(src + k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kTileUnroll; u++)
+        {
+            const uint64_t i = first + (uint64_t)u * blockDim.x;
+            const uint32_t b = (uint32_t)(i >> 2);
+            const int r = (int)(i & 3);
+            if (b >= nBlocks)
+                continue;
+            uint4 *dst = blocks + ((size_t)b * 4 + r) * kRowVec;
+            if (fast[u])
+            {
+#pragma unroll
+                for (int k = 0; k < kRowVec; k++)
+                    dst[k] = v[u][k];
+                continue;
+            }
+            // edge blocks (clamped columns) and unaligned images: pixel by pixel
+            const int by = (int)(b / (uint32_t)blocksPerRow), bx = (int)(b % (uint32_t)blocksPerRow);
+            const int x0 = bx * 4, y = min(by * 4 + r, height - 1);
+            const unsigned char *rowPtr = image + (size_t)y * pitch;
             uint32_t row[4 * (PIXEL_BYTES / 4)];
             for (int c = 0; c < 4; c++)
             {
@@ -81,16 +112,16 @@ namespace
     }
 
     // Drops the padding blocks: encoded rows of blocksPerRow blocks -> rows of ceil(width / 4) blocks (the payload order of the
-    // sample's KTX writer).  One thread per 8 output bytes.
+    // sample's KTX writer).  One thread per output block (VEC = uint2 for 8-byte blocks, uint4 for 16-byte blocks).
+    template<class VEC>
     __global__ void __launch_bounds__(256)
-    untile_blocks_kernel(const uint2 *__restrict__ encoded, int blocksPerRow, int realBlocksPerRow, int wordsPerBlock, uint64_t nWords, uint2 *__restrict__ out)
+    untile_blocks_kernel(const VEC *__restrict__ encoded, int blocksPerRow, int realBlocksPerRow, uint64_t nOut, VEC *__restrict__ out)
     {
         const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (i >= nWords)
+        if (i >= nOut)
             return;
-        const uint64_t block = i / (uint64_t)wordsPerBlock, word = i % (uint64_t)wordsPerBlock;
-        const uint64_t row = block / (uint64_t)realBlocksPerRow, col = block % (uint64_t)realBlocksPerRow;
-        out[i] = __ldg(encoded + (row * (uint64_t)blocksPerRow + col) * (uint64_t)wordsPerBlock + word);
+        const uint64_t row = i / (uint64_t)realBlocksPerRow, col = i % (uint64_t)realBlocksPerRow;
+        out[i] = __ldg(encoded + row * (uint64_t)blocksPerRow + col);
     }
 }
 
@@ -546,7 +577,7 @@ int cvttb200_tile_image(int pixelBytes, const void *image, int width, int height
     if (nBlocks > 0xffffff00u)
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "image too large for one call");
     const int vectorOK = ((uintptr_t)image % 16 == 0) && (rowPitchBytes % 16 == 0);
-    const unsigned grid = (unsigned)((nBlocks * 4 + 255) / 256);
+    const unsigned grid = (unsigned)((nBlocks * 4 + 256 * kTileUnroll - 1) / (256 * kTileUnroll));
     cudaStream_t stream = (cudaStream_t)streamPtr;
     if (pixelBytes == 4)
         tile_image_kernel<4><<<grid, 256, 0, stream>>>((const unsigned char *)image, width, height, rowPitchBytes, blocksPerRow, (uint32_t)nBlocks, (uint4 *)blocks, vectorOK);
@@ -564,10 +595,14 @@ int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t bl
     if (!is_device_pointer(encoded) || !is_device_pointer(out))
         return fail(CVTTB200_ERR_BAD_ARGUMENT, "cvttb200_untile_blocks works on device memory");
     const int blocksPerRow = ((width + 31) / 32) * 8, realBlocksPerRow = (width + 3) / 4;
-    const int wordsPerBlock = (int)(blockBytes / 8);
-    const uint64_t nWords = (uint64_t)((height + 3) / 4) * (uint64_t)realBlocksPerRow * (uint64_t)wordsPerBlock;
-    const unsigned grid = (unsigned)((nWords + 255) / 256);
-    untile_blocks_kernel<<<grid, 256, 0, (cudaStream_t)streamPtr>>>((const uint2 *)encoded, blocksPerRow, realBlocksPerRow, wordsPerBlock, nWords, (uint2 *)out);
+    const uint64_t nOut = (uint64_t)((height + 3) / 4) * (uint64_t)realBlocksPerRow;
+    const unsigned grid = (unsigned)((nOut + 255) / 256);
+    if (blockBytes == 16 && (uintptr_t)encoded % 16 == 0 && (uintptr_t)out % 16 == 0)
+        untile_blocks_kernel<uint4><<<grid, 256, 0, (cudaStream_t)streamPtr>>>((const uint4 *)encoded, blocksPerRow, realBlocksPerRow, nOut, (uint4 *)out);
+    else if (blockBytes == 16)
+        untile_blocks_kernel<uint2><<<(unsigned)((nOut * 2 + 255) / 256), 256, 0, (cudaStream_t)streamPtr>>>((const uint2 *)encoded, blocksPerRow * 2, realBlocksPerRow * 2, nOut * 2, (uint2 *)out);
+    else
+        untile_blocks_kernel<uint2><<<grid, 256, 0, (cudaStream_t)streamPtr>>>((const uint2 *)encoded, blocksPerRow, realBlocksPerRow, nOut, (uint2 *)out);
     g_launches++;
     CVTT_CUDA(cudaGetLastError());
     return CVTTB200_OK;
