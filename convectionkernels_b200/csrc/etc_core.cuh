@@ -1,17 +1,20 @@
-// ETC1 / ETC2 RGB / EAC alpha encode search, one 4x4 block per thread (lane = block; see cvtt_common.cuh).
+// ETC1 / ETC2 RGB / ETC2 punch-through / EAC alpha encode search, one 4x4 block per thread (lane = block; see cvtt_common.cuh).
 //
 // What it reproduces (reference elasota/ConvectionKernels, file:line):
-//   ETCComputer::CompressETC2Block            ConvectionKernels_ETC.cpp:1664-1887 (without punch-through)
+//   ETCComputer::CompressETC2Block            ConvectionKernels_ETC.cpp:1664-1887 (opaque and punch-through)
+//   EncodeVirtualTModePunchthrough            :887-1262, CompressETC1PunchthroughBlockInternal :2885-3080,
+//   TestHalfBlockPunchthrough                 :151-217
 //   ETCComputer::EncodePlanar                 :1274-1662
 //   ETCComputer::EncodeTMode / EncodeHMode    :396-647 / :649-885
 //   ETCComputer::CompressETC1BlockInternal    :2624-2882, TestHalfBlock :94-149,
-//   FindBestDifferentialCombination           :219-362 (the scalar sorted search, here per lane without a sort)
+//   FindBestDifferentialCombination           :219-362 (the scalar sorted search, here without a sort and warp-cooperative)
 //   CompressETC2AlphaBlockInternal            :1902-2085, QuantizeETC2Alpha :2366-2411 (8-bit alpha and EAC R11)
 //   EmitTModeBlock / EmitHModeBlock / EmitETC1Block  :2414-2622
 //   tables                                    ConvectionKernels_ETC1.h, ConvectionKernels_ETC2.h, ConvectionKernels_ETC2_Rounding.h
 //
-// Not implemented (rejected by the host with CVTTB200_ERR_UNSUPPORTED): Flags::ETC_UseFakeBT709 and the
-// punch-through variants.
+//   Flags::ETC_UseFakeBT709 / ETC_FakeBT709Accurate  ConvertToFakeBT709 / ResolveHalfBlockFakeBT709Rounding* / ResolveTHFakeBT709Rounding
+//                                             (etc_to_bt709, etc_resolve_half_block_bt709, etc_resolve_th_bt709)
+// Every format and flag of the reference's ETC entry points is implemented.
 //
 // Cross-lane semantics: every AnySet guard of these functions is idempotent except one.  In T
 // mode the candidate list of a lane with fewer unique line colours than the largest count in its group of 8 has a
