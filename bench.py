@@ -19,7 +19,8 @@ prints ONE JSON line:
                 (N = 1 only, bounded steps)
   strong        BASELINE.json configs[4]: ONE 8192x8192 texture on rank 0, 8-block-group ranges scattered over NCCL, encoded,
                 gathered back on rank 0 inside the step (strong scaling; reported at every N so that the curve has its base)
-  latency_8block_ms   one cvtt::Kernels::EncodeBC7-sized call (8 blocks, host buffers) through the C ABI
+  latency_8block_ms   one cvtt::Kernels::EncodeBC7-sized call (8 blocks, host buffers) through the C ABI;
+                latency_ms_by_blocks_per_call gives the same for larger batches
 With N > 1 (torchrun, one process per GPU) every rank encodes its own 4096x4096 texture (weak scaling) and the encoded
 ranges are gathered on rank 0 with one NCCL gather inside the timed step.
 `--impl reference` times the reference's own CPU implementation of the same configuration instead (rank 0 only).
@@ -439,12 +440,13 @@ def measure_strong(job, steps, warmup):
             "sharded_equals_single_gpu": differing == 0, "blocks_compared": n_blocks}
 
 
-def measure_latency(job, calls=30):
-    """One reference-sized call: cvtt::Kernels::EncodeBC7 on 8 blocks with host buffers through the C ABI (wall clock)."""
+def measure_latency(job, n_blocks=8, calls=30):
+    """One call of cvtt::Kernels::EncodeBC7 size (8 blocks) -- or a larger batch -- with host buffers through the C ABI
+    (wall clock, ms per call)."""
     api = job.api
     opt, plan = options_and_plan(api, "BC7")
-    blocks = np.ascontiguousarray(synthetic_blocks("rgba8", job.rank)[4096:4104])
-    out = np.empty((8, 16), np.uint8)
+    blocks = np.ascontiguousarray(synthetic_blocks("rgba8", job.rank)[4096:4096 + n_blocks])
+    out = np.empty((n_blocks, 16), np.uint8)
     for _ in range(3):
         api.encode("BC7", blocks, opt, plan, out=out)
     t0 = time.perf_counter()
@@ -486,6 +488,7 @@ def main():
     others, strong, latency = None, None, None
     if extras:
         latency = measure_latency(job)
+        latency_curve = {str(n): measure_latency(job, n, calls=10) for n in (8, 64, 512, 4096, 32768, 262144)} if job.world == 1 else None
         if job.world == 1:
             others = {}
             for f in OTHER_CONFIGS:
@@ -502,6 +505,8 @@ def main():
                 "roofline": main_rec["roofline"], "cpu_baseline": main_rec["cpu_baseline"]}
         if extras:
             line["latency_8block_ms"] = latency
+            if latency_curve is not None:
+                line["latency_ms_by_blocks_per_call"] = latency_curve      # host buffers, one call of that many blocks
             line["other_configs"] = others if others is not None else "measured at N=1 only"
             line["strong"] = strong
         print(json.dumps(line))
