@@ -72,6 +72,7 @@ namespace cvttb200
         uint64_t mode7RGBPartitionEnabled;
         uint32_t flags;
         int refineRounds;
+        int splitSlices;                   // > 0: small-call launch, cmds starts with this many offsets of independent sub-streams
         const uint32_t *cmds;
     };
 
@@ -1580,11 +1581,15 @@ namespace cvttb200
         CVTT_HD bool warp_any(bool x) const { return x; }
     };
 
-    // PUNCH: Flags::BC7_RespectPunchThrough; vote = the reference's AnySet / AllSet over the 8 blocks of one call
-    template<bool FAST, int STRIDE, bool PUNCH, class Vote, class Exchange>
-    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, Exchange &ex, uint32_t out[4])
+    // A block's best candidate so far as two 128-bit words (the small-call launch searches a block in several CTAs and
+    // reduces their winners; streams with single-colour candidates never take that launch, so `sc` does not travel).
+    struct BC7Candidate
     {
-        BC7Work work;
+        uint32_t a[4], b[4];      // a: error bits, key | mode << 12 | sub << 16 (bit 31: nothing committed), ep[0][0], ep[0][1]; b: ep[1][0..1], ep[2][0..1]
+    };
+
+    CVTT_HD void bc7_work_reset(BC7Work &work)
+    {
         work.error = FLT_MAX;
         work.key = -1;
         work.mode = 0;
@@ -1593,6 +1598,41 @@ namespace cvttb200
             work.ep[s][0] = work.ep[s][1] = 0;
         work.idx[0] = work.idx[1] = work.idx2[0] = work.idx2[1] = 0;
         work.sc[0] = work.sc[1] = work.sc[2] = 0;
+    }
+
+    CVTT_HD void bc7_candidate_pack(const BC7Work &work, BC7Candidate &c)
+    {
+        c.a[0] = as_uint(work.error);
+        c.a[1] = (work.key < 0) ? 0x80000000u : ((uint32_t)work.key | ((uint32_t)work.mode << 12) | ((uint32_t)work.sub << 16));
+        c.a[2] = work.ep[0][0]; c.a[3] = work.ep[0][1];
+        c.b[0] = work.ep[1][0]; c.b[1] = work.ep[1][1]; c.b[2] = work.ep[2][0]; c.b[3] = work.ep[2][1];
+    }
+
+    // lexicographic (error, reference key) minimum: the same winner as one thread walking every trial in any order
+    CVTT_HD void bc7_candidate_merge(BC7Work &work, const BC7Candidate &c)
+    {
+        if (c.a[1] & 0x80000000u)
+            return;
+        const float error = as_float(c.a[0]);
+        const int key = (int)(c.a[1] & 0xfffu);
+        if (error < work.error || (error == work.error && key < work.key))
+        {
+            work.error = error;
+            work.key = key;
+            work.mode = (int)((c.a[1] >> 12) & 0xfu);
+            work.sub = (int)((c.a[1] >> 16) & 0xffu);
+            work.ep[0][0] = c.a[2]; work.ep[0][1] = c.a[3];
+            work.ep[1][0] = c.b[0]; work.ep[1][1] = c.b[1]; work.ep[2][0] = c.b[2]; work.ep[2][1] = c.b[3];
+            work.sc[0] = work.sc[1] = work.sc[2] = 0;
+        }
+    }
+
+    // The search: walks the command stream at `pc` and leaves the block's best (mode, partition / rotation, endpoints) in work.
+    // PUNCH: Flags::BC7_RespectPunchThrough; vote = the reference's AnySet / AllSet over the 8 blocks of one call
+    template<bool FAST, int STRIDE, bool PUNCH, class Vote, class Exchange>
+    CVTT_HD void bc7_search_block(const BC7Params &P, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, Exchange &ex, const uint32_t *pc, BC7Work &work)
+    {
+        bc7_work_reset(work);
 
         // per-(mode, shape) results, indexed by the slot numbers the host assigned: error, endpoint 0, endpoint 1, single-colour marker
         uint32_t res[kBC7MaxSlots][4];
@@ -1605,7 +1645,6 @@ namespace cvttb200
         const bool allowMode7 = lf.anyBlockHasAlpha || (P.mode7RGBPartitionEnabled != 0); // BC67.cpp:1078
         const bool uniform = (P.flags & kFlag_Uniform) != 0;
 
-        const uint32_t *pc = P.cmds;
         for (;;)
         {
             // Every warp of the CTA walks the same command stream; keeping them on the same command keeps the code they
@@ -1847,7 +1886,12 @@ namespace cvttb200
                 bc7_dual_plane<FAST, STRIDE>(P, L.gv, L.gw, mode, rotation, indexSelector, seeds, wr, wSqr, rcpWr, work);
             }
         }
+    }
 
+    // Index selection for the winner and the block's 128 bits
+    template<bool FAST, int STRIDE>
+    CVTT_HD void bc7_finish_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, BC7Work &work, uint32_t out[4])
+    {
         // indexes of the winner
         {
             const int mode = work.mode;
@@ -1920,5 +1964,14 @@ namespace cvttb200
         }
 
         bc7_pack_block(work, T, out);
+    }
+
+    // The whole of BC7Computer::Pack for one block (BC67.cpp:1756-1878)
+    template<bool FAST, int STRIDE, bool PUNCH, class Vote, class Exchange>
+    CVTT_HD void bc7_encode_block(const BC7Params &P, const BC7PackTables &T, const BC7Lane<STRIDE> &L, const BC7LaneFlags &lf, Vote &vote, Exchange &ex, uint32_t out[4])
+    {
+        BC7Work work;
+        bc7_search_block<FAST, STRIDE, PUNCH>(P, L, lf, vote, ex, P.cmds, work);
+        bc7_finish_block<FAST, STRIDE>(P, T, L, work, out);
     }
 }

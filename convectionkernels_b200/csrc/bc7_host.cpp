@@ -1,6 +1,7 @@
 // Host-side BC7 support (see bc7_host.h).
 #include "bc7_host.h"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <string.h>
 
@@ -186,10 +187,152 @@ namespace cvttb200
                 w |= (uint32_t)slots[s] << (8 * s);
             cmds.push_back(w);
         }
+
+        // one PAIR2 command (bc7_core.cuh): the larger subset of the partition is A
+        void emit_pair2(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, int p, bool m1, bool m3, bool m7, bool splitWideRuns)
+        {
+            const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
+            const int shapes[2] = { kBC7Shapes2[p * 2], kBC7Shapes2[p * 2 + 1] };
+            const unsigned masks[2] = { kBC7ShapeMask[shapes[0]], kBC7ShapeMask[shapes[1]] };
+            const int a = popcount16(masks[1]) > popcount16(masks[0]) ? 1 : 0, b = 1 - a;
+            bool listedRGB[2] = { false, false }, listedRGBA[2] = { false, false };
+            for (int k = 0; k < 2; k++)
+            {
+                for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
+                    listedRGB[k] |= (plan.rgbShapeList[i] == shapes[k]);
+                for (int i = 0; i < plan.rgbaNumShapesToEvaluate; i++)
+                    listedRGBA[k] |= (plan.rgbaShapeList[i] == shapes[k]);
+            }
+            const int nRuns = (m1 ? 1 : 0) + (m3 ? 1 : 0) + (m7 ? 1 : 0);
+            cmds.push_back(kCmdPair2 | ((uint32_t)nRuns << 8) | ((uint32_t)listedRGB[a] << 16) | ((uint32_t)listedRGBA[a] << 17) | ((uint32_t)m7 << 18) |
+                           ((uint32_t)listedRGB[b] << 19) | ((uint32_t)listedRGBA[b] << 20) | ((uint32_t)a << 21) | ((uint32_t)(splitWideRuns ? 1 : 0) << 22) | ((uint32_t)p << 24));
+            cmds.push_back(masks[a] | ((uint32_t)popcount16(masks[a]) << 16));
+            cmds.push_back(masks[b] | ((uint32_t)popcount16(masks[b]) << 16));
+            // run word: mode | seeds of subset A << 4 | seeds of subset B << 8
+            if (m1) cmds.push_back(1u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
+            if (m3) cmds.push_back(3u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
+            if (m7) cmds.push_back(7u | ((uint32_t)std::min<int>(spRGBA[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGBA[shapes[b]], 4) << 8));
+        }
     }
 
-    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, bool pairCommands)
+    // kBC7StreamSplit: the stream for SMALL calls.  The search of a block is dealt out to `slices` CTAs (on as many SMs) in
+    // independent units -- mode 6, every mode-4/5 rotation, every two-subset partition (one PAIR2 command), every three-subset
+    // partition (its three shapes searched partition by partition through recycled slots, so that no unit reads another
+    // unit's results; shapes shared between partitions are searched once per partition that uses them).  Units go longest
+    // first to the least loaded slice.  Layout: cmds[s] = offset of slice s's sub-stream (each ends with END), s < slices.
+    // The launch reduces the slices' winners by (error, reference key): bc7_candidate_merge.
+    static int compile_split(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, int slices)
     {
+        struct Unit { int cost, kind; std::vector<uint32_t> words; };      // kind: 0 mode 6, 1 modes 4 / 5, 2 three subsets, 3 two subsets
+        std::vector<Unit> units;
+        const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
+        // trial passes of one shape: (parity combinations, two per pass) x seeds
+        auto passes = [](int mode, int seeds) { seeds = std::min(seeds, 4); return mode == 2 ? (seeds + 1) / 2 : (mode == 1 ? seeds : 2 * seeds); };
+
+        if (plan.mode6Enabled && spRGBA[0])
+        {
+            Unit u;
+            std::vector<Run> runs(1, Run{ 6, spRGBA[0], 0 });
+            emit_shape(u.words, plan, 0, runs);
+            const int slots[1] = { 0 };
+            emit_eval(u.words, 6, 0, 1, slots);
+            u.cost = 20 * passes(6, spRGBA[0]) + 16;
+            u.kind = 0;
+            units.push_back(u);
+        }
+        for (int mode = 4; mode <= 5; mode++)
+            for (int rotation = 0; rotation < 4; rotation++)
+                for (int isel = 0; isel < (mode == 4 ? 2 : 1); isel++)
+                {
+                    const int seeds = std::min<int>(4, mode == 4 ? plan.mode4SP[rotation][isel] : plan.mode5SP[rotation]);
+                    if (seeds <= 0)
+                        continue;
+                    Unit u;
+                    u.words.push_back(kCmdDual | ((uint32_t)mode << 8) | ((uint32_t)rotation << 16) | ((uint32_t)isel << 20) | ((uint32_t)seeds << 24));
+                    u.cost = 16 * 2 * seeds + 16;
+                    u.kind = 1;
+                    units.push_back(u);
+                }
+        for (int p = 0; p < 64; p++)
+        {
+            const int shapes[2] = { kBC7Shapes2[p * 2], kBC7Shapes2[p * 2 + 1] };
+            const bool rgbSearched = spRGB[shapes[0]] && spRGB[shapes[1]];
+            const bool m1 = ((plan.mode1PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m3 = ((plan.mode3PartitionEnabled >> p) & 1) && rgbSearched;
+            const bool m7 = spRGBA[shapes[0]] && spRGBA[shapes[1]];
+            if (!m1 && !m3 && !m7)
+                continue;
+            Unit u;
+            emit_pair2(u.words, plan, p, m1, m3, m7, kBC7SplitWideRuns);
+            u.cost = 16;
+            u.kind = 3;
+            for (int k = 0; k < 2; k++)
+                u.cost += popcount16(kBC7ShapeMask[shapes[k]]) * ((m1 ? passes(1, spRGB[shapes[k]]) : 0) + (m3 ? passes(3, spRGB[shapes[k]]) : 0) + (m7 ? passes(7, spRGBA[shapes[k]]) : 0));
+            units.push_back(u);
+        }
+        for (int p = 0; p < 64; p++)
+        {
+            const bool searched = spRGB[kBC7Shapes3[p * 3]] && spRGB[kBC7Shapes3[p * 3 + 1]] && spRGB[kBC7Shapes3[p * 3 + 2]];
+            const bool m0 = p < 16 && ((plan.mode0PartitionEnabled >> p) & 1) && searched;
+            const bool m2 = ((plan.mode2PartitionEnabled >> p) & 1) && searched;
+            if (!m0 && !m2)
+                continue;
+            Unit u;
+            u.cost = 24;
+            u.kind = 2;
+            int slots0[3], slots2[3];
+            for (int k = 0; k < 3; k++)
+            {
+                const int shape = kBC7Shapes3[p * 3 + k];
+                std::vector<Run> runs;
+                if (m0) runs.push_back(Run{ 0, spRGB[shape], slots0[k] = 6 + 2 * k });
+                if (m2) runs.push_back(Run{ 2, spRGB[shape], slots2[k] = 7 + 2 * k });
+                emit_shape(u.words, plan, shape, runs);
+                u.cost += popcount16(kBC7ShapeMask[shape]) * ((m0 ? passes(0, spRGB[shape]) : 0) + (m2 ? passes(2, spRGB[shape]) : 0));
+            }
+            if (m0) emit_eval(u.words, 0, p, 3, slots0);
+            if (m2) emit_eval(u.words, 2, p, 3, slots2);
+            units.push_back(u);
+        }
+
+        // Longest unit first onto the least loaded slice.  Within a slice the cheap one-subset and three-subset units go first:
+        // they give the block an error to beat, which lets the PAIR2 commands behind them drop second subsets.  (Starting
+        // every slice with a mode-6 search of its own for the same reason was measured: no gain at 3 slices, 15 % slower at 48.)
+        std::vector<size_t> order(units.size());
+        for (size_t i = 0; i < order.size(); i++)
+            order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return units[a].cost > units[b].cost; });
+        std::vector<int> load((size_t)slices, 0);
+        std::vector<std::vector<size_t> > assigned((size_t)slices);
+        for (size_t k = 0; k < order.size(); k++)
+        {
+            const Unit &u = units[order[k]];
+            const size_t slice = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[slice] += u.cost;
+            assigned[slice].push_back(order[k]);
+        }
+        std::vector<std::vector<uint32_t> > streams((size_t)slices);
+        for (size_t s = 0; s < (size_t)slices; s++)
+        {
+            std::stable_sort(assigned[s].begin(), assigned[s].end(), [&](size_t a, size_t b) { return units[a].kind < units[b].kind; });
+            for (size_t k = 0; k < assigned[s].size(); k++)
+                streams[s].insert(streams[s].end(), units[assigned[s][k]].words.begin(), units[assigned[s][k]].words.end());
+        }
+        cmds.assign((size_t)slices, 0u);
+        for (size_t s = 0; s < (size_t)slices; s++)
+        {
+            cmds[s] = (uint32_t)cmds.size();
+            cmds.insert(cmds.end(), streams[s].begin(), streams[s].end());
+            cmds.push_back(kCmdEnd);
+        }
+        return 12;
+    }
+
+    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, int form, int slices)
+    {
+        if (form == kBC7StreamSplit)
+            return compile_split(plan, cmds, std::max(1, slices));
+        const bool pairCommands = (form == kBC7StreamPair);
         cmds.clear();
         const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
         int maxSlot = 0;
@@ -277,25 +420,7 @@ namespace cvttb200
                 continue;
             if (pairCommands)
             {
-                const unsigned masks[2] = { kBC7ShapeMask[shapes[0]], kBC7ShapeMask[shapes[1]] };
-                const int a = popcount16(masks[1]) > popcount16(masks[0]) ? 1 : 0, b = 1 - a;
-                bool listedRGB[2] = { false, false }, listedRGBA[2] = { false, false };
-                for (int k = 0; k < 2; k++)
-                {
-                    for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
-                        listedRGB[k] |= (plan.rgbShapeList[i] == shapes[k]);
-                    for (int i = 0; i < plan.rgbaNumShapesToEvaluate; i++)
-                        listedRGBA[k] |= (plan.rgbaShapeList[i] == shapes[k]);
-                }
-                const int nRuns = (m1 ? 1 : 0) + (m3 ? 1 : 0) + (m7 ? 1 : 0);
-                cmds.push_back(kCmdPair2 | ((uint32_t)nRuns << 8) | ((uint32_t)listedRGB[a] << 16) | ((uint32_t)listedRGBA[a] << 17) | ((uint32_t)m7 << 18) |
-                               ((uint32_t)listedRGB[b] << 19) | ((uint32_t)listedRGBA[b] << 20) | ((uint32_t)a << 21) | ((uint32_t)(kBC7SplitWideRuns ? 1 : 0) << 22) | ((uint32_t)p << 24));
-                cmds.push_back(masks[a] | ((uint32_t)popcount16(masks[a]) << 16));
-                cmds.push_back(masks[b] | ((uint32_t)popcount16(masks[b]) << 16));
-                // run word: mode | seeds of subset A << 4 | seeds of subset B << 8
-                if (m1) cmds.push_back(1u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
-                if (m3) cmds.push_back(3u | ((uint32_t)std::min<int>(spRGB[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapes[b]], 4) << 8));
-                if (m7) cmds.push_back(7u | ((uint32_t)std::min<int>(spRGBA[shapes[a]], 4) << 4) | ((uint32_t)std::min<int>(spRGBA[shapes[b]], 4) << 8));
+                emit_pair2(cmds, plan, p, m1, m3, m7, kBC7SplitWideRuns);
                 continue;
             }
             for (int s = 0; s < 2; s++)

@@ -14,8 +14,12 @@ namespace cvttb200
     // BC7EncodingPlan::BC7EncodingPlan(), ConvectionKernels.h:166-198
     void bc7_plan_default(BC7PlanPOD &plan);
 
-    // Flattens a plan into SHAPE / EVAL / DUAL commands (see bc7_core.cuh).  Returns the number of result slots used.
-    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, bool pairCommands);
+    // Flattens a plan into the kernel's command stream (see bc7_core.cuh).  Returns the number of result slots used.
+    //   kBC7StreamPlain  SHAPE / EVAL / DUAL only (the kernels with per-trial group votes or single-colour candidates)
+    //   kBC7StreamPair   PAIR2 commands for the two-subset modes: second subsets as compacted tasks of the CTA
+    //   kBC7StreamSplit  small calls: `slices` independent sub-streams behind a table of their offsets (PAIR2 commands too)
+    enum { kBC7StreamPlain = 0, kBC7StreamPair = 1, kBC7StreamSplit = 2 };
+    int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, int form, int slices = 0);
 
     // Fills everything of BC7Params except `cmds`.  rcpN[n] must hold the host's _mm_rcp_ps((float)n), n = 0..16.
     void bc7_fill_params(BC7Params &P, const OptionsPOD &options, const BC7PlanPOD &plan, const float rcpN[17]);

@@ -2,6 +2,8 @@
 // Built with -fmad=false (numerical contract); see build.py.
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -16,6 +18,10 @@ namespace
 {
     constexpr int kBC7Threads = 384;     // 12 warps = 48 reference groups per CTA, one CTA per SM
     constexpr int kBC7CtasPerSM = 1;
+    constexpr int kBC7FinishThreads = 128;
+    // Small-call launch: slice counts the streams are compiled for.  The largest one whose grid fits one wave of the 148 SMs
+    // is taken; calls too large for the smallest take the normal launch.
+    constexpr int kBC7SliceChoices[] = { 144, 48, 24, 12, 6, 3 };
     // per thread: 16 packed pixels + 16 gathered biased pixels + 16 gathered pre-weighted pixels
     constexpr size_t kBC7SmemBytes = (size_t)kBC7Threads * 16 * (sizeof(uint32_t) + 2 * sizeof(F4));
 
@@ -182,7 +188,7 @@ namespace
     template<bool FAST, bool PUNCH>
     __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
     bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
-                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists)
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint4 *__restrict__ candidates)
     {
         extern __shared__ __align__(16) unsigned char smem[];
         F4 *sGv = reinterpret_cast<F4 *>(smem);
@@ -193,17 +199,32 @@ namespace
 
         // warp -> (class, four groups of that class); the expensive classes go first so that the tail of the launch is
         // filled by the cheap opaque warps
-        const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
-        const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
+        // Small-call launch (P.splitSlices > 0, launch_bc7): blockIdx.y = the slice of the search this CTA runs for its blocks
+        // (the smallest calls skip the classification: counts == nullptr, groups in call order); the winners of the slices go to `candidates` and bc7_finish_kernel
+        // reduces them.  All warps of a CTA still walk one stream, so they stay in step as in the normal launch.
+        const bool split = P.splitSlices > 0;
         uint32_t warp = blockIdx.x * (kBC7Threads / 32) + (tid >> 5);
-        uint32_t cls, clsCount;
-        if (warp < w1) { cls = 1; clsCount = n1; }
-        else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
-        else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
-        else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
-        const uint32_t slot = warp * 4 + (lane >> 3);
-        const bool active = slot < clsCount;
-        const uint32_t block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
+        bool active;
+        uint32_t block;
+        if (counts == nullptr)
+        {
+            const uint32_t group = warp * 4 + (lane >> 3);
+            active = group < nGroups;
+            block = active ? group * 8 + (lane & 7) : 0;
+        }
+        else
+        {
+            const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
+            const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
+            uint32_t cls, clsCount;
+            if (warp < w1) { cls = 1; clsCount = n1; }
+            else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
+            else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
+            else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
+            const uint32_t slot = warp * 4 + (lane >> 3);
+            active = slot < clsCount;
+            block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
+        }
 
         BC7Lane<kBC7Threads> L;
         L.raw = sRaw + tid;
@@ -268,21 +289,76 @@ namespace
         lf.warpHasWork = __any_sync(0xffffffffu, active);
         lf.warpAnyMode7 = __any_sync(0xffffffffu, active && mode7);
 
-        uint32_t o[4];
+        BC7Work work;
+        const uint32_t *pc = split ? P.cmds + __ldg(P.cmds + blockIdx.y) : P.cmds;
         if (PUNCH)
         {
             SegmentVote vote;
             vote.segMask = segMask;
-            bc7_encode_block<FAST, kBC7Threads, true>(P, c_bc7PackTables, L, lf, vote, ex, o);
+            bc7_search_block<FAST, kBC7Threads, true>(P, L, lf, vote, ex, pc, work);
         }
         else
         {
             BC7NoVote vote;
-            bc7_encode_block<FAST, kBC7Threads, false>(P, c_bc7PackTables, L, lf, vote, ex, o);
+            bc7_search_block<FAST, kBC7Threads, false>(P, L, lf, vote, ex, pc, work);
         }
 
+        if (split)
+        {
+            if (active)
+            {
+                BC7Candidate c;
+                bc7_candidate_pack(work, c);
+                uint4 *dst = candidates + ((size_t)blockIdx.y * nGroups * 8 + block) * 2;
+                dst[0] = make_uint4(c.a[0], c.a[1], c.a[2], c.a[3]);
+                dst[1] = make_uint4(c.b[0], c.b[1], c.b[2], c.b[3]);
+            }
+            return;
+        }
+        uint32_t o[4];
+        bc7_finish_block<FAST, kBC7Threads>(P, c_bc7PackTables, L, work, o);
         if (active)
             out[block] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+
+    // Second kernel of the small-call launch: one thread per block takes the (error, reference key) minimum of the slices'
+    // winners, selects the winner's indexes and packs the block.
+    template<bool FAST>
+    __global__ void __launch_bounds__(kBC7FinishThreads)
+    bc7_finish_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks, const uint4 *__restrict__ candidates)
+    {
+        __shared__ uint32_t sRaw[16 * kBC7FinishThreads];
+        const uint32_t tid = threadIdx.x, block = blockIdx.x * kBC7FinishThreads + tid;
+        if (block >= nBlocks)
+            return;
+        const uint4 *src = in + (size_t)block * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const uint4 v = __ldg(src + q);
+            sRaw[(q * 4 + 0) * kBC7FinishThreads + tid] = v.x;
+            sRaw[(q * 4 + 1) * kBC7FinishThreads + tid] = v.y;
+            sRaw[(q * 4 + 2) * kBC7FinishThreads + tid] = v.z;
+            sRaw[(q * 4 + 3) * kBC7FinishThreads + tid] = v.w;
+        }
+        BC7Lane<kBC7FinishThreads> L;
+        L.raw = sRaw + tid;
+        L.gv = nullptr;
+        L.gw = nullptr;
+        BC7Work work;
+        bc7_work_reset(work);
+        for (int s = 0; s < P.splitSlices; s++)
+        {
+            const uint4 *c4 = candidates + ((size_t)s * nBlocks + block) * 2;
+            const uint4 a = __ldg(c4), b = __ldg(c4 + 1);
+            BC7Candidate c;
+            c.a[0] = a.x; c.a[1] = a.y; c.a[2] = a.z; c.a[3] = a.w;
+            c.b[0] = b.x; c.b[1] = b.y; c.b[2] = b.z; c.b[3] = b.w;
+            bc7_candidate_merge(work, c);
+        }
+        uint32_t o[4];
+        bc7_finish_block<FAST, kBC7FinishThreads>(P, c_bc7PackTables, L, work, o);
+        out[block] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -320,19 +396,20 @@ namespace cvttb200
     }
 
     // caller holds ctx.planMutex and has made ctx.device current
-    static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, bool pairCommands, const uint32_t **dCmds)
+    // form: kBC7Stream* | slices << 8
+    static int get_plan_commands(DeviceContext &ctx, const BC7PlanPOD &plan, int form, const uint32_t **dCmds)
     {
         for (size_t i = 0; i < ctx.plans.size(); i++)
-            if (ctx.plans[i].pairCommands == pairCommands && memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
+            if (ctx.plans[i].form == form && memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
             {
                 *dCmds = ctx.plans[i].dCmds;
                 return CVTTB200_OK;
             }
         std::vector<uint32_t> cmds;
-        const int slots = bc7_compile_plan(plan, cmds, pairCommands);
+        const int slots = bc7_compile_plan(plan, cmds, form & 0xff, form >> 8);
         if (slots > kBC7MaxSlots)
             return fail(CVTTB200_ERR_BAD_ARGUMENT, "BC7 plan needs more result slots than the kernel provides");
-        if (ctx.plans.size() >= 16)
+        if (ctx.plans.size() >= 32)
         {
             // every launch that reads a cached plan was enqueued under planMutex, so after this synchronisation no kernel can
             // still be reading the evicted command stream
@@ -342,7 +419,7 @@ namespace cvttb200
         }
         PlanCacheEntry entry;
         entry.plan = plan;
-        entry.pairCommands = pairCommands;
+        entry.form = form;
         entry.dCmds = nullptr;
         if (!ctx.setupStream)
             CVTT_CUDA(cudaStreamCreateWithFlags(&ctx.setupStream, cudaStreamNonBlocking));
@@ -374,39 +451,92 @@ namespace cvttb200
         // PAIR2 commands hand a block's second subset to another thread; the variants whose trials vote inside the block's
         // group (BC7_RespectPunchThrough) or return more than endpoints (BC7_TrySingleColor) keep the plain command stream
         const bool pairCommands = (options.flags & (kFlag_BC7_RespectPunchThrough | kFlag_BC7_TrySingleColor)) == 0;
+        const uint32_t nGroups = (uint32_t)(nBlocks / 8);
+        const unsigned ctaWarps = kBC7Threads / 32;
+        const bool fast = (options.flags & kFlag_BC7_FastIndexing) != 0, punch = (options.flags & kFlag_BC7_RespectPunchThrough) != 0;
+
+        // Small calls (the reference's own call is 8 blocks).  In the normal launch one warp walks the whole search for its 32
+        // blocks, 3.6 ms whatever the size of the call, and a call of fewer than 148 x 12 x 32 blocks leaves SMs empty.  When
+        // the call's CTAs times a slice count fit one wave, the search of every block is instead dealt out to that many
+        // CTAs (blockIdx.y; kBC7StreamSplit sub-streams, same blocks, disjoint trials) and bc7_finish_kernel takes the
+        // (error, reference key) minimum of their winners -- the same block, since the order of the trials is free.
+        static const long splitOverride = getenv("CVTTB200_BC7_SPLIT") ? atol(getenv("CVTTB200_BC7_SPLIT")) : -1;      // A/B: 0 = never, n = n slices
+        // The small-call launch takes its groups in call order: the classification pre-pass brings up to three more partially
+        // filled warps, which costs more slices at the CTA-count steps than same-class warps gain (measured both ways).
+        const unsigned plainWarps = (nGroups + 3) / 4, classWarps = nGroups / 4 + 3;
+        int slices = 0;
+        if (pairCommands && nGroups > 0)
+        {
+            if (splitOverride > 0)
+                slices = (int)splitOverride;
+            else if (splitOverride < 0)
+                for (int k = 0; k < (int)(sizeof(kBC7SliceChoices) / sizeof(kBC7SliceChoices[0])) && !slices; k++)
+                    if ((plainWarps + ctaWarps - 1) / ctaWarps * (unsigned)kBC7SliceChoices[k] <= (unsigned)ctx.numSMs)
+                        slices = kBC7SliceChoices[k];
+        }
+        const bool classify = !slices;
+        P.splitSlices = slices;
+        const int form = slices ? (kBC7StreamSplit | (slices << 8)) : (pairCommands ? kBC7StreamPair : kBC7StreamPlain);
         const uint32_t *dCmds = nullptr;
-        int rc = get_plan_commands(ctx, plan, pairCommands, &dCmds);
+        int rc = get_plan_commands(ctx, plan, form, &dCmds);
         if (rc != CVTTB200_OK)
             return rc;
         P.cmds = dCmds;
 
-        // stream-ordered scratch for the group classification: counts[4] then lists[3][nGroups]
-        const uint32_t nGroups = (uint32_t)(nBlocks / 8);
-        uint32_t *dScratch = nullptr;
-        rc = pool_alloc(ctx, (void **)&dScratch, (4 + 3 * (size_t)nGroups) * sizeof(uint32_t), stream);
+        // stream-ordered scratch: group classification (counts[4] then lists[3][nGroups]), then the slices' winners
+        const size_t classifyBytes = classify ? (4 + 3 * (size_t)nGroups) * sizeof(uint32_t) : 0;
+        const size_t candOffset = (classifyBytes + 15) & ~(size_t)15;
+        unsigned char *dScratchBytes = nullptr;
+        rc = pool_alloc(ctx, (void **)&dScratchBytes, candOffset + (size_t)slices * nBlocks * 2 * sizeof(uint4) + 16, stream);
         if (rc != CVTTB200_OK)
             return rc;
-        CVTT_CUDA(cudaMemsetAsync(dScratch, 0, 4 * sizeof(uint32_t), stream));
-        bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
-        g_launches++;
+        uint32_t *dScratch = classify ? (uint32_t *)dScratchBytes : nullptr;
+        uint4 *dCand = (uint4 *)(dScratchBytes + candOffset);
+        if (classify)
+        {
+            CVTT_CUDA(cudaMemsetAsync(dScratch, 0, 4 * sizeof(uint32_t), stream));
+            bc7_classify_kernel<<<(unsigned)((nBlocks + 255) / 256), 256, 0, stream>>>((const uint4 *)dIn, (uint32_t)nBlocks, nGroups, dScratch, dScratch + 4);
+            g_launches++;
+        }
+        const uint32_t *dCounts = dScratch, *dLists = classify ? dScratch + 4 : nullptr;
+        const unsigned warps = classify ? classWarps : plainWarps;
+        const unsigned ctas = (warps + ctaWarps - 1) / ctaWarps;
+
+        if (slices)
+        {
+            const dim3 grid(ctas, (unsigned)slices);
+            const unsigned finishGrid = (unsigned)((nBlocks + kBC7FinishThreads - 1) / kBC7FinishThreads);
+            if (fast)
+            {
+                bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, nullptr, nGroups, dCounts, dLists, dCand);
+                bc7_finish_kernel<true><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks, dCand);
+            }
+            else
+            {
+                bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, nullptr, nGroups, dCounts, dLists, dCand);
+                bc7_finish_kernel<false><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks, dCand);
+            }
+            g_launches += 2;
+            CVTT_CUDA(cudaFreeAsync(dScratchBytes, stream));
+            CVTT_CUDA(cudaGetLastError());
+            return CVTTB200_OK;
+        }
 
         // at most three partially filled warps (one per class).  Two ways of avoiding the partial last wave were measured and
         // dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
         // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
         // 1 048 576 blocks, 3 % slower at 524 288).
-        const unsigned warps = nGroups / 4 + 3;
-        const unsigned grid = (warps + kBC7Threads / 32 - 1) / (kBC7Threads / 32);
-        const bool fast = (options.flags & kFlag_BC7_FastIndexing) != 0, punch = (options.flags & kFlag_BC7_RespectPunchThrough) != 0;
+        const unsigned grid = ctas;
         if (fast && !punch)
-            bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+            bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
         else if (!fast && !punch)
-            bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+            bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
         else if (fast)
-            bc7_encode_kernel<true, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+            bc7_encode_kernel<true, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
         else
-            bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4);
+            bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
         g_launches++;
-        CVTT_CUDA(cudaFreeAsync(dScratch, stream));
+        CVTT_CUDA(cudaFreeAsync(dScratchBytes, stream));
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;
     }

@@ -27,7 +27,7 @@ namespace cvttb200
     struct PlanCacheEntry
     {
         BC7PlanPOD plan;
-        bool pairCommands;                            // which of the two command-stream forms (bc7_compile_plan)
+        int form;                                     // which command-stream form (bc7_compile_plan: plain, pair, split)
         uint32_t *dCmds;
     };
 

@@ -2,6 +2,7 @@
 // so the kernel logic can be checked against the oracle in the GPU-less dev container.  It emulates the
 // kernel's warp of 32 lanes = 4 reference groups; it is NOT part of the product library and the product never
 // falls back to it.
+#include <stdlib.h>
 #include <thread>
 #include <vector>
 #include <xmmintrin.h>
@@ -26,7 +27,28 @@ namespace
         uint32_t o[4];
         BC7SoloExchange ex;                 // PAIR2 commands: the lane searches its own second subsets
         ex.raw = raw;
-        if (fast)
+        if (P.splitSlices > 0)
+        {
+            // the small-call launch: one search per slice (a CTA each in the kernel), winners through the candidate
+            // records, then bc7_finish_kernel's reduction
+            BC7Work work, best;
+            bc7_work_reset(best);
+            for (int s = 0; s < P.splitSlices; s++)
+            {
+                if (fast)
+                    bc7_search_block<true, 1, PUNCH>(P, L, lf, vote, ex, P.cmds + P.cmds[s], work);
+                else
+                    bc7_search_block<false, 1, PUNCH>(P, L, lf, vote, ex, P.cmds + P.cmds[s], work);
+                BC7Candidate c;
+                bc7_candidate_pack(work, c);
+                bc7_candidate_merge(best, c);
+            }
+            if (fast)
+                bc7_finish_block<true, 1>(P, T, L, best, o);
+            else
+                bc7_finish_block<false, 1>(P, T, L, best, o);
+        }
+        else if (fast)
             bc7_encode_block<true, 1, PUNCH>(P, T, L, lf, vote, ex, o);
         else
             bc7_encode_block<false, 1, PUNCH>(P, T, L, lf, vote, ex, o);
@@ -44,12 +66,15 @@ extern "C" int hostsim_encode_bc7(const uint8_t *blocks, size_t nBlocks, uint8_t
     std::vector<uint32_t> cmds;
     // the same choice of command stream as launch_bc7 makes
     const bool pairCommands = (options->flags & (kFlag_BC7_RespectPunchThrough | kFlag_BC7_TrySingleColor)) == 0;
-    int slots = bc7_compile_plan(*plan, cmds, pairCommands);
+    // CVTT_HOSTSIM_SPLIT=n: the small-call launch with n slices
+    const int slices = (pairCommands && getenv("CVTT_HOSTSIM_SPLIT")) ? atoi(getenv("CVTT_HOSTSIM_SPLIT")) : 0;
+    int slots = bc7_compile_plan(*plan, cmds, slices > 0 ? kBC7StreamSplit : (pairCommands ? kBC7StreamPair : kBC7StreamPlain), slices);
     if (slots > kBC7MaxSlots)
         return -2;
     BC7Params P;
     bc7_fill_params(P, *options, *plan, rcpN);
     P.cmds = cmds.data();
+    P.splitSlices = slices > 0 ? slices : 0;
     const BC7PackTables &T = bc7_pack_tables();
     const bool fast = (options->flags & kFlag_BC7_FastIndexing) != 0;
 

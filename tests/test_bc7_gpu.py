@@ -168,3 +168,51 @@ def test_full_size_properties(oracle):
 def test_two_lane_division_is_ieee():
     """f2_div (the packed reciprocal / Newton / remainder sequence of cvtt_common.cuh) against __fdiv_rn on 2^29 operand pairs"""
     assert api.selftest(samples=1 << 28, seed=7) == 0
+
+
+@pytest.mark.parametrize("n", [8, 16, 40, 264, 1152, 1160, 2312, 4616, 9224, 18816, 18824])
+def test_small_calls_take_the_split_launch_and_match_the_reference(reference, n):
+    """Calls of up to 18 816 blocks take the small-call launch: the search of every block dealt out to 48 / 24 / 12 / 6 / 3
+    CTAs (whichever still fits one wave) and the winners reduced by bc7_finish_kernel -- the reference's own call size, 8
+    blocks, included; 18 824 is the first size of the normal launch.  Bit-exact either way."""
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(512, 1024, seed=77))[:n]
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    want = reference.encode("BC7", blocks, _opt_bytes(o), np.frombuffer(p.tobytes(), np.uint8), threads=0)
+    got = api.EncodeBC7(blocks, o, p)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+@pytest.mark.parametrize("flags,quality", [(0x208, 100), (0x008, 37), (0x000, 100), (0x000, 1)])
+def test_small_calls_other_options(reference, flags, quality):
+    """the small-call launch under Uniform | FastIndexing, FastIndexing with a sparse plan, slow indexing, the sparsest plan"""
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(128, 256, seed=78))[:1024]
+    o, p = api.Options(), api.BC7EncodingPlan()
+    o.flags = flags
+    api.ConfigureBC7EncodingPlanFromQuality(p, quality)
+    want = reference.encode("BC7", blocks, _opt_bytes(o), np.frombuffer(p.tobytes(), np.uint8), threads=0)
+    got = api.EncodeBC7(blocks, o, p)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
+def test_small_call_latency_beats_one_reference_thread(reference):
+    """an unmodified caller's 8-block cvtt::Kernels::EncodeBC7 through the library must not be slower than the reference on one
+    core (it was 2x slower before the small-call launch)"""
+    import time
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(64, 64, seed=5))[:8]
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    ob, pb = _opt_bytes(o), np.frombuffer(p.tobytes(), np.uint8)
+    out = np.empty((8, 16), np.uint8)
+    for _ in range(3):
+        api.encode("BC7", blocks, o, p, out=out)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        api.encode("BC7", blocks, o, p, out=out)
+    ours = (time.perf_counter() - t0) / 20
+    reference.encode("BC7", blocks, ob, pb, threads=1)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        reference.encode("BC7", blocks, ob, pb, threads=1)
+    ref = (time.perf_counter() - t0) / 5
+    assert ours < ref, "8-block call: %.2f ms here, %.2f ms for the reference on one core" % (ours * 1e3, ref * 1e3)

@@ -109,6 +109,18 @@ def test_device_logic_on_cpu_matches_golden(hostsim, name):
     assert (got == g["expected"]).all(), first_mismatch(g["expected"], got)
 
 
+@pytest.mark.parametrize("name,slices", [("bc7_mixed_q100", 48), ("bc7_mixed_q100", 3), ("bc7_random_q40", 24), ("bc7_random_refine3_weights", 12),
+                                         ("bc7_random_defaultplan", 6), ("bc7_random_defaultplan", 200)])
+def test_small_call_stream_gives_the_same_blocks(hostsim, monkeypatch, name, slices):
+    """kBC7StreamSplit, the sub-streams of the small-call launch (independent units dealt out to `slices` CTAs, three-subset
+    shapes searched per partition, winners merged through the candidate records): same block, because the winner is a
+    lexicographic (error, reference key) minimum whatever the order.  200 slices: more slices than units, some stay empty."""
+    g = load_golden(name)
+    monkeypatch.setenv("CVTT_HOSTSIM_SPLIT", str(slices))
+    got = _hostsim_encode(hostsim, g["blocks"], g["options"], g["plan"], g["rcp"])
+    assert (got == g["expected"]).all(), first_mismatch(g["expected"], got)
+
+
 def test_device_logic_warp_skips_do_not_change_results(hostsim):
     """warp-level 'does any lane need this' skips are pure work avoidance"""
     g = load_golden("bc7_mixed_q100")

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-convectionkernels_b200/_build/lane_model | tee gpurun_out/lane_model.json
-python -m pytest tests/test_tiler_gpu.py -q -m gpu -x 2>&1 | tail -3
-python tools/time_tiler.py 2>&1 | tail -2 | tee gpurun_out/time_tiler.jsonl
+: > gpurun_out/small_calls.jsonl
+python tools/time_small_calls.py | tee -a gpurun_out/small_calls.jsonl
+CVTTB200_BC7_CLASSIFY_MAX=0 python tools/time_small_calls.py | tee -a gpurun_out/small_calls.jsonl
+CVTTB200_BC7_CLASSIFY_MAX=48 python tools/time_small_calls.py | tee -a gpurun_out/small_calls.jsonl
+python -m pytest tests/test_bc7_gpu.py tests/test_concurrency_gpu.py tests/test_dropin_cpp.py -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/pytest_bc7.log
