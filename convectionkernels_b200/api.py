@@ -482,3 +482,37 @@ def untile_blocks(encoded, width, height):
     with torch.cuda.device(encoded.device):
         _check(L.cvttb200_untile_blocks(encoded.data_ptr(), int(width), int(height), bb, out.data_ptr(), torch.cuda.current_stream(encoded.device).cuda_stream))
     return out
+
+
+def ktx_header(fmt, width, height):
+    """The 68 bytes the reference's sample packer writes in front of the encoded blocks (KTX 1.1 header + imageSize,
+    etc2packer/etc2packer.cpp:114-193).  Pure host code."""
+    L = _lib()
+    buf = ctypes.create_string_buffer(68)
+    L.cvttb200_ktx_header.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    _check(L.cvttb200_ktx_header(FORMATS[fmt], int(width), int(height), buf))
+    return buf.raw
+
+
+def pack_ktx(fmt, image, options=None):
+    """What the sample packer does with one RGBA8 image (etc2packer/etc2packer.cpp:106-293), on the GPU: block extraction with
+    clamped edges, the encode of `fmt`, removal of the padding blocks, KTX header.  image: torch CUDA uint8 (H, W, 4).
+    Returns the bytes of the .ktx file.  The two R11 targets take the sample's scalar, the channel sum scaled to 0..2047
+    (signed: to 0..1023, as the sample does), etc2packer.cpp:232-237."""
+    import torch
+    options = options or Options()
+    h, w = int(image.shape[0]), int(image.shape[1])
+    blocks = tile_image(image)
+    if fmt in ("EAC_R11U", "EAC_R11S"):
+        total = blocks[..., :3].to(torch.float64).sum(dim=-1) / (255.0 * 3.0)
+        scalar = torch.floor(total * (2047.0 if fmt == "EAC_R11U" else 1023.0) + 0.5).to(torch.int16)
+        enc = EncodeETC2Alpha11(scalar.contiguous(), fmt == "EAC_R11S", options)
+    else:
+        enc = encode(fmt, blocks, options)       # AllocETC2Data(options): allocation-time options = the call's, as in the sample
+    payload = untile_blocks(enc, w, h)
+    return ktx_header(fmt, w, h) + payload.cpu().numpy().tobytes()
+
+
+def write_ktx(path, fmt, image, options=None):
+    with open(path, "wb") as f:
+        f.write(pack_ktx(fmt, image, options))

@@ -555,6 +555,38 @@ int cvttb200_get_rcp_table(float *rcp17)
 
 const char *cvttb200_last_error(void) { return t_lastError.c_str(); }
 
+// etc2packer/etc2packer.cpp:114-193: what the sample packer puts in front of the encoded blocks
+int cvttb200_ktx_header(int format, int width, int height, void *header68)
+{
+    if (!header68 || width <= 0 || height <= 0)
+        return fail(CVTTB200_ERR_BAD_ARGUMENT, "bad KTX header request");
+    uint32_t glInternalFormat, glBaseInternalFormat, blockBytes = 8;
+    switch (format)
+    {
+    case CVTTB200_ETC1: glInternalFormat = 0x8D64; glBaseInternalFormat = 0x1907; break;
+    case CVTTB200_ETC2: glInternalFormat = 0x9274; glBaseInternalFormat = 0x1907; break;
+    case CVTTB200_ETC2_RGBA: glInternalFormat = 0x9278; glBaseInternalFormat = 0x1908; blockBytes = 16; break;
+    case CVTTB200_ETC2_PUNCHTHROUGH: glInternalFormat = 0x9276; glBaseInternalFormat = 0x1908; break;
+    case CVTTB200_EAC_R11U: glInternalFormat = 0x9270; glBaseInternalFormat = 0x1903; break;
+    case CVTTB200_EAC_R11S: glInternalFormat = 0x9271; glBaseInternalFormat = 0x1903; break;
+    default:
+        return fail(CVTTB200_ERR_UNSUPPORTED, "the KTX writer covers the sample packer's targets: ETC1, ETC2, ETC2_RGBA, ETC2_PUNCHTHROUGH, EAC_R11U, EAC_R11S");
+    }
+    static const uint8_t identifier[12] = { 0xAB, 0x4B, 0x54, 0x58, 0x20, 0x31, 0x31, 0xBB, 0x0D, 0x0A, 0x1A, 0x0A };
+    const uint32_t words[14] = {
+        0x04030201u,                 // endianness
+        0u, 1u, 0u,                  // glType, glTypeSize, glFormat (compressed data)
+        glInternalFormat, glBaseInternalFormat,
+        (uint32_t)width, (uint32_t)height, 0u,      // pixelDepth
+        0u, 1u, 1u,                  // array elements, faces, mip levels
+        0u,                          // bytesOfKeyValueData
+        (uint32_t)((width + 3) / 4) * (uint32_t)((height + 3) / 4) * blockBytes       // imageSize of the one level
+    };
+    memcpy(header68, identifier, 12);
+    memcpy((uint8_t *)header68 + 12, words, sizeof(words));
+    return CVTTB200_OK;
+}
+
 size_t cvttb200_tiled_block_count(int width, int height)
 {
     if (width <= 0 || height <= 0)

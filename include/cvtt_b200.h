@@ -170,6 +170,14 @@ int cvttb200_tile_image(int pixelBytes, const void *image, int width, int height
  * rows of ceil(width / 4) blocks, the order a KTX / DDS payload uses).  blockBytes is 8 or 16.  Device pointers. */
 int cvttb200_untile_blocks(const void *encoded, int width, int height, size_t blockBytes, void *out, void *stream);
 
+/* KTX 1.1 container header for the payload cvttb200_untile_blocks produces, as the reference's sample packer writes it
+ * (etc2packer/ktxheader.h; etc2packer/etc2packer.cpp:114-141 header fields, :143-180 GL enums per target, :190-193 the imageSize
+ * word): fills 68 bytes of HOST memory, the 64-byte header followed by the 32-bit byte count of the one mip level; the file is
+ * those 68 bytes followed by ceil(w/4) * ceil(h/4) encoded blocks in row-major order.  Formats: the sample's six targets --
+ * ETC1, ETC2, ETC2_RGBA, ETC2_PUNCHTHROUGH, EAC_R11U, EAC_R11S; anything else answers CVTTB200_ERR_UNSUPPORTED. */
+#define CVTTB200_KTX_HEADER_BYTES 68
+int cvttb200_ktx_header(int format, int width, int height, void *header68);
+
 /* ---- the hot path ---------------------------------------------------------------------------------------- */
 
 /* Encodes nBlocks (a multiple of 8) blocks.  `blocks` and `out` may each be host memory (pageable or pinned) or
