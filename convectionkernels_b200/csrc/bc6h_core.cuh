@@ -968,11 +968,8 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).
-    template<bool SIGNED, bool FAST, int STRIDE, class Vote>
-    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, uint32_t out[4])
+    CVTT_HD void bc6h_best_reset(BC6HBest &best)
     {
-        BC6HBest best;
         best.error = FLT_MAX;
         best.mode = 0;
         best.partition = 0;
@@ -983,39 +980,12 @@ namespace cvttb200
                 best.ep[s][e][0] = best.ep[s][e][1] = best.ep[s][e][2] = 0;
         for (int s = 0; s < 2; s++)
             best.q[s][0] = best.q[s][1] = best.q[s][2] = 0;
+    }
 
-        // endpoint fits of the 32 partitions and of the whole block (BC67.cpp:2739-2774)
-        float ufepBase[33][6], ufepOffs[33][6];
-        for (int p = 0; p < 32; p++)
-            for (int subset = 0; subset < 2; subset++)
-            {
-                const uint32_t mask = subset ? T.partitionMask[p] : ((uint32_t)~T.partitionMask[p] & 0xffffu);
-                int n = 0;
-                for (uint32_t m = mask; m; m &= m - 1)
-                    n++;
-                endpoint_selector3_masked(L, mask, n, P.w, ufepBase[p] + subset * 3, ufepOffs[p] + subset * 3);
-            }
-        endpoint_selector3_masked(L, 0xffffu, 16, P.w, ufepBase[32], ufepOffs[32]);
-        for (int ch = 0; ch < 3; ch++)
-            ufepBase[32][3 + ch] = ufepOffs[32][3 + ch] = 0.0f;
-
-        // g_hdrModesExistForPrecision (BC67.cpp:144-149)
-        const uint32_t existSingle = (1u << 10) | (1u << 11) | (1u << 12) | (1u << 16);
-        const uint32_t existPartitioned = (1u << 6) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10) | (1u << 11);
-        for (int partitionedInt = 0; partitionedInt < 2; partitionedInt++)
-            for (int aPrec = 16; aPrec >= 0; aPrec--)
-            {
-                if (!(((partitionedInt ? existPartitioned : existSingle) >> aPrec) & 1))
-                    continue;
-                if (partitionedInt)
-                {
-                    for (int p = 0; p < 32; p++)
-                        bc6h_partition<SIGNED, FAST, 8, STRIDE>(P, T, L, vote, true, aPrec, p, ufepBase[p], ufepOffs[p], best);
-                }
-                else
-                    bc6h_partition<SIGNED, FAST, 16, STRIDE>(P, T, L, vote, false, aPrec, 0, ufepBase[32], ufepOffs[32], best);
-            }
-
+    // The bit packing tail of BC6HComputer::Pack (BC67.cpp:2990-3050) for whatever `best` holds
+    template<bool SIGNED, bool FAST, int STRIDE>
+    CVTT_HD void bc6h_pack_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, const BC6HBest &best, uint32_t out[4])
+    {
         // header: scatter the endpoint fields into the mode's bit layout, then the indexes (PackingVector::Pack does not
         // mask its argument; the fix-up indexes have their top bit clear by construction)
         const uint8_t *mi = T.modes[best.mode];
@@ -1064,5 +1034,146 @@ namespace cvttb200
         out[1] = v[1];
         out[2] = v[2];
         out[3] = v[3];
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // The search as a numbered sequence of CALLS of bc6h_partition, in the reference's order (BC67.cpp:2776-2788): the four
+    // one-subset precisions 16, 12, 11, 10, then for each two-subset precision 11, 10, 9, 8, 7, 6 the 32 partitions.
+    //
+    // What the small-call launch (bc6h_kernels.cu) rests on.  A call changes a lane's best only through commits of
+    // combinations that are strictly better than its best error, so (1) the lane's best ERROR after a call is min(error
+    // before, smallest legal combination of the call) whatever the other lanes of its group do -- a lane that is better keeps
+    // the mode loop of its group going until it has committed -- and (2) the lane's final mode / endpoints are those it held
+    // at the end of its WINNER call, the first call that reaches its final error.  What the other lanes do decides only which
+    // of the legal modes a commit ends on (the group-wide mode loop), and that depends on their best errors at the START of
+    // the winner call.  So the calls can be searched in any grouping for their error histories alone (bc6h_search_calls),
+    // and a lane's block is then reproduced exactly by running its winner call once more for the whole group with every
+    // lane's true entry error (bc6h_history + bc6h_run_call).
+    enum { kBC6HCalls = 4 + 6 * 32 };
+
+    CVTT_HD void bc6h_call_info(int call, bool &partitioned, int &aPrec, int &p)
+    {
+        if (call < 4)
+        {
+            partitioned = false;
+            aPrec = call == 0 ? 16 : 13 - call;
+            p = 0;
+        }
+        else
+        {
+            partitioned = true;
+            aPrec = 11 - ((call - 4) >> 5);
+            p = (call - 4) & 31;
+        }
+    }
+
+    // One call: the endpoint fits of its partition (BC67.cpp:2739-2774), then the trials
+    template<bool SIGNED, bool FAST, int STRIDE, class Vote>
+    CVTT_HD void bc6h_run_call(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, int call, BC6HBest &best)
+    {
+        bool partitioned;
+        int aPrec, p;
+        bc6h_call_info(call, partitioned, aPrec, p);
+        float base[6] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f }, offs[6] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+        if (partitioned)
+        {
+            for (int subset = 0; subset < 2; subset++)
+            {
+                const uint32_t mask = subset ? T.partitionMask[p] : ((uint32_t)~T.partitionMask[p] & 0xffffu);
+                int n = 0;
+                for (uint32_t m = mask; m; m &= m - 1)
+                    n++;
+                endpoint_selector3_masked(L, mask, n, P.w, base + subset * 3, offs + subset * 3);
+            }
+            bc6h_partition<SIGNED, FAST, 8, STRIDE>(P, T, L, vote, true, aPrec, p, base, offs, best);
+        }
+        else
+        {
+            endpoint_selector3_masked(L, 0xffffu, 16, P.w, base, offs);
+            bc6h_partition<SIGNED, FAST, 16, STRIDE>(P, T, L, vote, false, aPrec, 0, base, offs, best);
+        }
+    }
+
+    // Calls [callBegin, callEnd) from a fresh best; running[(call - callBegin) * stride] receives the lane's best error after each
+    // call (a running minimum local to this range).  (Starting every range with the first calls of the search, to have an
+    // error to prune against, is exact too -- they precede every range -- but was measured: they cost what they save.)
+    template<bool SIGNED, bool FAST, int STRIDE, class Vote>
+    CVTT_HD void bc6h_search_calls(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, int callBegin, int callEnd, float *running, size_t stride, bool store)
+    {
+        BC6HBest best;
+        bc6h_best_reset(best);
+        for (int call = callBegin; call < callEnd; call++)
+        {
+            bc6h_run_call<SIGNED, FAST, STRIDE>(P, T, L, vote, call, best);
+            if (store)
+                running[(size_t)(call - callBegin) * stride] = best.error;
+        }
+    }
+
+    // The lane's error history from the per-range running minima: history[call * stride], ranges of callsPerSlice calls.
+    // Returns the best error before call `upto` (FLT_MAX for none) and the first call that reached it (-1: nothing committed).
+    CVTT_HD float bc6h_history(const float *history, size_t stride, int callsPerSlice, int upto, int &winner)
+    {
+        float cur = FLT_MAX, base = FLT_MAX;
+        winner = -1;
+        int inSlice = 0;
+        for (int call = 0; call < upto; call++)
+        {
+            if (inSlice == 0)
+                base = cur;
+            const float r = history[(size_t)call * stride];
+            const float g = (r < base) ? r : base;
+            if (g < cur)
+            {
+                cur = g;
+                winner = call;
+            }
+            if (++inSlice == callsPerSlice)
+                inSlice = 0;
+        }
+        return cur;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).
+    template<bool SIGNED, bool FAST, int STRIDE, class Vote>
+    CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, uint32_t out[4])
+    {
+        BC6HBest best;
+        bc6h_best_reset(best);
+
+        // endpoint fits of the 32 partitions and of the whole block (BC67.cpp:2739-2774)
+        float ufepBase[33][6], ufepOffs[33][6];
+        for (int p = 0; p < 32; p++)
+            for (int subset = 0; subset < 2; subset++)
+            {
+                const uint32_t mask = subset ? T.partitionMask[p] : ((uint32_t)~T.partitionMask[p] & 0xffffu);
+                int n = 0;
+                for (uint32_t m = mask; m; m &= m - 1)
+                    n++;
+                endpoint_selector3_masked(L, mask, n, P.w, ufepBase[p] + subset * 3, ufepOffs[p] + subset * 3);
+            }
+        endpoint_selector3_masked(L, 0xffffu, 16, P.w, ufepBase[32], ufepOffs[32]);
+        for (int ch = 0; ch < 3; ch++)
+            ufepBase[32][3 + ch] = ufepOffs[32][3 + ch] = 0.0f;
+
+        // g_hdrModesExistForPrecision (BC67.cpp:144-149)
+        const uint32_t existSingle = (1u << 10) | (1u << 11) | (1u << 12) | (1u << 16);
+        const uint32_t existPartitioned = (1u << 6) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10) | (1u << 11);
+        for (int partitionedInt = 0; partitionedInt < 2; partitionedInt++)
+            for (int aPrec = 16; aPrec >= 0; aPrec--)
+            {
+                if (!(((partitionedInt ? existPartitioned : existSingle) >> aPrec) & 1))
+                    continue;
+                if (partitionedInt)
+                {
+                    for (int p = 0; p < 32; p++)
+                        bc6h_partition<SIGNED, FAST, 8, STRIDE>(P, T, L, vote, true, aPrec, p, ufepBase[p], ufepOffs[p], best);
+                }
+                else
+                    bc6h_partition<SIGNED, FAST, 16, STRIDE>(P, T, L, vote, false, aPrec, 0, ufepBase[32], ufepOffs[32], best);
+            }
+
+        bc6h_pack_block<SIGNED, FAST, STRIDE>(P, T, L, best, out);
     }
 }

@@ -450,7 +450,7 @@ namespace
         if (format <= CVTTB200_BC5S)
             return launch_s3tc(format, dIn, nBlocks, dOut, rq.options, rq.rcpN, stream);
         if (format == CVTTB200_BC6HU || format == CVTTB200_BC6HS)
-            return launch_bc6h(dIn, nBlocks, dOut, rq.options, format == CVTTB200_BC6HS, rq.rcpN, stream);
+            return launch_bc6h(ctx, dIn, nBlocks, dOut, rq.options, format == CVTTB200_BC6HS, rq.rcpN, stream);
         return launch_etc(ctx, format, dIn, nBlocks, dOut, rq.options, rq.etc2AllocOptions, stream);
     }
 

@@ -60,7 +60,7 @@ namespace cvttb200
     int bc7_selftest_div(uint64_t samples, uint64_t seed, uint64_t *mismatches);
 
     int bc6h_device_setup();
-    int launch_bc6h(const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, bool isSigned, const float *rcpN, cudaStream_t stream);
+    int launch_bc6h(DeviceContext &ctx, const void *dIn, size_t nBlocks, void *dOut, const OptionsPOD &options, bool isSigned, const float *rcpN, cudaStream_t stream);
 
     int etc_device_setup();
     // allocOptions: the Options AllocETC2Data was called with (the reference fixes the chroma side axes there, ETC.cpp:3117-3145)

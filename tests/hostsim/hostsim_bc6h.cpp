@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY.  CPU build of the BC6H per-thread device code (convectionkernels_b200/csrc/bc6h_core.cuh).
 // The eight lanes of a reference group run as eight host threads; the group votes of the kernel (ballots over an
 // 8-lane segment) become a spin barrier with an OR reduction.  Not part of the product library.
+#include <algorithm>
 #include <thread>
 #include <vector>
 #include <xmmintrin.h>
@@ -60,6 +61,97 @@ static int encode_bc6h(const int16_t *blocks, size_t nBlocks, uint8_t *out, cons
             threads.emplace_back(fast ? run_lane<true, true> : run_lane<true, false>, lane, lanesPerWarp, &groups[lane / 8], &warp, &P, blocks, nBlocks, out);
         else
             threads.emplace_back(fast ? run_lane<false, true> : run_lane<false, false>, lane, lanesPerWarp, &groups[lane / 8], &warp, &P, blocks, nBlocks, out);
+    }
+    for (auto &t : threads)
+        t.join();
+    return 0;
+}
+
+// The small-call launch of bc6h_kernels.cu: the calls of the search dealt out in ranges of callsPerSlice (a CTA each in the
+// kernel: here one after the other, each from a fresh best), then per group one re-run of every distinct winner call with the
+// lanes' true entry errors.  One group = eight host threads.
+namespace
+{
+    template<bool SIGNED, bool FAST>
+    void run_lane_split(int lane, GroupShared *groupShared, GroupShared *warpShared, const BC6HParams *P, const int16_t *blocks, size_t nBlocks, uint8_t *out, int callsPerSlice, float *history, int *winners)
+    {
+        HostWarpVote vote;
+        vote.group.g = groupShared;
+        vote.warp.g = warpShared;           // its own barrier object, also of eight threads: the warp scope is the group here
+        const BC6HTables &T = bc6h_tables();
+        for (size_t base = 0; base < nBlocks; base += 8)
+        {
+            const size_t block = base + lane;
+            const int16_t *src = blocks + block * 64;
+            float pw[48];
+            uint32_t raw[32], tab[24];
+            BC6HLane<1> L;
+            L.pw = pw;
+            L.raw = raw;
+            L.tab = tab;
+            for (int px = 0; px < 16; px++)
+                bc6h_load_pixel<SIGNED>(*P, L, px, src[px * 4 + 0], src[px * 4 + 1], src[px * 4 + 2]);
+            float *hist = history + block;          // [call][nBlocks]
+            for (int callBegin = 0; callBegin < kBC6HCalls; callBegin += callsPerSlice)
+                bc6h_search_calls<SIGNED, FAST, 1>(*P, T, L, vote, callBegin, std::min<int>(kBC6HCalls, callBegin + callsPerSlice), hist + (size_t)callBegin * nBlocks, nBlocks, true);
+            int winner;
+            bc6h_history(hist, nBlocks, callsPerSlice, kBC6HCalls, winner);
+            winners[block] = winner;
+            vote.any(false);            // barrier: every lane of the group has published its winner
+            BC6HBest mine;
+            bc6h_best_reset(mine);
+            for (int k = 0; k < 8; k++)
+            {
+                // k-th distinct winner call of the group, in lane order
+                int list[8], count = 0;
+                for (int j = 0; j < 8; j++)
+                {
+                    const int w = winners[base + j];
+                    bool seen = w < 0;
+                    for (int i = 0; i < count; i++)
+                        seen = seen || list[i] == w;
+                    if (!seen)
+                        list[count++] = w;
+                }
+                if (k >= count)
+                    break;
+                const int call = list[k];
+                int unused;
+                BC6HBest best;
+                bc6h_best_reset(best);
+                best.error = bc6h_history(hist, nBlocks, callsPerSlice, call, unused);
+                bc6h_run_call<SIGNED, FAST, 1>(*P, T, L, vote, call, best);
+                if (winner == call)
+                    mine = best;
+            }
+            uint32_t o[4];
+            bc6h_pack_block<SIGNED, FAST, 1>(*P, T, L, mine, o);
+            memcpy(out + block * 16, o, 16);
+            vote.any(false);            // nobody overwrites winners[] of the next group's slots early (distinct slots anyway)
+        }
+    }
+}
+
+extern "C" int hostsim_encode_bc6h_split(const int16_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, int isSigned, const float *rcpTable, int callsPerSlice)
+{
+    if (nBlocks % 8 || callsPerSlice < 1)
+        return -1;
+    float rcpN[17];
+    for (int n = 0; n < 17; n++)
+        rcpN[n] = rcpTable ? rcpTable[n] : _mm_cvtss_f32(_mm_rcp_ps(_mm_set1_ps((float)n)));
+    BC6HParams P;
+    bc6h_fill_params(P, *options, rcpN);
+    const bool fast = (options->flags & kFlag_BC6H_FastIndexing) != 0;
+    GroupShared group, warp;
+    std::vector<float> history((size_t)kBC6HCalls * nBlocks);
+    std::vector<int> winners(nBlocks);
+    std::vector<std::thread> threads;
+    for (int lane = 0; lane < 8; lane++)
+    {
+        if (isSigned)
+            threads.emplace_back(fast ? run_lane_split<true, true> : run_lane_split<true, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, history.data(), winners.data());
+        else
+            threads.emplace_back(fast ? run_lane_split<false, true> : run_lane_split<false, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, history.data(), winners.data());
     }
     for (auto &t : threads)
         t.join();

@@ -40,6 +40,19 @@ def test_random_blocks_against_reference(reference, fmt, flags):
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("fmt,n", [("BC6HU", 8), ("BC6HU", 40), ("BC6HS", 1536), ("BC6HU", 37888), ("BC6HU", 37896), ("BC6HS", 37896)])
+def test_small_calls_take_the_split_launch_and_match_the_reference(reference, fmt, n):
+    """Calls of up to 37 888 blocks take the small-call launch (the 196 calls of the search dealt out to up to 49 times as many
+    CTAs that record error histories, bc6h_resolve_kernel re-runs every block's winner call for its group); 37 896 blocks is
+    the first size of the normal launch.  Bit-exact either way, group coupling included (random blocks: every group mixes)."""
+    blocks = np.ascontiguousarray(np.concatenate([synth.image_to_blocks(synth.hdr_ramp_f16(256, 512, seed=12, signed=fmt.endswith("S"))),
+                                                  synth.random_blocks_f16(37896 - 8192, seed=31, signed=fmt.endswith("S"))])[::-1][:n])
+    o = api.Options()
+    want = reference.encode(fmt, blocks, _opt_bytes(o), threads=0)
+    got = api.encode(fmt, blocks, o)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
 def test_group_coupling_is_reproduced(reference):
     """the same block encodes differently next to different neighbours; the kernel must follow the reference"""
     base = synth.random_blocks_f16(64, seed=5)
