@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:bc6h -c 24 --csv --log-file gpurun_out/bc6h_split_launches.csv python tools/time_small_calls.py BC6HU 8 4096 16384 > /dev/null 2>&1
-cut -d, -f5,9,12- gpurun_out/bc6h_split_launches.csv | tail -26
-CVTTB200_BC6H_SPLIT=196 python tools/time_small_calls.py BC6HU 4096 16384 | cut -c1-300
-CVTTB200_BC6H_SPLIT=98 python tools/time_small_calls.py BC6HU 4096 16384 | cut -c1-300
+python -m pytest tests/test_etc_gpu.py -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/pytest_etc.log
+: > gpurun_out/small_calls_etc.jsonl
+for f in ETC2_RGBA ETC2 ETC1; do python tools/time_small_calls.py $f 8 64 512 2560 4096 8192 16384 32768 37888 | tee -a gpurun_out/small_calls_etc.jsonl; done
+CVTTB200_ETC_SPLIT=0 python tools/time_small_calls.py ETC2_RGBA 8 512 4096 32768 | tee -a gpurun_out/small_calls_etc.jsonl
+for u in $(seq 0 26); do echo -n "unit $u " | tee -a gpurun_out/small_calls_etc.jsonl; CVTTB200_ETC_ONLY_UNIT=$u python tools/time_small_calls.py ETC2_RGBA 512 | cut -c1-120 | tee -a gpurun_out/small_calls_etc.jsonl; done
+for u in 0 1 2 3; do echo -n "etc1 unit $u " | tee -a gpurun_out/small_calls_etc.jsonl; CVTTB200_ETC_ONLY_UNIT=$u python tools/time_small_calls.py ETC1 512 | cut -c1-120 | tee -a gpurun_out/small_calls_etc.jsonl; done
+python tools/time_format.py ETC2_RGBA | tee -a gpurun_out/small_calls_etc.jsonl
+python tools/time_format.py ETC1 | tee -a gpurun_out/small_calls_etc.jsonl
