@@ -1496,7 +1496,10 @@ namespace cvttb200
     // The exchange between a block's owner thread and the threads that run its tasks goes through this interface.  The
     // kernel implements it with shared memory (bc7_kernels.cu); a single lane (tests/hostsim, and kernels whose command
     // streams hold no PAIR2) runs its own tasks one after the other.
-    enum { kBC7PairClasses = 6 };
+    // Up to kBC7PairGroup consecutive PAIR2 commands are searched as one group: their first halves back to back, ONE exchange
+    // for the tasks of all of them.  A partition leaves 4-6 chunks of tasks for the 12 warps of a CTA, so two partitions'
+    // tasks run in the time of one (a block's best is then one partition stale when the second one's wants are decided).
+    enum { kBC7PairGroup = 2, kBC7PairClassesPerCommand = 6, kBC7PairClasses = kBC7PairGroup * kBC7PairClassesPerCommand };
 
     struct BC7SoloExchange
     {
@@ -1520,15 +1523,11 @@ namespace cvttb200
         CVTT_HD F4 result(int cls) const { return posted[cls]; }
     };
 
-    // Second half of a PAIR2 command: runs the task slots dealt to this thread.  pc points at the command.
+    // Second half of a group of PAIR2 commands: runs the task slots dealt to this thread.  pcs point at the commands; class =
+    // command * 6 + run * 2 + unit.
     template<bool FAST, int STRIDE, class Exchange>
-    CVTT_HD void bc7_pair2_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *pc, int total)
+    CVTT_HD void bc7_pair2_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *const *pcs, int total)
     {
-        const uint32_t w0 = pc[0], w2 = pc[2];
-        const bool listedRGB = (w0 >> 19) & 1, listedRGBA = (w0 >> 20) & 1, split = (w0 >> 22) & 1;
-        const uint32_t maskB = w2 & 0xffffu;
-        const int nB = (w2 >> 16) & 0xff;
-
         for (int slot = ex.first_slot(); ex.chunk_in_range(slot, total); slot += ex.slot_stride())
         {
             int cls, owner;
@@ -1536,7 +1535,13 @@ namespace cvttb200
             const bool hasTask = owner >= 0;
             if (!ex.task_any(hasTask))
                 continue;
-            const int r = cls >> 1, unit = cls & 1;
+            const int command = cls >= kBC7PairClassesPerCommand ? 1 : 0, local = cls - command * kBC7PairClassesPerCommand;
+            const uint32_t *pc = pcs[command];
+            const uint32_t w0 = pc[0], w2 = pc[2];
+            const bool listedRGB = (w0 >> 19) & 1, listedRGBA = (w0 >> 20) & 1, split = (w0 >> 22) & 1;
+            const uint32_t maskB = w2 & 0xffffu;
+            const int nB = (w2 >> 16) & 0xff;
+            const int r = local >> 1, unit = local & 1;
             const uint32_t rw = pc[3 + r];
             const int mode = rw & 0xf, seeds = (rw >> 8) & 0xf;
             const int o = hasTask ? owner : 0;
@@ -1661,11 +1666,21 @@ namespace cvttb200
                 if (op == kCmdPair2)
                 {
                     // no block, no task to offer, but the exchange's barriers and the task warps need every warp of the CTA
+                    const uint32_t *pcs[kBC7PairGroup];
+                    int commands = 0;
+                    while (commands < kBC7PairGroup && (pc[0] & 0xff) == kCmdPair2)
+                    {
+                        if (commands)
+                            cta_sync();             // the rendezvous the working warps keep before a command of the group
+                        pcs[commands++] = pc;
+                        pc += 3 + (int)((pc[0] >> 8) & 0xff);
+                    }
+                    for (int k = commands; k < kBC7PairGroup; k++)
+                        pcs[k] = pcs[0];
                     ex.publish(0u);
                     const int total = ex.compact(0u);
-                    bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pc, total);
+                    bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
                     ex.sync();
-                    pc += 3 + (int)((w0 >> 8) & 0xff);
                     continue;
                 }
                 pc += (op == kCmdShape) ? 2 + (int)((w0 >> 8) & 0xff) : (op == kCmdEval ? 2 : 1);
@@ -1782,86 +1797,111 @@ namespace cvttb200
             }
             else if (op == kCmdPair2)
             {
-                // Two-subset modes, one partition: subset A (the larger one) for every block, subset B only where A's error
-                // leaves room below the block's best.  total = err(A) + err(B) >= err(A) (errors are sums of non-negative
+                // Two-subset modes, one partition per command: subset A (the larger one) for every block, subset B only where A's
+                // error leaves room below the block's best.  total = err(A) + err(B) >= err(A) (errors are sums of non-negative
                 // terms and fl(a + b) is monotonic), so a block whose err(A) already exceeds its best cannot take this
-                // (mode, partition) whatever B gives -- the reference evaluates it and rejects it.
-                const int nRuns = (w0 >> 8) & 0xff, partition = (w0 >> 24) & 0x3f;
-                const bool listedRGB = (w0 >> 16) & 1, listedRGBA = (w0 >> 17) & 1, needRGBA = (w0 >> 18) & 1, aIsSubset1 = (w0 >> 21) & 1;
-                const uint32_t w1 = pc[1];
-                const uint32_t maskA = w1 & 0xffffu;
-                const int nA = (w1 >> 16) & 0xff;
-
-                float sumV[4], accA;
-                bc7_gather<STRIDE>(L, maskA, 0, P.w, sumV, accA);
-                const float staticAlphaError = uniform ? accA : fmul(accA, P.wSq[3]);
-                float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
-                bc7_shape_fits<STRIDE>(P, L.gw, nA, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
-
-                const bool split = (w0 >> 22) & 1;
-                float errA[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
-                uint32_t epA[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
-                uint32_t wantMask = 0;                              // bit (run * 2 + unit)
-                for (int r = 0; r < nRuns; r++)
+                // (mode, partition) whatever B gives -- the reference evaluates it and rejects it.  Consecutive commands form a
+                // group (kBC7PairGroup): first halves back to back, one exchange for the second halves of all of them.
+                const uint32_t *pcs[kBC7PairGroup];
+                float errA[kBC7PairGroup][3];
+                uint32_t epA[kBC7PairGroup][3][2];
+                uint32_t wantMask = 0;                              // bit (command * 6 + run * 2 + unit)
+                int commands = 0;
+                while (commands < kBC7PairGroup && (pc[0] & 0xff) == kCmdPair2)
                 {
-                    const uint32_t rw = pc[3 + r];
-                    const int mode = rw & 0xf, seeds = (rw >> 4) & 0xf;
-                    if ((mode < 4 && !lf.warpAnyRGB) || (mode == 7 && !lf.warpAnyMode7))
-                        continue;
-                    BC7ShapeBest best;
-                    bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nA, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best);
-                    bool eligible = true;                              // the lane conditions of the partition scan, BC67.cpp:1602-1634
-                    if (mode < 4 && !lf.allowRGBModes)
-                        eligible = false;
-                    if (mode == 7)
+                    if (commands)
+                        cta_sync();
+                    const int k = commands++;
+                    pcs[k] = pc;
+                    const uint32_t c0 = pc[0];
+                    const int nRuns = (c0 >> 8) & 0xff, partition = (c0 >> 24) & 0x3f;
+                    const bool listedRGB = (c0 >> 16) & 1, listedRGBA = (c0 >> 17) & 1, needRGBA = (c0 >> 18) & 1;
+                    const uint32_t w1 = pc[1];
+                    const uint32_t maskA = w1 & 0xffffu;
+                    const int nA = (w1 >> 16) & 0xff;
+
+                    float sumV[4], accA;
+                    bc7_gather<STRIDE>(L, maskA, 0, P.w, sumV, accA);
+                    const float staticAlphaError = uniform ? accA : fmul(accA, P.wSq[3]);
+                    float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+                    bc7_shape_fits<STRIDE>(P, L.gw, nA, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
+
+                    const bool split = (c0 >> 22) & 1;
+                    for (int r = 0; r < 3; r++)
                     {
-                        if (!allowMode7)
-                            eligible = false;
-                        if (lf.anyBlockHasAlpha && ((P.mode7RGBPartitionEnabled >> partition) & 1) == 0 && !lf.blockHasNonMaxAlpha)
-                            eligible = false;
+                        errA[k][r] = FLT_MAX;
+                        epA[k][r][0] = epA[k][r][1] = 0;
                     }
-                    if (eligible && !(best.err > work.error))
+                    for (int r = 0; r < nRuns; r++)
                     {
-                        errA[r] = best.err;
-                        epA[r][0] = best.e0;
-                        epA[r][1] = best.e1;
-                        wantMask |= ((mode != 1 && split) ? 3u : 1u) << (2 * r);
+                        const uint32_t rw = pc[3 + r];
+                        const int mode = rw & 0xf, seeds = (rw >> 4) & 0xf;
+                        if ((mode < 4 && !lf.warpAnyRGB) || (mode == 7 && !lf.warpAnyMode7))
+                            continue;
+                        BC7ShapeBest best;
+                        bc7_run_pair_mode<FAST, STRIDE>(P, mode, L.gv, L.gw, nA, seeds, baseRGB, offsRGB, baseRGBA, offsRGBA, sumV, staticAlphaError, best);
+                        bool eligible = true;                              // the lane conditions of the partition scan, BC67.cpp:1602-1634
+                        if (mode < 4 && !lf.allowRGBModes)
+                            eligible = false;
+                        if (mode == 7)
+                        {
+                            if (!allowMode7)
+                                eligible = false;
+                            if (lf.anyBlockHasAlpha && ((P.mode7RGBPartitionEnabled >> partition) & 1) == 0 && !lf.blockHasNonMaxAlpha)
+                                eligible = false;
+                        }
+                        if (eligible && !(best.err > work.error))
+                        {
+                            errA[k][r] = best.err;
+                            epA[k][r][0] = best.e0;
+                            epA[k][r][1] = best.e1;
+                            wantMask |= ((mode != 1 && split) ? 3u : 1u) << (k * kBC7PairClassesPerCommand + 2 * r);
+                        }
                     }
+                    pc += 3 + nRuns;
                 }
+                for (int k = commands; k < kBC7PairGroup; k++)
+                    pcs[k] = pcs[0];
                 ex.publish((lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
                 const int total = ex.compact(wantMask);
-                bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pc, total);
+                bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
                 ex.sync();
-                for (int r = 0; r < nRuns; r++)
+                for (int k = 0; k < commands; k++)
                 {
-                    if (!((wantMask >> (2 * r)) & 1u))
-                        continue;
-                    const int mode = pc[3 + r] & 0xf;
-                    F4 got = ex.result(2 * r);
-                    if ((wantMask >> (2 * r + 1)) & 1u)
+                    const uint32_t c0 = pcs[k][0];
+                    const int nRuns = (c0 >> 8) & 0xff, partition = (c0 >> 24) & 0x3f;
+                    const bool aIsSubset1 = (c0 >> 21) & 1;
+                    for (int r = 0; r < nRuns; r++)
                     {
-                        // the run was searched as two units: "first strictly better in sequence order" over both
-                        const F4 other = ex.result(2 * r + 1);
-                        if (other.x < got.x || (other.x == got.x && (int)as_uint(other.y) < (int)as_uint(got.y)))
-                            got = other;
-                    }
-                    const float totalError = aIsSubset1 ? fadd(got.x, errA[r]) : fadd(errA[r], got.x);       // subset 0 + subset 1
-                    const int key = bc7_mode_order(mode) * 64 + partition;
-                    if (totalError < work.error || (totalError == work.error && key < work.key))
-                    {
-                        work.error = totalError;
-                        work.key = key;
-                        work.mode = mode;
-                        work.sub = partition;
-                        const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
-                        work.ep[sA][0] = epA[r][0];
-                        work.ep[sA][1] = epA[r][1];
-                        work.ep[sB][0] = as_uint(got.z);
-                        work.ep[sB][1] = as_uint(got.w);
-                        work.sc[0] = work.sc[1] = work.sc[2] = 0;
+                        const int cls = k * kBC7PairClassesPerCommand + 2 * r;
+                        if (!((wantMask >> cls) & 1u))
+                            continue;
+                        const int mode = pcs[k][3 + r] & 0xf;
+                        F4 got = ex.result(cls);
+                        if ((wantMask >> (cls + 1)) & 1u)
+                        {
+                            // the run was searched as two units: "first strictly better in sequence order" over both
+                            const F4 other = ex.result(cls + 1);
+                            if (other.x < got.x || (other.x == got.x && (int)as_uint(other.y) < (int)as_uint(got.y)))
+                                got = other;
+                        }
+                        const float totalError = aIsSubset1 ? fadd(got.x, errA[k][r]) : fadd(errA[k][r], got.x);       // subset 0 + subset 1
+                        const int key = bc7_mode_order(mode) * 64 + partition;
+                        if (totalError < work.error || (totalError == work.error && key < work.key))
+                        {
+                            work.error = totalError;
+                            work.key = key;
+                            work.mode = mode;
+                            work.sub = partition;
+                            const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
+                            work.ep[sA][0] = epA[k][r][0];
+                            work.ep[sA][1] = epA[k][r][1];
+                            work.ep[sB][0] = as_uint(got.z);
+                            work.ep[sB][1] = as_uint(got.w);
+                            work.sc[0] = work.sc[1] = work.sc[2] = 0;
+                        }
                     }
                 }
-                pc += 3 + nRuns;
             }
             else // kCmdDual
             {

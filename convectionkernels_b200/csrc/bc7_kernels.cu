@@ -27,33 +27,33 @@ namespace
 
     __constant__ BC7PackTables c_bc7PackTables;
 
-    // The exchange of the PAIR2 commands (bc7_core.cuh) inside one CTA.  compact() turns the per-thread "wanted classes" masks
-    // into one dense list of owner threads per class, each padded to whole 32-slot chunks; chunk k goes to warp k mod 12, so
-    // only as many warps as there are chunks walk the second subset's trials.  Results travel through entries 8 + class of the
-    // owner's gathered-pixel array gv: subset B is the smaller subset of its partition (at most 8 pixels), so during the task
-    // phase no gather touches entries 8..15 of anybody's array.
+    // The exchange of a group of PAIR2 commands (bc7_core.cuh) inside one CTA.  compact() turns the per-thread "wanted classes"
+    // masks into one dense list of owner threads per class, each padded to whole 32-slot chunks; chunk k goes to warp k mod 12,
+    // so only as many warps as there are chunks walk the second subsets' trials.  Results travel through entries 8..13 of the
+    // owner's gathered-pixel arrays (gv for the first command of the group, gw for the second): subset B is the smaller subset
+    // of its partition (at most 8 pixels), so during the task phase no gather touches entries 8..15 of anybody's arrays.
     struct BC7CtaExchange
     {
-        enum { kWarps = kBC7Threads / 32, kListSlots = kBC7Threads * 5 + kBC7PairClasses * 32 };
-        F4 *gvBase;
+        // a thread wants at most 5 classes per command (one unit of mode 1, two each of modes 3 and 7)
+        enum { kWarps = kBC7Threads / 32, kListSlots = kBC7Threads * 5 * kBC7PairGroup + kBC7PairClasses * 32 };
+        F4 *gvBase, *gwBase;
         const uint32_t *rawBase;
         uint16_t *list;             // [kListSlots]
         uint16_t *warpCounts;       // [kWarps][kBC7PairClasses]
+        int *classBase;             // [kBC7PairClasses + 1], then [kBC7PairClasses] counts
         uint8_t *flags;             // [kBC7Threads]
         uint32_t tid;
-        int classBase[kBC7PairClasses + 1], classCount[kBC7PairClasses];
 
         __device__ __forceinline__ void publish(uint32_t f) { flags[tid] = (uint8_t)f; }
         __device__ __forceinline__ int compact(uint32_t wantMask)
         {
             const uint32_t lane = tid & 31, warp = tid >> 5;
-            uint32_t ballots[kBC7PairClasses];
 #pragma unroll
             for (int c = 0; c < kBC7PairClasses; c++)
             {
-                ballots[c] = __ballot_sync(0xffffffffu, (wantMask >> c) & 1u);
+                const uint32_t ballot = __ballot_sync(0xffffffffu, (wantMask >> c) & 1u);
                 if (lane == 0)
-                    warpCounts[warp * kBC7PairClasses + c] = (uint16_t)__popc(ballots[c]);
+                    warpCounts[warp * kBC7PairClasses + c] = (uint16_t)__popc(ballot);
             }
             __syncthreads();
             int pos = 0;
@@ -68,13 +68,18 @@ namespace
                     before += (k < warp) ? n : 0u;
                     total += n;
                 }
-                classBase[c] = pos;
-                classCount[c] = (int)total;
+                if (tid == 0)
+                {
+                    classBase[c] = pos;
+                    classBase[kBC7PairClasses + 1 + c] = (int)total;
+                }
+                const uint32_t ballot = __ballot_sync(0xffffffffu, (wantMask >> c) & 1u);
                 if ((wantMask >> c) & 1u)
-                    list[pos + before + __popc(ballots[c] & ((1u << lane) - 1u))] = (uint16_t)tid;
+                    list[pos + before + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)tid;
                 pos += (int)((total + 31u) & ~31u);
             }
-            classBase[kBC7PairClasses] = pos;
+            if (tid == 0)
+                classBase[kBC7PairClasses] = pos;
             __syncthreads();
             return pos;
         }
@@ -88,21 +93,19 @@ namespace
 #pragma unroll
             for (int c = 1; c < kBC7PairClasses; c++)
                 cls = (chunk >= classBase[c]) ? c : cls;
-            int base = classBase[0], count = classCount[0];
-#pragma unroll
-            for (int c = 1; c < kBC7PairClasses; c++)
-            {
-                base = (cls == c) ? classBase[c] : base;
-                count = (cls == c) ? classCount[c] : count;
-            }
+            const int base = classBase[cls], count = classBase[kBC7PairClasses + 1 + cls];
             owner = (slot - base < count) ? (int)list[slot] : -1;
         }
         __device__ __forceinline__ uint32_t owner_flags(int owner) const { return flags[owner]; }
         __device__ __forceinline__ const uint32_t *owner_raw(int owner) const { return rawBase + owner; }
         __device__ __forceinline__ bool task_any(bool x) const { return __any_sync(0xffffffffu, x) != 0; }
-        __device__ __forceinline__ void post(int owner, int cls, const F4 &r) { gvBase[(8 + cls) * kBC7Threads + owner] = r; }
+        __device__ __forceinline__ F4 *slot_of(int owner, int cls) const
+        {
+            return (cls < kBC7PairClassesPerCommand ? gvBase + (8 + cls) * kBC7Threads : gwBase + (8 + cls - kBC7PairClassesPerCommand) * kBC7Threads) + owner;
+        }
+        __device__ __forceinline__ void post(int owner, int cls, const F4 &r) { *slot_of(owner, cls) = r; }
         __device__ __forceinline__ void sync() { __syncthreads(); }
-        __device__ __forceinline__ F4 result(int cls) const { return gvBase[(8 + cls) * kBC7Threads + tid]; }
+        __device__ __forceinline__ F4 result(int cls) const { return *slot_of((int)tid, cls); }
     };
 
     // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
@@ -233,12 +236,15 @@ namespace
 
         __shared__ uint16_t sTaskList[BC7CtaExchange::kListSlots];
         __shared__ uint16_t sWarpCounts[BC7CtaExchange::kWarps * kBC7PairClasses];
+        __shared__ int sClassBase[2 * kBC7PairClasses + 1];
         __shared__ uint8_t sOwnerFlags[kBC7Threads];
         BC7CtaExchange ex;
         ex.gvBase = sGv;
+        ex.gwBase = sGw;
         ex.rawBase = sRaw;
         ex.list = sTaskList;
         ex.warpCounts = sWarpCounts;
+        ex.classBase = sClassBase;
         ex.flags = sOwnerFlags;
         ex.tid = tid;
 
