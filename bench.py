@@ -19,7 +19,9 @@ prints ONE JSON line:
                 (N = 1 only, bounded steps)
   strong        BASELINE.json configs[4]: ONE 8192x8192 texture on rank 0, 8-block-group ranges scattered over NCCL, encoded,
                 gathered back on rank 0 inside the step (strong scaling; reported at every N so that the curve has its base)
-  latency_8block_ms   one cvtt::Kernels::EncodeBC7-sized call (8 blocks, host buffers) through the C ABI;
+  latency_8block_ms   one cvtt::Kernels::EncodeBC7-sized call (8 blocks, host buffers) through the C ABI, next to
+                reference_one_thread_8block_ms, the same call through the unmodified reference on one host thread
+                (both also in every other_configs record);
                 latency_ms_by_blocks_per_call gives the same for larger batches
 With N > 1 (torchrun, one process per GPU) every rank encodes its own 4096x4096 texture (weak scaling) and the encoded
 ranges are gathered on rank 0 with one NCCL gather inside the timed step.
@@ -440,19 +442,38 @@ def measure_strong(job, steps, warmup):
             "sharded_equals_single_gpu": differing == 0, "blocks_compared": n_blocks}
 
 
-def measure_latency(job, n_blocks=8, calls=30):
-    """One call of cvtt::Kernels::EncodeBC7 size (8 blocks) -- or a larger batch -- with host buffers through the C ABI
+def measure_latency(job, n_blocks=8, calls=30, fmt="BC7"):
+    """One call of cvtt::Kernels::Encode* size (8 blocks) -- or a larger batch -- with host buffers through the C ABI
     (wall clock, ms per call)."""
     api = job.api
-    opt, plan = options_and_plan(api, "BC7")
-    blocks = np.ascontiguousarray(synthetic_blocks("rgba8", job.rank)[4096:4096 + n_blocks])
-    out = np.empty((n_blocks, 16), np.uint8)
+    opt, plan = options_and_plan(api, fmt)
+    blocks = np.ascontiguousarray(synthetic_blocks(FORMAT_CONFIGS[fmt][2], job.rank)[4096:4096 + n_blocks])
+    out = np.empty((n_blocks, FORMAT_CONFIGS[fmt][4]), np.uint8)
     for _ in range(3):
-        api.encode("BC7", blocks, opt, plan, out=out)
+        api.encode(fmt, blocks, opt, plan, out=out)
     t0 = time.perf_counter()
     for _ in range(calls):
-        api.encode("BC7", blocks, opt, plan, out=out)
+        api.encode(fmt, blocks, opt, plan, out=out)
     return (time.perf_counter() - t0) / calls * 1e3
+
+
+def reference_latency(fmt, n_blocks=8, calls=5):
+    """the same call through the unmodified reference on ONE host thread (oracle/_ref), ms per call; None without it"""
+    try:
+        from oracle.loader import Reference
+        from convectionkernels_b200 import api
+        R = Reference()
+        opt, plan = options_and_plan(api, fmt)
+        ob = np.frombuffer(bytes(memoryview(opt)), np.uint8)
+        pb = None if plan is None else np.frombuffer(plan.tobytes(), np.uint8)
+        blocks = np.ascontiguousarray(synthetic_blocks(FORMAT_CONFIGS[fmt][2], 0)[4096:4096 + n_blocks])
+        R.encode(fmt, blocks, ob, pb, threads=1)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            R.encode(fmt, blocks, ob, pb, threads=1)
+        return (time.perf_counter() - t0) / calls * 1e3
+    except Exception:
+        return None
 
 
 def main():
@@ -494,6 +515,8 @@ def main():
             for f in OTHER_CONFIGS:
                 r = measure_format(job, f, max(2, min(args.steps, 3)), 3, with_cpu=True)
                 r["config"] = make_config(f, 1)
+                r["latency_8block_ms"] = measure_latency(job, fmt=f)
+                r["reference_one_thread_8block_ms"] = reference_latency(f)
                 others[f] = r
         strong = measure_strong(job, max(2, min(args.steps, 3)), 3)
 
@@ -505,6 +528,7 @@ def main():
                 "roofline": main_rec["roofline"], "cpu_baseline": main_rec["cpu_baseline"]}
         if extras:
             line["latency_8block_ms"] = latency
+            line["reference_one_thread_8block_ms"] = reference_latency("BC7") if job.world == 1 else None
             if latency_curve is not None:
                 line["latency_ms_by_blocks_per_call"] = latency_curve      # host buffers, one call of that many blocks
             line["other_configs"] = others if others is not None else "measured at N=1 only"
