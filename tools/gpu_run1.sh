@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-for k in 1 2 4 8 1000; do echo -n "sync period $k: "; CVTTB200_BC7_SHAPE_SYNC=$k python tools/time_format.py BC7 2>&1 | tail -1 | cut -c1-120; done | tee gpurun_out/shape_sync.txt
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/bench_under_ncu.log 2>&1
+bash tools/prof_one.sh BC7 bc7_encode bc7_r2h
