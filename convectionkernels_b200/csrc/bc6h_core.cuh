@@ -1135,45 +1135,16 @@ namespace cvttb200
     }
 
     // ---------------------------------------------------------------------------------------------------------
-    // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).
+    // The whole search for one block and the bit packing tail (BC67.cpp:2990-3050).  The endpoint fits of a call's partition
+    // (BC67.cpp:2739-2774) are made when the call runs, not kept in a table of all 33 across the search: a fit is ~1 % of a
+    // call, the table was 1.6 KB of local memory per thread (more than the L2 holds for the resident threads).
     template<bool SIGNED, bool FAST, int STRIDE, class Vote>
     CVTT_HD void bc6h_encode_block(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, uint32_t out[4])
     {
         BC6HBest best;
         bc6h_best_reset(best);
-
-        // endpoint fits of the 32 partitions and of the whole block (BC67.cpp:2739-2774)
-        float ufepBase[33][6], ufepOffs[33][6];
-        for (int p = 0; p < 32; p++)
-            for (int subset = 0; subset < 2; subset++)
-            {
-                const uint32_t mask = subset ? T.partitionMask[p] : ((uint32_t)~T.partitionMask[p] & 0xffffu);
-                int n = 0;
-                for (uint32_t m = mask; m; m &= m - 1)
-                    n++;
-                endpoint_selector3_masked(L, mask, n, P.w, ufepBase[p] + subset * 3, ufepOffs[p] + subset * 3);
-            }
-        endpoint_selector3_masked(L, 0xffffu, 16, P.w, ufepBase[32], ufepOffs[32]);
-        for (int ch = 0; ch < 3; ch++)
-            ufepBase[32][3 + ch] = ufepOffs[32][3 + ch] = 0.0f;
-
-        // g_hdrModesExistForPrecision (BC67.cpp:144-149)
-        const uint32_t existSingle = (1u << 10) | (1u << 11) | (1u << 12) | (1u << 16);
-        const uint32_t existPartitioned = (1u << 6) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 10) | (1u << 11);
-        for (int partitionedInt = 0; partitionedInt < 2; partitionedInt++)
-            for (int aPrec = 16; aPrec >= 0; aPrec--)
-            {
-                if (!(((partitionedInt ? existPartitioned : existSingle) >> aPrec) & 1))
-                    continue;
-                if (partitionedInt)
-                {
-                    for (int p = 0; p < 32; p++)
-                        bc6h_partition<SIGNED, FAST, 8, STRIDE>(P, T, L, vote, true, aPrec, p, ufepBase[p], ufepOffs[p], best);
-                }
-                else
-                    bc6h_partition<SIGNED, FAST, 16, STRIDE>(P, T, L, vote, false, aPrec, 0, ufepBase[32], ufepOffs[32], best);
-            }
-
+        for (int call = 0; call < kBC6HCalls; call++)
+            bc6h_run_call<SIGNED, FAST, STRIDE>(P, T, L, vote, call, best);
         bc6h_pack_block<SIGNED, FAST, STRIDE>(P, T, L, best, out);
     }
 }

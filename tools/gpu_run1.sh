@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/bench_under_ncu.log 2>&1
-bash tools/prof_one.sh BC7 bc7_encode bc7_r2h
+python tools/time_format.py BC6HU | tee gpurun_out/time_bc6hu.json
+python tools/time_format.py BC6HS | tee gpurun_out/time_bc6hs.json
+python -m pytest tests/test_bc6h_gpu.py -q -m gpu -x 2>&1 | tail -3
