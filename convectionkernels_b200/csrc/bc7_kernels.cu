@@ -21,7 +21,7 @@ namespace
     constexpr int kBC7FinishThreads = 128;
     // Small-call launch: slice counts the streams are compiled for.  The largest one whose grid fits one wave of the 148 SMs
     // is taken; calls too large for the smallest take the normal launch.
-    constexpr int kBC7SliceChoices[] = { 144, 48, 24, 12, 6, 3 };
+    constexpr int kBC7SliceChoices[] = { 144, 48, 24, 12, 6, 3, 2 };
     // per thread: 16 packed pixels + 16 gathered biased pixels + 16 gathered pre-weighted pixels
     constexpr size_t kBC7SmemBytes = (size_t)kBC7Threads * 16 * (sizeof(uint32_t) + 2 * sizeof(F4));
 

@@ -170,11 +170,11 @@ def test_two_lane_division_is_ieee():
     assert api.selftest(samples=1 << 28, seed=7) == 0
 
 
-@pytest.mark.parametrize("n", [8, 16, 40, 264, 1152, 1160, 2312, 4616, 9224, 18816, 18824])
+@pytest.mark.parametrize("n", [8, 16, 40, 264, 1152, 1160, 2312, 4616, 9224, 18816, 18824, 28416, 28424])
 def test_small_calls_take_the_split_launch_and_match_the_reference(reference, n):
-    """Calls of up to 18 816 blocks take the small-call launch: the search of every block dealt out to 48 / 24 / 12 / 6 / 3
-    CTAs (whichever still fits one wave) and the winners reduced by bc7_finish_kernel -- the reference's own call size, 8
-    blocks, included; 18 824 is the first size of the normal launch.  Bit-exact either way."""
+    """Calls of up to 28 416 blocks take the small-call launch: the search of every block dealt out to 144 / 48 / 24 / 12 / 6 /
+    3 / 2 CTAs (whichever still fits one wave) and the winners reduced by bc7_finish_kernel -- the reference's own call size,
+    8 blocks, included; 28 424 is the first size of the normal launch.  Bit-exact either way."""
     blocks = synth.image_to_blocks(synth.mixed_rgba8(512, 1024, seed=77))[:n]
     o, p = api.Options(), api.BC7EncodingPlan()
     api.ConfigureBC7EncodingPlanFromQuality(p, 100)
