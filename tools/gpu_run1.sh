@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_bc7_gpu.py -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/pytest_bc7.log
-python tools/time_small_calls.py BC7 18816 18824 24000 28416 28424 | tee gpurun_out/small_bc7_s2.json
-CVTTB200_BC7_SPLIT=0 python tools/time_small_calls.py BC7 18824 24000 28416 | tee -a gpurun_out/small_bc7_s2.json
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+: > gpurun_out/threads_small.jsonl
+python tools/time_threads_small.py 8 | tee -a gpurun_out/threads_small.jsonl
+for s in 48 12 6 3; do CVTTB200_BC7_SPLIT=$s python tools/time_threads_small.py 8 | tee -a gpurun_out/threads_small.jsonl; done
+CVTTB200_BC7_SPLIT=0 python tools/time_threads_small.py 8 | tee -a gpurun_out/threads_small.jsonl
