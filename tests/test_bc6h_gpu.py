@@ -53,6 +53,23 @@ def test_small_calls_take_the_split_launch_and_match_the_reference(reference, fm
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("fmt,flags", [("BC6HU", None), ("BC6HS", None), ("BC6HU", api.Flags.Default | 0x40), ("BC6HS", api.Flags.Default | 0x240)])
+def test_every_slice_count_equals_the_normal_launch(fmt, flags):
+    """75 776 random blocks in one call take the normal launch (verified against the reference above and in bench.py); the same
+    blocks in calls of 8 ... 37 888 take the small-call launch with 196 ... 2 ranges.  Groups are independent, so every call
+    must return the corresponding bytes of the big one -- random blocks, so every group exercises the mode-loop coupling."""
+    blocks = synth.random_blocks_f16(75776, seed=91, signed=fmt.endswith("S"))
+    o = api.Options()
+    if flags is not None:
+        o.flags = flags
+    whole = api.encode(fmt, blocks, o)
+    start = 0
+    for n in (8, 16, 128, 640, 1536, 3072, 6144, 12288, 37888):
+        got = api.encode(fmt, np.ascontiguousarray(blocks[start:start + n]), o)
+        assert (got == whole[start:start + n]).all(), (n, first_mismatch(whole[start:start + n], got))
+        start += n
+
+
 def test_group_coupling_is_reproduced(reference):
     """the same block encodes differently next to different neighbours; the kernel must follow the reference"""
     base = synth.random_blocks_f16(64, seed=5)

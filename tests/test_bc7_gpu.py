@@ -183,6 +183,22 @@ def test_small_calls_take_the_split_launch_and_match_the_reference(reference, n)
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("quality", [100, 55])
+def test_every_slice_count_equals_the_normal_launch(quality):
+    """65 536 random blocks in one call take the normal launch; the same blocks in calls of 8 ... 28 416 take the small-call launch
+    with 144 ... 2 slices.  Groups are independent, so every call must return the corresponding bytes of the big one."""
+    blocks = synth.random_blocks_rgba8(65536, seed=92)
+    blocks[::3, :, 3] = 255                      # a third of the blocks opaque: groups of every class
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, quality)
+    whole = api.EncodeBC7(blocks, o, p)
+    start = 0
+    for n in (8, 384, 1152, 2304, 4608, 9216, 18816, 28416):
+        got = api.EncodeBC7(np.ascontiguousarray(blocks[start:start + n]), o, p)
+        assert (got == whole[start:start + n]).all(), (n, first_mismatch(whole[start:start + n], got))
+        start += n
+
+
 @pytest.mark.parametrize("flags,quality", [(0x208, 100), (0x008, 37), (0x000, 100), (0x000, 1)])
 def test_small_calls_other_options(reference, flags, quality):
     """the small-call launch under Uniform | FastIndexing, FastIndexing with a sparse plan, slow indexing, the sparsest plan"""
