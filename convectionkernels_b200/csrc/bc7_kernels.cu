@@ -182,6 +182,30 @@ namespace
     }
 
 
+    // warp -> four groups: in call order (counts == nullptr, the smallest calls skip the classification), else (class, four groups
+    // of that class) with the expensive classes first, so that the tail of the launch is filled by the cheap opaque warps
+    __device__ __forceinline__ void bc7_map_block(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint32_t nGroups, uint32_t warp, uint32_t lane,
+                                                  bool &active, uint32_t &block)
+    {
+        if (counts == nullptr)
+        {
+            const uint32_t group = warp * 4 + (lane >> 3);
+            active = group < nGroups;
+            block = active ? group * 8 + (lane & 7) : 0;
+            return;
+        }
+        const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
+        const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
+        uint32_t cls, clsCount;
+        if (warp < w1) { cls = 1; clsCount = n1; }
+        else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
+        else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
+        else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
+        const uint32_t slot = warp * 4 + (lane >> 3);
+        active = slot < clsCount;
+        block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
+    }
+
     // One thread per block, warp = 4 reference groups of one class; see cvtt_common.cuh / bc7_core.cuh.
     //  * input: each thread reads its own 64-byte PixelBlockU8 with four 128-bit loads (512 B contiguous per group) and
     //    keeps it packed in shared memory, laid out [pixel][thread] (conflict-free)
@@ -191,7 +215,7 @@ namespace
     template<bool FAST, bool PUNCH>
     __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
     bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
-                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint4 *__restrict__ candidates)
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint4 *__restrict__ candidates, uint32_t warpBase, uint32_t candStride)
     {
         extern __shared__ __align__(16) unsigned char smem[];
         F4 *sGv = reinterpret_cast<F4 *>(smem);
@@ -202,32 +226,14 @@ namespace
 
         // warp -> (class, four groups of that class); the expensive classes go first so that the tail of the launch is
         // filled by the cheap opaque warps
-        // Small-call launch (P.splitSlices > 0, launch_bc7): blockIdx.y = the slice of the search this CTA runs for its blocks
-        // (the smallest calls skip the classification: counts == nullptr, groups in call order); the winners of the slices go to `candidates` and bc7_finish_kernel
-        // reduces them.  All warps of a CTA still walk one stream, so they stay in step as in the normal launch.
+        // Sliced launch (P.splitSlices > 0; launch_bc7: small calls, and the partial second wave of a call of one to one and a
+        // third waves): blockIdx.y = the slice of the search this CTA runs for its blocks; the winners of the slices go to
+        // `candidates` ([slice][thread of the launch]) and bc7_finish_kernel reduces them.  All warps of a CTA still walk one
+        // stream, so they stay in step.
         const bool split = P.splitSlices > 0;
-        uint32_t warp = blockIdx.x * (kBC7Threads / 32) + (tid >> 5);
         bool active;
         uint32_t block;
-        if (counts == nullptr)
-        {
-            const uint32_t group = warp * 4 + (lane >> 3);
-            active = group < nGroups;
-            block = active ? group * 8 + (lane & 7) : 0;
-        }
-        else
-        {
-            const uint32_t n0 = counts[0], n1 = counts[1], n2 = counts[2];
-            const uint32_t w1 = (n1 + 3) >> 2, w2 = (n2 + 3) >> 2, w0 = (n0 + 3) >> 2;
-            uint32_t cls, clsCount;
-            if (warp < w1) { cls = 1; clsCount = n1; }
-            else if (warp < w1 + w2) { cls = 2; clsCount = n2; warp -= w1; }
-            else if (warp < w1 + w2 + w0) { cls = 0; clsCount = n0; warp -= w1 + w2; }
-            else { cls = 0; clsCount = 0; }      // surplus warp of the last CTA: no work, but it keeps the CTA's barriers company
-            const uint32_t slot = warp * 4 + (lane >> 3);
-            active = slot < clsCount;
-            block = active ? lists[(size_t)cls * nGroups + slot] * 8 + (lane & 7) : 0;
-        }
+        bc7_map_block(counts, lists, nGroups, warpBase + blockIdx.x * (kBC7Threads / 32) + (tid >> 5), lane, active, block);
 
         BC7Lane<kBC7Threads> L;
         L.raw = sRaw + tid;
@@ -315,7 +321,7 @@ namespace
             {
                 BC7Candidate c;
                 bc7_candidate_pack(work, c);
-                uint4 *dst = candidates + ((size_t)blockIdx.y * nGroups * 8 + block) * 2;
+                uint4 *dst = candidates + ((size_t)blockIdx.y * candStride + blockIdx.x * kBC7Threads + tid) * 2;
                 dst[0] = make_uint4(c.a[0], c.a[1], c.a[2], c.a[3]);
                 dst[1] = make_uint4(c.b[0], c.b[1], c.b[2], c.b[3]);
             }
@@ -327,15 +333,21 @@ namespace
             out[block] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 
-    // Second kernel of the small-call launch: one thread per block takes the (error, reference key) minimum of the slices'
-    // winners, selects the winner's indexes and packs the block.
+    // Second kernel of a sliced launch: thread t of the launch (same warp -> blocks mapping as the encode kernel) takes the
+    // (error, reference key) minimum of the slices' winners for its block, selects the winner's indexes and packs the block.
     template<bool FAST>
     __global__ void __launch_bounds__(kBC7FinishThreads)
-    bc7_finish_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks, const uint4 *__restrict__ candidates)
+    bc7_finish_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, const uint4 *__restrict__ candidates, uint32_t warpBase, uint32_t candStride)
     {
         __shared__ uint32_t sRaw[16 * kBC7FinishThreads];
-        const uint32_t tid = threadIdx.x, block = blockIdx.x * kBC7FinishThreads + tid;
-        if (block >= nBlocks)
+        const uint32_t tid = threadIdx.x, t = blockIdx.x * kBC7FinishThreads + tid;
+        if (t >= candStride)
+            return;
+        bool active;
+        uint32_t block;
+        bc7_map_block(counts, lists, nGroups, warpBase + (t >> 5), t & 31, active, block);
+        if (!active)
             return;
         const uint4 *src = in + (size_t)block * 4;
 #pragma unroll
@@ -355,7 +367,7 @@ namespace
         bc7_work_reset(work);
         for (int s = 0; s < P.splitSlices; s++)
         {
-            const uint4 *c4 = candidates + ((size_t)s * nBlocks + block) * 2;
+            const uint4 *c4 = candidates + ((size_t)s * candStride + t) * 2;
             const uint4 a = __ldg(c4), b = __ldg(c4 + 1);
             BC7Candidate c;
             c.a[0] = a.x; c.a[1] = a.y; c.a[2] = a.z; c.a[3] = a.w;
@@ -408,7 +420,9 @@ namespace cvttb200
         for (size_t i = 0; i < ctx.plans.size(); i++)
             if (ctx.plans[i].form == form && memcmp(&ctx.plans[i].plan, &plan, sizeof(plan)) == 0)
             {
-                *dCmds = ctx.plans[i].dCmds;
+                // most recently used last: a launch that looks up two streams must not lose the first to the second's eviction
+                std::rotate(ctx.plans.begin() + (ptrdiff_t)i, ctx.plans.begin() + (ptrdiff_t)i + 1, ctx.plans.end());
+                *dCmds = ctx.plans.back().dCmds;
                 return CVTTB200_OK;
             }
         std::vector<uint32_t> cmds;
@@ -467,9 +481,11 @@ namespace cvttb200
         // CTAs (blockIdx.y; kBC7StreamSplit sub-streams, same blocks, disjoint trials) and bc7_finish_kernel takes the
         // (error, reference key) minimum of their winners -- the same block, since the order of the trials is free.
         static const long splitOverride = getenv("CVTTB200_BC7_SPLIT") ? atol(getenv("CVTTB200_BC7_SPLIT")) : -1;      // A/B: 0 = never, n = n slices
+        static const long tailOverride = getenv("CVTTB200_BC7_TAIL") ? atol(getenv("CVTTB200_BC7_TAIL")) : -1;         // A/B: 0 = no sliced second wave
         // The small-call launch takes its groups in call order: the classification pre-pass brings up to three more partially
         // filled warps, which costs more slices at the CTA-count steps than same-class warps gain (measured both ways).
         const unsigned plainWarps = (nGroups + 3) / 4, classWarps = nGroups / 4 + 3;
+        const unsigned numSMs = (unsigned)ctx.numSMs;
         int slices = 0;
         if (pairCommands && nGroups > 0)
         {
@@ -477,23 +493,45 @@ namespace cvttb200
                 slices = (int)splitOverride;
             else if (splitOverride < 0)
                 for (int k = 0; k < (int)(sizeof(kBC7SliceChoices) / sizeof(kBC7SliceChoices[0])) && !slices; k++)
-                    if ((plainWarps + ctaWarps - 1) / ctaWarps * (unsigned)kBC7SliceChoices[k] <= (unsigned)ctx.numSMs)
+                    if ((plainWarps + ctaWarps - 1) / ctaWarps * (unsigned)kBC7SliceChoices[k] <= numSMs)
                         slices = kBC7SliceChoices[k];
         }
         const bool classify = !slices;
-        P.splitSlices = slices;
-        const int form = slices ? (kBC7StreamSplit | (slices << 8)) : (pairCommands ? kBC7StreamPair : kBC7StreamPlain);
-        const uint32_t *dCmds = nullptr;
-        int rc = get_plan_commands(ctx, plan, form, &dCmds);
+        const unsigned warps = classify ? classWarps : plainWarps;
+        const unsigned ctas = (warps + ctaWarps - 1) / ctaWarps;
+
+        // Calls of one to one and a third waves (one CTA per SM; a 1024 x 1024 texture is 1.15): the CTAs behind the whole wave
+        // would hold a few SMs for a whole CTA time while the others idle, so they are launched sliced as well -- the same warps
+        // (the tail of the class order, the cheap opaque groups), with the slice count that still fits the wave, three at
+        // least.  65 536 blocks: 11.3 -> 10.0 ms.  Two slices lose (81 920 blocks: 11.7 -> 12.2 ms), and with two or more whole
+        // waves in front the last CTAs fill in dynamically and slicing them is neutral or worse (524 288 blocks: 9.46 -> 9.20
+        // Mblocks/s), so it stays with the one case.
+        unsigned mainCtas = slices ? 0u : ctas, tailCtas = 0;
+        int tailSlices = 0;
+        if (!slices && pairCommands && tailOverride != 0 && ctas > numSMs && ctas < 2 * numSMs && numSMs / (ctas - numSMs) >= 3)
+        {
+            tailCtas = ctas - numSMs;
+            mainCtas = numSMs;
+            tailSlices = (int)std::min<unsigned>(numSMs / tailCtas, 48u);
+        }
+        const int sliced = slices ? slices : tailSlices;            // slice count of the sliced launch, if there is one
+        const unsigned slicedCtas = slices ? ctas : tailCtas;
+        const uint32_t slicedWarpBase = slices ? 0u : mainCtas * ctaWarps, candStride = slicedCtas * kBC7Threads;
+
+        const uint32_t *dCmds = nullptr, *dCmdsSliced = nullptr;
+        int rc = CVTTB200_OK;
+        if (mainCtas)
+            rc = get_plan_commands(ctx, plan, pairCommands ? kBC7StreamPair : kBC7StreamPlain, &dCmds);
+        if (rc == CVTTB200_OK && sliced)
+            rc = get_plan_commands(ctx, plan, kBC7StreamSplit | (sliced << 8), &dCmdsSliced);
         if (rc != CVTTB200_OK)
             return rc;
-        P.cmds = dCmds;
 
         // stream-ordered scratch: group classification (counts[4] then lists[3][nGroups]), then the slices' winners
         const size_t classifyBytes = classify ? (4 + 3 * (size_t)nGroups) * sizeof(uint32_t) : 0;
         const size_t candOffset = (classifyBytes + 15) & ~(size_t)15;
         unsigned char *dScratchBytes = nullptr;
-        rc = pool_alloc(ctx, (void **)&dScratchBytes, candOffset + (size_t)slices * nBlocks * 2 * sizeof(uint4) + 16, stream);
+        rc = pool_alloc(ctx, (void **)&dScratchBytes, candOffset + (size_t)sliced * candStride * 2 * sizeof(uint4) + 16, stream);
         if (rc != CVTTB200_OK)
             return rc;
         uint32_t *dScratch = classify ? (uint32_t *)dScratchBytes : nullptr;
@@ -505,43 +543,45 @@ namespace cvttb200
             g_launches++;
         }
         const uint32_t *dCounts = dScratch, *dLists = classify ? dScratch + 4 : nullptr;
-        const unsigned warps = classify ? classWarps : plainWarps;
-        const unsigned ctas = (warps + ctaWarps - 1) / ctaWarps;
+        const uint4 *in = (const uint4 *)dIn;
+        uint4 *out = (uint4 *)dOut;
 
-        if (slices)
+        // at most three partially filled warps (one per class).  Two other ways of avoiding a partial last wave were measured
+        // and dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
+        // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
+        // 1 048 576 blocks, 3 % slower at 524 288).
+        if (mainCtas)
         {
-            const dim3 grid(ctas, (unsigned)slices);
-            const unsigned finishGrid = (unsigned)((nBlocks + kBC7FinishThreads - 1) / kBC7FinishThreads);
+            P.splitSlices = 0;
+            P.cmds = dCmds;
+            if (fast && !punch)
+                bc7_encode_kernel<true, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+            else if (!fast && !punch)
+                bc7_encode_kernel<false, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+            else if (fast)
+                bc7_encode_kernel<true, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+            else
+                bc7_encode_kernel<false, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+            g_launches++;
+        }
+        if (sliced)
+        {
+            P.splitSlices = sliced;
+            P.cmds = dCmdsSliced;
+            const dim3 grid(slicedCtas, (unsigned)sliced);
+            const unsigned finishGrid = (candStride + kBC7FinishThreads - 1) / kBC7FinishThreads;
             if (fast)
             {
-                bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, nullptr, nGroups, dCounts, dLists, dCand);
-                bc7_finish_kernel<true><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks, dCand);
+                bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
+                bc7_finish_kernel<true><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, in, out, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
             }
             else
             {
-                bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, nullptr, nGroups, dCounts, dLists, dCand);
-                bc7_finish_kernel<false><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, (uint32_t)nBlocks, dCand);
+                bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
+                bc7_finish_kernel<false><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, in, out, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
             }
             g_launches += 2;
-            CVTT_CUDA(cudaFreeAsync(dScratchBytes, stream));
-            CVTT_CUDA(cudaGetLastError());
-            return CVTTB200_OK;
         }
-
-        // at most three partially filled warps (one per class).  Two ways of avoiding the partial last wave were measured and
-        // dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
-        // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
-        // 1 048 576 blocks, 3 % slower at 524 288).
-        const unsigned grid = ctas;
-        if (fast && !punch)
-            bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
-        else if (!fast && !punch)
-            bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
-        else if (fast)
-            bc7_encode_kernel<true, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
-        else
-            bc7_encode_kernel<false, true><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, (const uint4 *)dIn, (uint4 *)dOut, nGroups, dScratch, dScratch + 4, nullptr);
-        g_launches++;
         CVTT_CUDA(cudaFreeAsync(dScratchBytes, stream));
         CVTT_CUDA(cudaGetLastError());
         return CVTTB200_OK;

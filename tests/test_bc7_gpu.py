@@ -183,6 +183,21 @@ def test_small_calls_take_the_split_launch_and_match_the_reference(reference, n)
     assert (got == want).all(), first_mismatch(want, got)
 
 
+@pytest.mark.parametrize("n,launches", [(65536, 4), (75576, 4), (81920, 2), (131072, 2)])
+def test_partial_second_wave_is_sliced_and_matches_the_reference(reference, n, launches):
+    """Calls of one to one and a third waves (148 SMs x 12 warps x 32 blocks; a 1024 x 1024 texture is 1.15): the CTAs behind
+    the whole wave run as a sliced launch of their own (65 536 blocks: 23 CTAs x 6 slices).  Larger calls and calls whose second
+    wave is more than a third full keep the single launch.  Bit-exact."""
+    blocks = synth.image_to_blocks(synth.mixed_rgba8(1024, 2048, seed=79))[:n]
+    o, p = api.Options(), api.BC7EncodingPlan()
+    api.ConfigureBC7EncodingPlanFromQuality(p, 100)
+    want = reference.encode("BC7", blocks, _opt_bytes(o), np.frombuffer(p.tobytes(), np.uint8), threads=0)
+    before = api.launch_count()
+    got = api.EncodeBC7(blocks, o, p)
+    assert api.launch_count() == before + launches      # classification, whole wave (, sliced second wave, its finish kernel)
+    assert (got == want).all(), first_mismatch(want, got)
+
+
 @pytest.mark.parametrize("quality", [100, 55])
 def test_every_slice_count_equals_the_normal_launch(quality):
     """65 536 random blocks in one call take the normal launch; the same blocks in calls of 8 ... 28 416 take the small-call launch
