@@ -1,2 +1,2 @@
-python tools/time_format.py BC7 2>&1 | tail -1 | cut -c1-110
-CVTTB200_BC7_PAIR_ORDER=0 python tools/time_format.py BC7 2>&1 | tail -1 | cut -c1-110
+mkdir -p gpurun_out
+for f in ETC2_RGBA ETC1; do python tools/time_format.py $f 2>&1 | tail -1 | cut -c1-130; done | tee gpurun_out/etc_giveup.txt
