@@ -19,6 +19,39 @@ namespace
 
     __constant__ ETCTables c_etcTables;
 
+    // EAC alpha of a block whose 16 alphas are all `a`: the search is a pure function of the 16 values, so its result for the 256
+    // constant blocks is computed once per device by the search itself (eac_flat_lut_kernel) and looked up when a whole warp
+    // holds such blocks (opaque regions).  The reference runs the search every time.
+    __device__ uint2 g_eacFlatLut[256];
+
+    __global__ void eac_flat_lut_kernel()
+    {
+        int a[16];
+        for (int px = 0; px < 16; px++)
+            a[px] = (int)threadIdx.x;
+        uint32_t o[2];
+        etc_alpha_encode_block(c_etcTables, a, false, false, o);
+        g_eacFlatLut[threadIdx.x] = make_uint2(o[0], o[1]);
+    }
+
+    // 8-bit EAC alpha for one thread's block; a warp whose blocks are all constant in alpha takes the table
+    __device__ __forceinline__ void eac_alpha8(const int *alpha, uint32_t out[2])
+    {
+        bool flat = true;
+#pragma unroll
+        for (int px = 1; px < 16; px++)
+            flat = flat && alpha[px] == alpha[0];
+        if (__all_sync(0xffffffffu, flat))
+        {
+            const uint2 v = g_eacFlatLut[alpha[0]];
+            out[0] = v.x;
+            out[1] = v.y;
+            return;
+        }
+        etc_alpha_encode_block(c_etcTables, alpha, false, false, out);
+    }
+
+
 
     enum { kETCKindETC1 = 0, kETCKindETC2 = 1, kETCKindETC2RGBA = 2, kETCKindETC2Punchthrough = 3 };
 
@@ -103,7 +136,7 @@ namespace
             if (KIND == kETCKindETC2RGBA)
             {
                 uint32_t a[2];
-                etc_alpha_encode_block(c_etcTables, alpha, false, false, a);
+                eac_alpha8(alpha, a);
                 if (active)
                     reinterpret_cast<uint4 *>(out)[block] = make_uint4(etc_bswap(a[0]), etc_bswap(a[1]), etc_bswap(color[0]), etc_bswap(color[1]));
             }
@@ -119,9 +152,7 @@ namespace
     __global__ void __launch_bounds__(128)
     eac_encode_kernel(const void *__restrict__ in, uint2 *__restrict__ out, uint32_t nBlocks)
     {
-        const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
-        if (block >= nBlocks)
-            return;
+        const uint32_t block = ::min(blockIdx.x * blockDim.x + threadIdx.x, nBlocks - 1);     // surplus threads repeat the last block
         int a[16];
         if (KIND == 0)
         {
@@ -159,7 +190,10 @@ namespace
             }
         }
         uint32_t o[2];
-        etc_alpha_encode_block(c_etcTables, a, KIND != 0, KIND == 2, o);
+        if (KIND == 0)
+            eac_alpha8(a, o);
+        else
+            etc_alpha_encode_block(c_etcTables, a, true, KIND == 2, o);
         out[block] = make_uint2(etc_bswap(o[0]), etc_bswap(o[1]));
     }
 }
@@ -169,6 +203,8 @@ namespace cvttb200
     int etc_device_setup()
     {
         CVTT_CUDA(cudaMemcpyToSymbol(c_etcTables, &etc_tables(), sizeof(ETCTables)));
+        eac_flat_lut_kernel<<<1, 256>>>();
+        CVTT_CUDA(cudaGetLastError());
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
         CVTT_CUDA(cudaFuncSetAttribute(etc_encode_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kETCSmemBytes));
