@@ -215,7 +215,8 @@ namespace
     template<bool FAST, bool PUNCH>
     __global__ void __launch_bounds__(kBC7Threads, kBC7CtasPerSM)
     bc7_encode_kernel(const __grid_constant__ BC7Params P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nGroups,
-                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint4 *__restrict__ candidates, uint32_t warpBase, uint32_t candStride)
+                      const uint32_t *__restrict__ counts, const uint32_t *__restrict__ lists, uint4 *__restrict__ candidates, uint32_t warpBase, uint32_t candStride,
+                      uint32_t warpsPerCta)
     {
         extern __shared__ __align__(16) unsigned char smem[];
         F4 *sGv = reinterpret_cast<F4 *>(smem);
@@ -233,7 +234,10 @@ namespace
         const bool split = P.splitSlices > 0;
         bool active;
         uint32_t block;
-        bc7_map_block(counts, lists, nGroups, warpBase + blockIdx.x * (kBC7Threads / 32) + (tid >> 5), lane, active, block);
+        // warpsPerCta < 12 (calls of less than one wave): the CTA's first warps hold blocks, the others only take part in the
+        // barriers and in the PAIR2 task phases, so that every SM gets a CTA
+        const uint32_t warpInCta = tid >> 5;
+        bc7_map_block(counts, lists, nGroups, warpInCta < warpsPerCta ? warpBase + blockIdx.x * warpsPerCta + warpInCta : 0xffffff00u, lane, active, block);
 
         BC7Lane<kBC7Threads> L;
         L.raw = sRaw + tid;
@@ -550,18 +554,27 @@ namespace cvttb200
         // and dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
         // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
         // 1 048 576 blocks, 3 % slower at 524 288).
+        // Calls of less than one wave that are not sliced: CTAs of fewer working warps, one CTA on every SM (32 768 blocks: 148
+        // CTAs of 7 working warps instead of 86 of 12)
+        static const long spreadOverride = getenv("CVTTB200_BC7_SPREAD") ? atol(getenv("CVTTB200_BC7_SPREAD")) : -1;    // A/B: 0 = always 12 warps
+        unsigned mainWarpsPerCta = ctaWarps;
+        if (mainCtas && !sliced && mainCtas < numSMs && spreadOverride != 0)
+        {
+            mainWarpsPerCta = std::max(1u, (warps + numSMs - 1) / numSMs);
+            mainCtas = (warps + mainWarpsPerCta - 1) / mainWarpsPerCta;
+        }
         if (mainCtas)
         {
             P.splitSlices = 0;
             P.cmds = dCmds;
             if (fast && !punch)
-                bc7_encode_kernel<true, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+                bc7_encode_kernel<true, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u, mainWarpsPerCta);
             else if (!fast && !punch)
-                bc7_encode_kernel<false, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+                bc7_encode_kernel<false, false><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u, mainWarpsPerCta);
             else if (fast)
-                bc7_encode_kernel<true, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+                bc7_encode_kernel<true, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u, mainWarpsPerCta);
             else
-                bc7_encode_kernel<false, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u);
+                bc7_encode_kernel<false, true><<<mainCtas, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, out, nGroups, dCounts, dLists, nullptr, 0u, 0u, mainWarpsPerCta);
             g_launches++;
         }
         if (sliced)
@@ -572,12 +585,12 @@ namespace cvttb200
             const unsigned finishGrid = (candStride + kBC7FinishThreads - 1) / kBC7FinishThreads;
             if (fast)
             {
-                bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
+                bc7_encode_kernel<true, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride, ctaWarps);
                 bc7_finish_kernel<true><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, in, out, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
             }
             else
             {
-                bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
+                bc7_encode_kernel<false, false><<<grid, kBC7Threads, kBC7SmemBytes, stream>>>(P, in, nullptr, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride, ctaWarps);
                 bc7_finish_kernel<false><<<finishGrid, kBC7FinishThreads, 0, stream>>>(P, in, out, nGroups, dCounts, dLists, dCand, slicedWarpBase, candStride);
             }
             g_launches += 2;
