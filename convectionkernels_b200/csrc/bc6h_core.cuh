@@ -1094,14 +1094,16 @@ namespace cvttb200
         }
     }
 
-    // Calls [callBegin, callEnd) from a fresh best; running[(call - callBegin) * stride] receives the lane's best error after each
-    // call (a running minimum local to this range).  (Starting every range with the first calls of the search, to have an
-    // error to prune against, is exact too -- they precede every range -- but was measured: they cost what they save.)
+    // Calls [callBegin, callEnd) from a best that holds nothing but the error `startError`; running[(call - callBegin) * stride]
+    // receives the lane's best error after each call, a running minimum local to this range.  startError is FLT_MAX or the
+    // lane's best error after calls that PRECEDE the range (something to prune against): such calls are part of every prefix
+    // the history is asked for, so the minima stay exact.
     template<bool SIGNED, bool FAST, int STRIDE, class Vote>
-    CVTT_HD void bc6h_search_calls(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, int callBegin, int callEnd, float *running, size_t stride, bool store)
+    CVTT_HD void bc6h_search_calls(const BC6HParams &P, const BC6HTables &T, const BC6HLane<STRIDE> &L, Vote &vote, int callBegin, int callEnd, float startError, float *running, size_t stride, bool store)
     {
         BC6HBest best;
         bc6h_best_reset(best);
+        best.error = startError;
         for (int call = callBegin; call < callEnd; call++)
         {
             bc6h_run_call<SIGNED, FAST, STRIDE>(P, T, L, vote, call, best);
@@ -1110,26 +1112,22 @@ namespace cvttb200
         }
     }
 
-    // The lane's error history from the per-range running minima: history[call * stride], ranges of callsPerSlice calls.
-    // Returns the best error before call `upto` (FLT_MAX for none) and the first call that reached it (-1: nothing committed).
-    CVTT_HD float bc6h_history(const float *history, size_t stride, int callsPerSlice, int upto, int &winner)
+    // The lane's error history from the ranges' running minima, history[call * stride]: every entry is the minimum over SOME
+    // calls up to and including its own, so the running minimum of the entries is the best error after each call whatever the
+    // ranges were.  Returns the best error before call `upto` (FLT_MAX for none) and the first call that reached it (-1:
+    // nothing committed).
+    CVTT_HD float bc6h_history(const float *history, size_t stride, int upto, int &winner)
     {
-        float cur = FLT_MAX, base = FLT_MAX;
+        float cur = FLT_MAX;
         winner = -1;
-        int inSlice = 0;
         for (int call = 0; call < upto; call++)
         {
-            if (inSlice == 0)
-                base = cur;
             const float r = history[(size_t)call * stride];
-            const float g = (r < base) ? r : base;
-            if (g < cur)
+            if (r < cur)
             {
-                cur = g;
+                cur = r;
                 winner = call;
             }
-            if (++inSlice == callsPerSlice)
-                inSlice = 0;
         }
         return cur;
     }

@@ -72,7 +72,10 @@ namespace
 
     // Small-call launch, first kernel (bc6h_core.cuh, "The search as a numbered sequence of CALLS"): blockIdx.y = a range of
     // callsPerSlice calls of the search, run from a fresh best for the CTA's blocks; only the error history leaves the kernel:
-    // history[call * nBlocks + block].
+    // history[call * nBlocks + block].  (Ranges that start from the error of the four one-subset calls, done by a launch of
+    // their own first, are exact too -- bc6h_search_calls, tests/test_bc6h_host.py -- and were measured: BC6HU 4 % slower at
+    // 512-8192 blocks, BC6HS 12 % faster at 4096-16 384; what prunes in the sequential search is the best PARTITION found so
+    // far, not the one-subset modes.)
     template<bool SIGNED, bool FAST>
     __global__ void __launch_bounds__(kBC6HThreads, 4)
     bc6h_search_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint32_t nBlocks, int callsPerSlice, float *__restrict__ history)
@@ -87,14 +90,14 @@ namespace
         SegmentVote vote;
         vote.segMask = 0xffu << (tid & 24);
         const int callBegin = (int)blockIdx.y * callsPerSlice, callEnd = ::min((int)kBC6HCalls, callBegin + callsPerSlice);
-        bc6h_search_calls<SIGNED, FAST, kBC6HThreads>(P, c_bc6hTables, L, vote, callBegin, callEnd, history + (size_t)callBegin * nBlocks + (active ? block : 0), nBlocks, active);
+        bc6h_search_calls<SIGNED, FAST, kBC6HThreads>(P, c_bc6hTables, L, vote, callBegin, callEnd, FLT_MAX, history + (size_t)callBegin * nBlocks + (active ? block : 0), nBlocks, active);
     }
 
     // Small-call launch, second kernel: warp = (group, k).  Its first eight lanes hold the group's blocks; they re-run the k-th
     // distinct winner call of the group from the lanes' true entry errors, and the lanes whose winner it is pack their block.
     template<bool SIGNED, bool FAST>
     __global__ void __launch_bounds__(kBC6HThreads, 4)
-    bc6h_resolve_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks, int callsPerSlice, const float *__restrict__ history)
+    bc6h_resolve_kernel(const __grid_constant__ BC6HParams P, const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t nBlocks, const float *__restrict__ history)
     {
         extern __shared__ __align__(16) unsigned char smem[];
         const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -108,7 +111,7 @@ namespace
         const float *hist = history + (active ? block : 0);
         int winner = -1;
         if (active)
-            bc6h_history(hist, nBlocks, callsPerSlice, kBC6HCalls, winner);
+            bc6h_history(hist, nBlocks, kBC6HCalls, winner);
         // k-th distinct winner of the group, in lane order
         int call = -1, count = 0;
         int seen[8];
@@ -142,7 +145,7 @@ namespace
         }
         int unused;
         // the lanes without a block can never be better than their best: they add no work to the warp's votes
-        best.error = active ? bc6h_history(hist, nBlocks, callsPerSlice, call, unused) : -FLT_MAX;
+        best.error = active ? bc6h_history(hist, nBlocks, call, unused) : -FLT_MAX;
 
         SegmentVote vote;
         vote.segMask = 0xffu << (tid & 24);
@@ -191,7 +194,7 @@ namespace cvttb200
         bc6h_search_kernel<SIGNED, FAST><<<dim3(ctas, slices), kBC6HThreads, smem, stream>>>(P, in, (uint32_t)nBlocks, callsPerSlice, dHistory);
         // one warp per (group, distinct winner call): eight per group, the surplus ones leave at once
         const unsigned resolveCtas = (unsigned)((nBlocks / 8 * 8 + kBC6HThreads / 32 - 1) / (kBC6HThreads / 32));
-        bc6h_resolve_kernel<SIGNED, FAST><<<resolveCtas, kBC6HThreads, smem, stream>>>(P, in, out, (uint32_t)nBlocks, callsPerSlice, dHistory);
+        bc6h_resolve_kernel<SIGNED, FAST><<<resolveCtas, kBC6HThreads, smem, stream>>>(P, in, out, (uint32_t)nBlocks, dHistory);
         g_launches += 2;
         CVTT_CUDA(cudaFreeAsync(dHistory, stream));
         CVTT_CUDA(cudaGetLastError());

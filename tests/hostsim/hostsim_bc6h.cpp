@@ -72,8 +72,19 @@ static int encode_bc6h(const int16_t *blocks, size_t nBlocks, uint8_t *out, cons
 // lanes' true entry errors.  One group = eight host threads.
 namespace
 {
+    // what a range starts from: the lane's best error after the first seedCalls calls of the search, when they precede the range
+    // (the kernel runs those calls in a launch of their own, before the ranges that read them)
+    float seed_error(const float *hist, size_t stride, int callBegin, int seedCalls)
+    {
+        float e = FLT_MAX;
+        if (callBegin >= seedCalls)
+            for (int c = 0; c < seedCalls; c++)
+                e = std::min(e, hist[(size_t)c * stride]);
+        return e;
+    }
+
     template<bool SIGNED, bool FAST>
-    void run_lane_split(int lane, GroupShared *groupShared, GroupShared *warpShared, const BC6HParams *P, const int16_t *blocks, size_t nBlocks, uint8_t *out, int callsPerSlice, float *history, int *winners)
+    void run_lane_split(int lane, GroupShared *groupShared, GroupShared *warpShared, const BC6HParams *P, const int16_t *blocks, size_t nBlocks, uint8_t *out, int callsPerSlice, int seedCalls, float *history, int *winners)
     {
         HostWarpVote vote;
         vote.group.g = groupShared;
@@ -93,9 +104,9 @@ namespace
                 bc6h_load_pixel<SIGNED>(*P, L, px, src[px * 4 + 0], src[px * 4 + 1], src[px * 4 + 2]);
             float *hist = history + block;          // [call][nBlocks]
             for (int callBegin = 0; callBegin < kBC6HCalls; callBegin += callsPerSlice)
-                bc6h_search_calls<SIGNED, FAST, 1>(*P, T, L, vote, callBegin, std::min<int>(kBC6HCalls, callBegin + callsPerSlice), hist + (size_t)callBegin * nBlocks, nBlocks, true);
+                bc6h_search_calls<SIGNED, FAST, 1>(*P, T, L, vote, callBegin, std::min<int>(kBC6HCalls, callBegin + callsPerSlice), seed_error(hist, nBlocks, callBegin, seedCalls), hist + (size_t)callBegin * nBlocks, nBlocks, true);
             int winner;
-            bc6h_history(hist, nBlocks, callsPerSlice, kBC6HCalls, winner);
+            bc6h_history(hist, nBlocks, kBC6HCalls, winner);
             winners[block] = winner;
             vote.any(false);            // barrier: every lane of the group has published its winner
             BC6HBest mine;
@@ -119,7 +130,7 @@ namespace
                 int unused;
                 BC6HBest best;
                 bc6h_best_reset(best);
-                best.error = bc6h_history(hist, nBlocks, callsPerSlice, call, unused);
+                best.error = bc6h_history(hist, nBlocks, call, unused);
                 bc6h_run_call<SIGNED, FAST, 1>(*P, T, L, vote, call, best);
                 if (winner == call)
                     mine = best;
@@ -132,7 +143,7 @@ namespace
     }
 }
 
-extern "C" int hostsim_encode_bc6h_split(const int16_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, int isSigned, const float *rcpTable, int callsPerSlice)
+extern "C" int hostsim_encode_bc6h_split(const int16_t *blocks, size_t nBlocks, uint8_t *out, const OptionsPOD *options, int isSigned, const float *rcpTable, int callsPerSlice, int seedCalls)
 {
     if (nBlocks % 8 || callsPerSlice < 1)
         return -1;
@@ -149,9 +160,9 @@ extern "C" int hostsim_encode_bc6h_split(const int16_t *blocks, size_t nBlocks, 
     for (int lane = 0; lane < 8; lane++)
     {
         if (isSigned)
-            threads.emplace_back(fast ? run_lane_split<true, true> : run_lane_split<true, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, history.data(), winners.data());
+            threads.emplace_back(fast ? run_lane_split<true, true> : run_lane_split<true, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, seedCalls, history.data(), winners.data());
         else
-            threads.emplace_back(fast ? run_lane_split<false, true> : run_lane_split<false, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, history.data(), winners.data());
+            threads.emplace_back(fast ? run_lane_split<false, true> : run_lane_split<false, false>, lane, &group, &warp, &P, blocks, nBlocks, out, callsPerSlice, seedCalls, history.data(), winners.data());
     }
     for (auto &t : threads)
         t.join();

@@ -21,7 +21,7 @@ def hostsim_bc6h():
     H = ctypes.CDLL(out)
     H.hostsim_encode_bc6h.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     H.hostsim_encode_bc6h_warp.argtypes = H.hostsim_encode_bc6h.argtypes
-    H.hostsim_encode_bc6h_split.argtypes = H.hostsim_encode_bc6h.argtypes + [ctypes.c_int]
+    H.hostsim_encode_bc6h_split.argtypes = H.hostsim_encode_bc6h.argtypes + [ctypes.c_int, ctypes.c_int]
     return H
 
 
@@ -102,11 +102,12 @@ def test_pruning_does_not_change_results(hostsim_bc6h, monkeypatch):
     assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)
 
 
-@pytest.mark.parametrize("name,calls_per_slice", [(n, c) for n in golden_names("bc6h") for c in (4, 33)] + [("bc6hu_random", 1), ("bc6hs_random", 196), ("bc6hs_random", 7)])
-def test_small_call_launch_logic_matches_golden(hostsim_bc6h, name, calls_per_slice):
+@pytest.mark.parametrize("name,calls_per_slice,seed_calls", [(n, c, k) for n in golden_names("bc6h") for c, k in ((4, 4), (33, 0))] + [("bc6hu_random", 1, 0), ("bc6hs_random", 196, 0), ("bc6hs_random", 7, 4), ("bc6hu_random", 2, 4)])
+def test_small_call_launch_logic_matches_golden(hostsim_bc6h, name, calls_per_slice, seed_calls):
     """The small-call launch (bc6h_kernels.cu): the 196 calls of the search in independent ranges that only record error
     histories, then one re-run of each lane's winner call for its whole group with the true entry errors (bc6h_core.cuh,
-    "The search as a numbered sequence of CALLS").  Same bytes as the sequential search, group coupling included."""
+    "The search as a numbered sequence of CALLS"), with and without the ranges starting from the error of the four one-subset
+    calls.  Same bytes as the sequential search, group coupling included."""
     if name not in golden_names("bc6h"):
         pytest.skip("no such fixture")
     g = load_golden(name)
@@ -116,5 +117,5 @@ def test_small_call_launch_logic_matches_golden(hostsim_bc6h, name, calls_per_sl
     opt = np.ascontiguousarray(g["options"])
     rcp = np.ascontiguousarray(g["rcp"], dtype=np.float32)
     signed = 1 if str(g["fmt"]) == "BC6HS" else 0
-    assert hostsim_bc6h.hostsim_encode_bc6h_split(blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data, calls_per_slice) == 0
+    assert hostsim_bc6h.hostsim_encode_bc6h_split(blocks.ctypes.data, n, out.ctypes.data, opt.ctypes.data, signed, rcp.ctypes.data, calls_per_slice, seed_calls) == 0
     assert (out == g["expected"]).all(), first_mismatch(g["expected"], out)

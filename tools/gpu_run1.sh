@@ -1,13 +1,6 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/bench_under_ncu.log 2>&1
-bash tools/prof_one.sh BC7 bc7_encode bc7_r2k
-python tools/summarize_profile.py r02_bc7_final gpurun_out/bc7_r2k.ncu-rep 151552 gpurun_out/launches.csv bc7 > /dev/null
-python bench.py --impl reference 2>&1 | tail -1 > gpurun_out/bench_ref.json
-python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench.json
-python -c "
-import json
-b=json.load(open('gpurun_out/bench.json'))
-print(b['value'], b['e2e']['value'], b['roofline']['frac'], b['latency_8block_ms'], b['latency_ms_by_blocks_per_call'])
-for k,v in b['other_configs'].items(): print(k, v['value'], v['e2e']['value'], v['roofline']['frac'], v['latency_8block_ms'], v['cpu_baseline']['bit_exact_vs_gpu'])
-print(b['strong']['value'])
-"
+python -m pytest tests/test_bc6h_gpu.py -q -m gpu -x 2>&1 | tail -3
+python tools/time_small_calls.py BC6HU 8 64 512 1536 4096 8192 16384 32768 | cut -c1-420 | tee gpurun_out/bc6h_seed.txt
+CVTTB200_BC6H_SEED=0 python tools/time_small_calls.py BC6HU 8 64 512 1536 4096 8192 16384 32768 | cut -c1-420 | tee -a gpurun_out/bc6h_seed.txt
+python tools/time_small_calls.py BC6HS 512 4096 16384 | cut -c1-300 | tee -a gpurun_out/bc6h_seed.txt
+CVTTB200_BC6H_SEED=0 python tools/time_small_calls.py BC6HS 512 4096 16384 | cut -c1-300 | tee -a gpurun_out/bc6h_seed.txt
