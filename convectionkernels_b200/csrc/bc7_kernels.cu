@@ -554,11 +554,13 @@ namespace cvttb200
         // and dropped: 11 or 12 warps per CTA over whole waves (7.57 against 7.80 Mblocks/s: warps are bound to schedulers and
         // three of the four still carry three warps), and a last wave of light CTAs with 3-6 working warps each (no change at
         // 1 048 576 blocks, 3 % slower at 524 288).
-        // Calls of less than one wave that are not sliced: CTAs of fewer working warps, one CTA on every SM (32 768 blocks: 148
-        // CTAs of 7 working warps instead of 86 of 12)
+        // Calls of half a wave to one wave that are not sliced: CTAs of fewer working warps, one CTA on every SM (32 768 blocks: 148
+        // CTAs of 7 working warps instead of 86 of 12).  Not below half a wave: a CTA takes a whole SM whatever its working
+        // warps, so spreading a small call would keep concurrent callers' launches from running side by side
+        // (tests/test_concurrency_gpu.py), and with fewer than six warps per SM a warp is no faster anyway.
         static const long spreadOverride = getenv("CVTTB200_BC7_SPREAD") ? atol(getenv("CVTTB200_BC7_SPREAD")) : -1;    // A/B: 0 = always 12 warps
         unsigned mainWarpsPerCta = ctaWarps;
-        if (mainCtas && !sliced && mainCtas < numSMs && spreadOverride != 0)
+        if (mainCtas && !sliced && mainCtas < numSMs && 2 * mainCtas > numSMs && spreadOverride != 0)
         {
             mainWarpsPerCta = std::max(1u, (warps + numSMs - 1) / numSMs);
             mainCtas = (warps + mainWarpsPerCta - 1) / mainWarpsPerCta;
