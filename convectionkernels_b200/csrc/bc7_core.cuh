@@ -77,7 +77,7 @@ namespace cvttb200
     };
 
     // Command stream opcodes (built by bc7_plan.cpp)
-    enum { kCmdEnd = 0, kCmdShape = 1, kCmdEval = 2, kCmdDual = 3, kCmdPair2 = 4 };
+    enum { kCmdEnd = 0, kCmdShape = 1, kCmdEval = 2, kCmdDual = 3, kCmdPair2 = 4, kCmdTriple = 5 };
     enum { kBC7MaxSlots = 184 };
 
     // lexicographic order of the reference's commit sequence: modes 0,1,2,3,6,7 (TrySinglePlane) then 4,5 (TryDualPlane)
@@ -1500,6 +1500,8 @@ namespace cvttb200
     // for the tasks of all of them.  A partition leaves 4-6 chunks of tasks for the 12 warps of a CTA, so two partitions'
     // tasks run in the time of one (a block's best is then one partition stale when the second one's wants are decided).
     enum { kBC7PairGroup = 2, kBC7PairClassesPerCommand = 6, kBC7PairClasses = kBC7PairGroup * kBC7PairClassesPerCommand };
+    // TRIPLE commands (three-subset modes 0 / 2, one partition each) form groups of four: class = command * 2 + run
+    enum { kBC7TripleGroup = 4 };
 
     struct BC7SoloExchange
     {
@@ -1521,6 +1523,10 @@ namespace cvttb200
         CVTT_HD void post(int, int cls, const F4 &r) { posted[cls] = r; }
         CVTT_HD void sync() {}
         CVTT_HD F4 result(int cls) const { return posted[cls]; }
+        // TRIPLE commands post two words per class (classes 0 .. kBC7TripleGroup * 2 - 1)
+        F4 posted2[kBC7PairClasses][2];
+        CVTT_HD void post2(int, int cls, const F4 &a, const F4 &b) { posted2[cls][0] = a; posted2[cls][1] = b; }
+        CVTT_HD void result2(int cls, F4 &a, F4 &b) const { a = posted2[cls][0]; b = posted2[cls][1]; }
     };
 
     // Second half of a group of PAIR2 commands: runs the task slots dealt to this thread.  pcs point at the commands; class =
@@ -1573,6 +1579,62 @@ namespace cvttb200
                 res.z = as_float(best.e0);
                 res.w = as_float(best.e1);
                 ex.post(owner, cls, res);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // TRIPLE commands (three-subset modes 0 / 2, one partition): the partition's LARGEST subset (the anchor) has been searched
+    // for every block by a SHAPE command; the other two subsets are searched only for the blocks whose anchor error leaves
+    // room below their best (total = sum of three non-negative errors >= the anchor's, fl(a + b) monotonic), as tasks dealt out
+    // to the warps of the CTA exactly like the second halves of PAIR2 commands.  Per block 95-99 % of them are dead.
+    //   w0: TRIPLE | runs << 8 | anchor subset << 16 | B listed << 18 | C listed << 19 | partition << 24
+    //   w1: mask of subset B | pixels << 16 | subset number << 24;   w2: the same for subset C
+    //   run word: mode | seeds of B << 4 | seeds of C << 8 | result slot of the anchor << 16
+    // A task posts (err B, err C) and (B endpoints, C endpoints).
+    template<bool FAST, int STRIDE, class Exchange>
+    CVTT_HD void bc7_triple_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *const *pcs, int total)
+    {
+        for (int slot = ex.first_slot(); ex.chunk_in_range(slot, total); slot += ex.slot_stride())
+        {
+            int cls, owner;
+            ex.task(slot, cls, owner);
+            const bool hasTask = owner >= 0;
+            if (!ex.task_any(hasTask))
+                continue;
+            const uint32_t *pc = pcs[(cls >> 1) & (kBC7TripleGroup - 1)];
+            const uint32_t w0 = pc[0], rw = pc[3 + (cls & 1)];
+            const int mode = rw & 0xf;
+            BC7Lane<STRIDE> LB = L;
+            LB.raw = ex.owner_raw(hasTask ? owner : 0);
+            BC7ShapeBest found[2];
+            for (int half = 0; half < 2; half++)
+            {
+                const uint32_t w = pc[1 + half];
+                const int n = (w >> 16) & 0xff, seeds = (rw >> (4 + 4 * half)) & 0xf;
+                const bool listed = (w0 >> (18 + half)) & 1;
+                float sumV[4], accA;
+                bc7_gather<STRIDE>(LB, w & 0xffffu, 0, P.w, sumV, accA);
+                const float staticAlphaError = (P.flags & kFlag_Uniform) ? accA : fmul(accA, P.wSq[3]);
+                float baseRGB[3], offsRGB[3], baseRGBA[4], offsRGBA[4];
+                // only blocks whose group allows the RGB modes have tasks
+                bc7_shape_fits<STRIDE>(P, L.gw, n, listed, false, false, true, false, true, false, baseRGB, offsRGB, baseRGBA, offsRGBA);
+                if (mode == 0)
+                    bc7_shape_trials<0, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, found[half]);
+                else
+                    bc7_shape_trials<2, FAST, STRIDE>(P, L.gv, L.gw, n, seeds, baseRGB, offsRGB, sumV, staticAlphaError, found[half]);
+            }
+            if (hasTask)
+            {
+                F4 e, ep;
+                e.x = found[0].err;
+                e.y = found[1].err;
+                e.z = e.w = 0.0f;
+                ep.x = as_float(found[0].e0);
+                ep.y = as_float(found[0].e1);
+                ep.z = as_float(found[1].e0);
+                ep.w = as_float(found[1].e1);
+                ex.post2(owner, cls, e, ep);
             }
         }
     }
@@ -1680,6 +1742,23 @@ namespace cvttb200
                     ex.publish(0u);
                     const int total = ex.compact(0u);
                     bc7_pair2_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
+                    ex.sync();
+                    continue;
+                }
+                if (op == kCmdTriple)
+                {
+                    const uint32_t *pcs[kBC7TripleGroup];
+                    int commands = 0;
+                    while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple)
+                    {
+                        pcs[commands++] = pc;
+                        pc += 3 + (int)((pc[0] >> 8) & 0xff);
+                    }
+                    for (int k = commands; k < kBC7TripleGroup; k++)
+                        pcs[k] = pcs[0];
+                    ex.publish(0u);
+                    const int total = ex.compact(0u);
+                    bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
                     ex.sync();
                     continue;
                 }
@@ -1898,6 +1977,80 @@ namespace cvttb200
                             work.ep[sA][1] = epA[k][r][1];
                             work.ep[sB][0] = as_uint(got.z);
                             work.ep[sB][1] = as_uint(got.w);
+                            work.sc[0] = work.sc[1] = work.sc[2] = 0;
+                        }
+                    }
+                }
+            }
+            else if (op == kCmdTriple)
+            {
+                const uint32_t *pcs[kBC7TripleGroup];
+                float errA[kBC7TripleGroup][2];
+                uint32_t epA[kBC7TripleGroup][2][2];
+                uint32_t wantMask = 0;                              // bit (command * 2 + run)
+                int commands = 0;
+                while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple)
+                {
+                    const int k = commands++;
+                    pcs[k] = pc;
+                    const int nRuns = (pc[0] >> 8) & 0xff;
+                    for (int r = 0; r < 2; r++)
+                    {
+                        errA[k][r] = FLT_MAX;
+                        epA[k][r][0] = epA[k][r][1] = 0;
+                    }
+                    for (int r = 0; r < nRuns; r++)
+                    {
+                        const int slotA = (pc[3 + r] >> 16) & 0xff;
+                        const float e = as_float(res[slotA][0]);
+                        // the lane condition of the partition scan (BC67.cpp:1602-1634) and room below the best
+                        if (lf.warpAnyRGB && lf.allowRGBModes && !(e > work.error))
+                        {
+                            errA[k][r] = e;
+                            epA[k][r][0] = res[slotA][1];
+                            epA[k][r][1] = res[slotA][2];
+                            wantMask |= 1u << (k * 2 + r);
+                        }
+                    }
+                    pc += 3 + nRuns;
+                }
+                for (int k = commands; k < kBC7TripleGroup; k++)
+                    pcs[k] = pcs[0];
+                ex.publish((lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
+                const int total = ex.compact(wantMask);
+                bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
+                ex.sync();
+                for (int k = 0; k < commands; k++)
+                {
+                    const uint32_t c0 = pcs[k][0];
+                    const int nRuns = (c0 >> 8) & 0xff, partition = (c0 >> 24) & 0x3f, sA = (c0 >> 16) & 3;
+                    const int sB = (pcs[k][1] >> 24) & 3, sC = (pcs[k][2] >> 24) & 3;
+                    for (int r = 0; r < nRuns; r++)
+                    {
+                        const int cls = k * 2 + r;
+                        if (!((wantMask >> cls) & 1u))
+                            continue;
+                        const int mode = pcs[k][3 + r] & 0xf;
+                        F4 e, ep;
+                        ex.result2(cls, e, ep);
+                        float errs[3];
+                        errs[sA] = errA[k][r];
+                        errs[sB] = e.x;
+                        errs[sC] = e.y;
+                        const float totalError = fadd(fadd(errs[0], errs[1]), errs[2]);       // EVAL's order: subset 0 + 1 + 2
+                        const int key = bc7_mode_order(mode) * 64 + partition;
+                        if (totalError < work.error || (totalError == work.error && key < work.key))
+                        {
+                            work.error = totalError;
+                            work.key = key;
+                            work.mode = mode;
+                            work.sub = partition;
+                            work.ep[sA][0] = epA[k][r][0];
+                            work.ep[sA][1] = epA[k][r][1];
+                            work.ep[sB][0] = as_uint(ep.x);
+                            work.ep[sB][1] = as_uint(ep.y);
+                            work.ep[sC][0] = as_uint(ep.z);
+                            work.ep[sC][1] = as_uint(ep.w);
                             work.sc[0] = work.sc[1] = work.sc[2] = 0;
                         }
                     }

@@ -159,6 +159,8 @@ namespace cvttb200
         // PAIR2: search subset B of the modes with four parity combinations (3, 7) as two tasks of one parity pair each
         // (shorter task phases, the subset's fit is repeated) or as one
         const bool kBC7SplitWideRuns = true;
+        // pair form: three-subset modes as SHAPE commands for the anchors + TRIPLE commands (A/B: CVTTB200_BC7_TRIPLE=0 keeps SHAPE / EVAL)
+        const bool kBC7TripleCommands = getenv("CVTTB200_BC7_TRIPLE") ? atoi(getenv("CVTTB200_BC7_TRIPLE")) != 0 : true;
 
         void emit_shape(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, int shape, const std::vector<Run> &runs)
         {
@@ -376,6 +378,58 @@ namespace cvttb200
                 enabled[1][p] = ((plan.mode2PartitionEnabled >> p) & 1) && searched;
             }
             int nextSlot = 6;
+            if (pairCommands && kBC7TripleCommands)
+            {
+                // TRIPLE commands (bc7_core.cuh): only each partition's largest subset, the anchor, is searched for every block
+                int anchor[64];
+                for (int p = 0; p < 64; p++)
+                {
+                    anchor[p] = 0;
+                    for (int k = 1; k < 3; k++)
+                        if (popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + k]]) > popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + anchor[p]]]))
+                            anchor[p] = k;
+                    for (int m = 0; m < 2; m++)
+                        if (enabled[m][p])
+                            slotOf[m][kBC7Shapes3[p * 3 + anchor[p]]] = 0;
+                }
+                for (int shape = 0; shape < 243; shape++)
+                {
+                    std::vector<Run> runs;
+                    if (slotOf[0][shape] == 0)
+                        runs.push_back(Run{ 0, spRGB[shape], slotOf[0][shape] = nextSlot++ });
+                    if (slotOf[1][shape] == 0)
+                        runs.push_back(Run{ 2, spRGB[shape], slotOf[1][shape] = nextSlot++ });
+                    if (!runs.empty())
+                        emit_shape(cmds, plan, shape, runs);
+                }
+                for (int p = 0; p < 64; p++)
+                {
+                    if (!enabled[0][p] && !enabled[1][p])
+                        continue;
+                    int others[2], n = 0;
+                    for (int k = 0; k < 3; k++)
+                        if (k != anchor[p])
+                            others[n++] = k;
+                    const int shapeA = kBC7Shapes3[p * 3 + anchor[p]], shapeB = kBC7Shapes3[p * 3 + others[0]], shapeC = kBC7Shapes3[p * 3 + others[1]];
+                    bool listedB = false, listedC = false;
+                    for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
+                    {
+                        listedB |= (plan.rgbShapeList[i] == shapeB);
+                        listedC |= (plan.rgbShapeList[i] == shapeC);
+                    }
+                    const int nRuns = (enabled[0][p] ? 1 : 0) + (enabled[1][p] ? 1 : 0);
+                    cmds.push_back(kCmdTriple | ((uint32_t)nRuns << 8) | ((uint32_t)anchor[p] << 16) | ((uint32_t)listedB << 18) | ((uint32_t)listedC << 19) | ((uint32_t)p << 24));
+                    cmds.push_back(kBC7ShapeMask[shapeB] | ((uint32_t)popcount16(kBC7ShapeMask[shapeB]) << 16) | ((uint32_t)others[0] << 24));
+                    cmds.push_back(kBC7ShapeMask[shapeC] | ((uint32_t)popcount16(kBC7ShapeMask[shapeC]) << 16) | ((uint32_t)others[1] << 24));
+                    for (int m = 0; m < 2; m++)
+                        if (enabled[m][p])
+                            cmds.push_back((uint32_t)(m ? 2 : 0) | ((uint32_t)std::min<int>(spRGB[shapeB], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapeC], 4) << 8) |
+                                           ((uint32_t)slotOf[m][shapeA] << 16));
+                }
+                maxSlot = std::max(maxSlot, nextSlot);
+            }
+            else
+            {
             for (int m = 0; m < 2; m++)
                 for (int p = 0; p < 64; p++)
                     if (enabled[m][p])
@@ -399,6 +453,7 @@ namespace cvttb200
                         emit_eval(cmds, m ? 2 : 0, p, 3, slots);
                     }
             maxSlot = std::max(maxSlot, nextSlot);
+            }
         }
 
         // Two-subset modes 1, 3, 7, partition-major: every two-subset shape belongs to exactly one partition.  A (mode,

@@ -106,6 +106,22 @@ namespace
         __device__ __forceinline__ void post(int owner, int cls, const F4 &r) { *slot_of(owner, cls) = r; }
         __device__ __forceinline__ void sync() { __syncthreads(); }
         __device__ __forceinline__ F4 result(int cls) const { return *slot_of((int)tid, cls); }
+        // TRIPLE commands: two words per class, classes 0 .. 7 -> entries 8 .. 15 of gv, then of gw (the subsets a task gathers
+        // have at most 7 pixels)
+        __device__ __forceinline__ F4 *slot2_of(int owner, int word) const
+        {
+            return (word < 8 ? gvBase + (8 + word) * kBC7Threads : gwBase + word * kBC7Threads) + owner;
+        }
+        __device__ __forceinline__ void post2(int owner, int cls, const F4 &a, const F4 &b)
+        {
+            *slot2_of(owner, 2 * cls) = a;
+            *slot2_of(owner, 2 * cls + 1) = b;
+        }
+        __device__ __forceinline__ void result2(int cls, F4 &a, F4 &b) const
+        {
+            a = *slot2_of((int)tid, 2 * cls);
+            b = *slot2_of((int)tid, 2 * cls + 1);
+        }
     };
 
     // Pre-pass: sorts the reference groups (8 consecutive blocks = one reference call) into three classes by the two
