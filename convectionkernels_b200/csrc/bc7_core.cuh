@@ -1984,9 +1984,8 @@ namespace cvttb200
             }
             else if (op == kCmdTriple)
             {
+                // the anchors' results stay in their slots: nothing but the wanted classes is carried across the task phase
                 const uint32_t *pcs[kBC7TripleGroup];
-                float errA[kBC7TripleGroup][2];
-                uint32_t epA[kBC7TripleGroup][2][2];
                 uint32_t wantMask = 0;                              // bit (command * 2 + run)
                 int commands = 0;
                 while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple)
@@ -1994,23 +1993,12 @@ namespace cvttb200
                     const int k = commands++;
                     pcs[k] = pc;
                     const int nRuns = (pc[0] >> 8) & 0xff;
-                    for (int r = 0; r < 2; r++)
-                    {
-                        errA[k][r] = FLT_MAX;
-                        epA[k][r][0] = epA[k][r][1] = 0;
-                    }
                     for (int r = 0; r < nRuns; r++)
                     {
-                        const int slotA = (pc[3 + r] >> 16) & 0xff;
-                        const float e = as_float(res[slotA][0]);
+                        const float e = as_float(res[(pc[3 + r] >> 16) & 0xff][0]);
                         // the lane condition of the partition scan (BC67.cpp:1602-1634) and room below the best
                         if (lf.warpAnyRGB && lf.allowRGBModes && !(e > work.error))
-                        {
-                            errA[k][r] = e;
-                            epA[k][r][0] = res[slotA][1];
-                            epA[k][r][1] = res[slotA][2];
                             wantMask |= 1u << (k * 2 + r);
-                        }
                     }
                     pc += 3 + nRuns;
                 }
@@ -2020,39 +2008,33 @@ namespace cvttb200
                 const int total = ex.compact(wantMask);
                 bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
                 ex.sync();
-                for (int k = 0; k < commands; k++)
+                for (uint32_t m = wantMask; m; m &= m - 1)
                 {
-                    const uint32_t c0 = pcs[k][0];
-                    const int nRuns = (c0 >> 8) & 0xff, partition = (c0 >> 24) & 0x3f, sA = (c0 >> 16) & 3;
-                    const int sB = (pcs[k][1] >> 24) & 3, sC = (pcs[k][2] >> 24) & 3;
-                    for (int r = 0; r < nRuns; r++)
+                    const int cls = ctz32(m), k = cls >> 1, r = cls & 1;
+                    const uint32_t c0 = pcs[k][0], rw = pcs[k][3 + r];
+                    const int partition = (c0 >> 24) & 0x3f, sA = (c0 >> 16) & 3, sB = (pcs[k][1] >> 24) & 3, sC = (pcs[k][2] >> 24) & 3;
+                    const int mode = rw & 0xf, slotA = (rw >> 16) & 0xff;
+                    F4 e, ep;
+                    ex.result2(cls, e, ep);
+                    float errs[3];
+                    errs[sA] = as_float(res[slotA][0]);
+                    errs[sB] = e.x;
+                    errs[sC] = e.y;
+                    const float totalError = fadd(fadd(errs[0], errs[1]), errs[2]);       // EVAL's order: subset 0 + 1 + 2
+                    const int key = bc7_mode_order(mode) * 64 + partition;
+                    if (totalError < work.error || (totalError == work.error && key < work.key))
                     {
-                        const int cls = k * 2 + r;
-                        if (!((wantMask >> cls) & 1u))
-                            continue;
-                        const int mode = pcs[k][3 + r] & 0xf;
-                        F4 e, ep;
-                        ex.result2(cls, e, ep);
-                        float errs[3];
-                        errs[sA] = errA[k][r];
-                        errs[sB] = e.x;
-                        errs[sC] = e.y;
-                        const float totalError = fadd(fadd(errs[0], errs[1]), errs[2]);       // EVAL's order: subset 0 + 1 + 2
-                        const int key = bc7_mode_order(mode) * 64 + partition;
-                        if (totalError < work.error || (totalError == work.error && key < work.key))
-                        {
-                            work.error = totalError;
-                            work.key = key;
-                            work.mode = mode;
-                            work.sub = partition;
-                            work.ep[sA][0] = epA[k][r][0];
-                            work.ep[sA][1] = epA[k][r][1];
-                            work.ep[sB][0] = as_uint(ep.x);
-                            work.ep[sB][1] = as_uint(ep.y);
-                            work.ep[sC][0] = as_uint(ep.z);
-                            work.ep[sC][1] = as_uint(ep.w);
-                            work.sc[0] = work.sc[1] = work.sc[2] = 0;
-                        }
+                        work.error = totalError;
+                        work.key = key;
+                        work.mode = mode;
+                        work.sub = partition;
+                        work.ep[sA][0] = res[slotA][1];
+                        work.ep[sA][1] = res[slotA][2];
+                        work.ep[sB][0] = as_uint(ep.x);
+                        work.ep[sB][1] = as_uint(ep.y);
+                        work.ep[sC][0] = as_uint(ep.z);
+                        work.ep[sC][1] = as_uint(ep.w);
+                        work.sc[0] = work.sc[1] = work.sc[2] = 0;
                     }
                 }
             }
