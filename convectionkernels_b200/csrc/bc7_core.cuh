@@ -1881,9 +1881,9 @@ namespace cvttb200
                 // terms and fl(a + b) is monotonic), so a block whose err(A) already exceeds its best cannot take this
                 // (mode, partition) whatever B gives -- the reference evaluates it and rejects it.  Consecutive commands form a
                 // group (kBC7PairGroup): first halves back to back, one exchange for the second halves of all of them.
+                // The first halves' results wait in result slots 0 .. 5 (free in this stream form once mode 6 has been scanned):
+                // nothing but the wanted classes is carried in registers across the task phase.
                 const uint32_t *pcs[kBC7PairGroup];
-                float errA[kBC7PairGroup][3];
-                uint32_t epA[kBC7PairGroup][3][2];
                 uint32_t wantMask = 0;                              // bit (command * 6 + run * 2 + unit)
                 int commands = 0;
                 while (commands < kBC7PairGroup && (pc[0] & 0xff) == kCmdPair2)
@@ -1906,11 +1906,6 @@ namespace cvttb200
                     bc7_shape_fits<STRIDE>(P, L.gw, nA, listedRGB, listedRGBA, needRGBA, lf.allowRGBModes, usePCA4, lf.warpAnyRGB, lf.warpAnyPCA4, baseRGB, offsRGB, baseRGBA, offsRGBA);
 
                     const bool split = (c0 >> 22) & 1;
-                    for (int r = 0; r < 3; r++)
-                    {
-                        errA[k][r] = FLT_MAX;
-                        epA[k][r][0] = epA[k][r][1] = 0;
-                    }
                     for (int r = 0; r < nRuns; r++)
                     {
                         const uint32_t rw = pc[3 + r];
@@ -1931,9 +1926,9 @@ namespace cvttb200
                         }
                         if (eligible && !(best.err > work.error))
                         {
-                            errA[k][r] = best.err;
-                            epA[k][r][0] = best.e0;
-                            epA[k][r][1] = best.e1;
+                            res[k * 3 + r][0] = as_uint(best.err);
+                            res[k * 3 + r][1] = best.e0;
+                            res[k * 3 + r][2] = best.e1;
                             wantMask |= ((mode != 1 && split) ? 3u : 1u) << (k * kBC7PairClassesPerCommand + 2 * r);
                         }
                     }
@@ -1964,7 +1959,8 @@ namespace cvttb200
                             if (other.x < got.x || (other.x == got.x && (int)as_uint(other.y) < (int)as_uint(got.y)))
                                 got = other;
                         }
-                        const float totalError = aIsSubset1 ? fadd(got.x, errA[k][r]) : fadd(errA[k][r], got.x);       // subset 0 + subset 1
+                        const float errA = as_float(res[k * 3 + r][0]);
+                        const float totalError = aIsSubset1 ? fadd(got.x, errA) : fadd(errA, got.x);       // subset 0 + subset 1
                         const int key = bc7_mode_order(mode) * 64 + partition;
                         if (totalError < work.error || (totalError == work.error && key < work.key))
                         {
@@ -1973,8 +1969,8 @@ namespace cvttb200
                             work.mode = mode;
                             work.sub = partition;
                             const int sA = aIsSubset1 ? 1 : 0, sB = 1 - sA;
-                            work.ep[sA][0] = epA[k][r][0];
-                            work.ep[sA][1] = epA[k][r][1];
+                            work.ep[sA][0] = res[k * 3 + r][1];
+                            work.ep[sA][1] = res[k * 3 + r][2];
                             work.ep[sB][0] = as_uint(got.z);
                             work.ep[sB][1] = as_uint(got.w);
                             work.sc[0] = work.sc[1] = work.sc[2] = 0;
