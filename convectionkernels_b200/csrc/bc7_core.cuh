@@ -1500,8 +1500,9 @@ namespace cvttb200
     // for the tasks of all of them.  A partition leaves 4-6 chunks of tasks for the 12 warps of a CTA, so two partitions'
     // tasks run in the time of one (a block's best is then one partition stale when the second one's wants are decided).
     enum { kBC7PairGroup = 2, kBC7PairClassesPerCommand = 6, kBC7PairClasses = kBC7PairGroup * kBC7PairClassesPerCommand };
-    // TRIPLE commands (three-subset modes 0 / 2, one partition each) form groups of four: class = command * 2 + run
-    enum { kBC7TripleGroup = 4 };
+    // TRIPLE commands (three-subset modes 0 / 2, one partition each) form groups of up to eight commands with up to eight runs
+    // between them: class = the run's number in the group (a nibble map gives command and run back)
+    enum { kBC7TripleGroup = 8, kBC7TripleClasses = 8 };
 
     struct BC7SoloExchange
     {
@@ -1523,7 +1524,7 @@ namespace cvttb200
         CVTT_HD void post(int, int cls, const F4 &r) { posted[cls] = r; }
         CVTT_HD void sync() {}
         CVTT_HD F4 result(int cls) const { return posted[cls]; }
-        // TRIPLE commands post two words per class (classes 0 .. kBC7TripleGroup * 2 - 1)
+        // TRIPLE commands post two words per class (classes 0 .. kBC7TripleClasses - 1)
         F4 posted2[kBC7PairClasses][2];
         CVTT_HD void post2(int, int cls, const F4 &a, const F4 &b) { posted2[cls][0] = a; posted2[cls][1] = b; }
         CVTT_HD void result2(int cls, F4 &a, F4 &b) const { a = posted2[cls][0]; b = posted2[cls][1]; }
@@ -1593,7 +1594,7 @@ namespace cvttb200
     //   run word: mode | seeds of B << 4 | seeds of C << 8 | result slot of the anchor << 16
     // A task posts (err B, err C) and (B endpoints, C endpoints).
     template<bool FAST, int STRIDE, class Exchange>
-    CVTT_HD void bc7_triple_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *const *pcs, int total)
+    CVTT_HD void bc7_triple_tasks(const BC7Params &P, const BC7Lane<STRIDE> &L, Exchange &ex, const uint32_t *const *pcs, uint32_t classMap, int total)
     {
         for (int slot = ex.first_slot(); ex.chunk_in_range(slot, total); slot += ex.slot_stride())
         {
@@ -1602,8 +1603,9 @@ namespace cvttb200
             const bool hasTask = owner >= 0;
             if (!ex.task_any(hasTask))
                 continue;
-            const uint32_t *pc = pcs[(cls >> 1) & (kBC7TripleGroup - 1)];
-            const uint32_t w0 = pc[0], rw = pc[3 + (cls & 1)];
+            const uint32_t entry = (classMap >> (4 * (cls & (kBC7TripleClasses - 1)))) & 15u;      // command << 1 | run
+            const uint32_t *pc = pcs[entry >> 1];
+            const uint32_t w0 = pc[0], rw = pc[3 + (entry & 1u)];
             const int mode = rw & 0xf;
             BC7Lane<STRIDE> LB = L;
             LB.raw = ex.owner_raw(hasTask ? owner : 0);
@@ -1748,17 +1750,21 @@ namespace cvttb200
                 if (op == kCmdTriple)
                 {
                     const uint32_t *pcs[kBC7TripleGroup];
-                    int commands = 0;
-                    while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple)
+                    uint32_t classMap = 0;
+                    int commands = 0, classes = 0;
+                    while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple && classes + (int)((pc[0] >> 8) & 0xff) <= kBC7TripleClasses)
                     {
+                        const int nRuns = (pc[0] >> 8) & 0xff;
+                        for (int r = 0; r < nRuns; r++)
+                            classMap |= (uint32_t)(commands * 2 + r) << (4 * classes++);
                         pcs[commands++] = pc;
-                        pc += 3 + (int)((pc[0] >> 8) & 0xff);
+                        pc += 3 + nRuns;
                     }
                     for (int k = commands; k < kBC7TripleGroup; k++)
                         pcs[k] = pcs[0];
                     ex.publish(0u);
                     const int total = ex.compact(0u);
-                    bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
+                    bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, classMap, total);
                     ex.sync();
                     continue;
                 }
@@ -1982,31 +1988,33 @@ namespace cvttb200
             {
                 // the anchors' results stay in their slots: nothing but the wanted classes is carried across the task phase
                 const uint32_t *pcs[kBC7TripleGroup];
-                uint32_t wantMask = 0;                              // bit (command * 2 + run)
-                int commands = 0;
-                while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple)
+                uint32_t wantMask = 0, classMap = 0;                // bit (class); nibble (class) = command << 1 | run
+                int commands = 0, classes = 0;
+                while (commands < kBC7TripleGroup && (pc[0] & 0xff) == kCmdTriple && classes + (int)((pc[0] >> 8) & 0xff) <= kBC7TripleClasses)
                 {
-                    const int k = commands++;
-                    pcs[k] = pc;
                     const int nRuns = (pc[0] >> 8) & 0xff;
                     for (int r = 0; r < nRuns; r++)
                     {
                         const float e = as_float(res[(pc[3 + r] >> 16) & 0xff][0]);
                         // the lane condition of the partition scan (BC67.cpp:1602-1634) and room below the best
                         if (lf.warpAnyRGB && lf.allowRGBModes && !(e > work.error))
-                            wantMask |= 1u << (k * 2 + r);
+                            wantMask |= 1u << classes;
+                        classMap |= (uint32_t)(commands * 2 + r) << (4 * classes++);
                     }
+                    pcs[commands++] = pc;
                     pc += 3 + nRuns;
                 }
                 for (int k = commands; k < kBC7TripleGroup; k++)
                     pcs[k] = pcs[0];
                 ex.publish((lf.allowRGBModes ? 1u : 0u) | (usePCA4 ? 2u : 0u));
                 const int total = ex.compact(wantMask);
-                bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, total);
+                bc7_triple_tasks<FAST, STRIDE>(P, L, ex, pcs, classMap, total);
                 ex.sync();
                 for (uint32_t m = wantMask; m; m &= m - 1)
                 {
-                    const int cls = ctz32(m), k = cls >> 1, r = cls & 1;
+                    const int cls = ctz32(m);
+                    const uint32_t entry = (classMap >> (4 * cls)) & 15u;
+                    const int k = (int)(entry >> 1), r = (int)(entry & 1u);
                     const uint32_t c0 = pcs[k][0], rw = pcs[k][3 + r];
                     const int partition = (c0 >> 24) & 0x3f, sA = (c0 >> 16) & 3, sB = (pcs[k][1] >> 24) & 3, sC = (pcs[k][2] >> 24) & 3;
                     const int mode = rw & 0xf, slotA = (rw >> 16) & 0xff;
