@@ -217,15 +217,80 @@ namespace cvttb200
         }
     }
 
+    // index (0..2) of the partition's largest subset, the anchor of its TRIPLE command (the first one on ties)
+    static int triple_anchor(int p)
+    {
+        int a = 0;
+        for (int k = 1; k < 3; k++)
+            if (popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + k]]) > popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + a]]))
+                a = k;
+        return a;
+    }
+
+    // one TRIPLE command (bc7_core.cuh); slotA0 / slotA2: the result slots of the anchor's mode-0 / mode-2 search
+    static void emit_triple(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, int p, bool m0, bool m2, int slotA0, int slotA2)
+    {
+        const uint8_t *spRGB = plan.seedPointsForShapeRGB;
+        const int anchor = triple_anchor(p);
+        int others[2], n = 0;
+        for (int k = 0; k < 3; k++)
+            if (k != anchor)
+                others[n++] = k;
+        const int shapeB = kBC7Shapes3[p * 3 + others[0]], shapeC = kBC7Shapes3[p * 3 + others[1]];
+        bool listedB = false, listedC = false;
+        for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
+        {
+            listedB |= (plan.rgbShapeList[i] == shapeB);
+            listedC |= (plan.rgbShapeList[i] == shapeC);
+        }
+        const int nRuns = (m0 ? 1 : 0) + (m2 ? 1 : 0);
+        cmds.push_back(kCmdTriple | ((uint32_t)nRuns << 8) | ((uint32_t)anchor << 16) | ((uint32_t)listedB << 18) | ((uint32_t)listedC << 19) | ((uint32_t)p << 24));
+        cmds.push_back(kBC7ShapeMask[shapeB] | ((uint32_t)popcount16(kBC7ShapeMask[shapeB]) << 16) | ((uint32_t)others[0] << 24));
+        cmds.push_back(kBC7ShapeMask[shapeC] | ((uint32_t)popcount16(kBC7ShapeMask[shapeC]) << 16) | ((uint32_t)others[1] << 24));
+        const uint32_t seedWord = ((uint32_t)std::min<int>(spRGB[shapeB], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapeC], 4) << 8);
+        if (m0) cmds.push_back(0u | seedWord | ((uint32_t)slotA0 << 16));
+        if (m2) cmds.push_back(2u | seedWord | ((uint32_t)slotA2 << 16));
+    }
+
+    // SHAPE commands for the anchors of the given three-subset partitions (each distinct shape once, slots from nextSlot up),
+    // then their TRIPLE commands, adjacent so that the kernel takes them in groups
+    static void emit_three_subset_block(std::vector<uint32_t> &cmds, const BC7PlanPOD &plan, const bool enabled[2][64], int &nextSlot)
+    {
+        const uint8_t *spRGB = plan.seedPointsForShapeRGB;
+        int slotOf[2][243];
+        for (int i = 0; i < 243; i++)
+            slotOf[0][i] = slotOf[1][i] = -1;
+        for (int p = 0; p < 64; p++)
+            for (int m = 0; m < 2; m++)
+                if (enabled[m][p])
+                    slotOf[m][kBC7Shapes3[p * 3 + triple_anchor(p)]] = 0;
+        for (int shape = 0; shape < 243; shape++)
+        {
+            std::vector<Run> runs;
+            if (slotOf[0][shape] == 0)
+                runs.push_back(Run{ 0, spRGB[shape], slotOf[0][shape] = nextSlot++ });
+            if (slotOf[1][shape] == 0)
+                runs.push_back(Run{ 2, spRGB[shape], slotOf[1][shape] = nextSlot++ });
+            if (!runs.empty())
+                emit_shape(cmds, plan, shape, runs);
+        }
+        for (int p = 0; p < 64; p++)
+            if (enabled[0][p] || enabled[1][p])
+            {
+                const int shapeA = kBC7Shapes3[p * 3 + triple_anchor(p)];
+                emit_triple(cmds, plan, p, enabled[0][p], enabled[1][p], slotOf[0][shapeA], slotOf[1][shapeA]);
+            }
+    }
+
     // kBC7StreamSplit: the stream for SMALL calls.  The search of a block is dealt out to `slices` CTAs (on as many SMs) in
     // independent units -- mode 6, every mode-4/5 rotation, every two-subset partition (one PAIR2 command), every three-subset
-    // partition (its three shapes searched partition by partition through recycled slots, so that no unit reads another
-    // unit's results; shapes shared between partitions are searched once per partition that uses them).  Units go longest
-    // first to the least loaded slice.  Layout: cmds[s] = offset of slice s's sub-stream (each ends with END), s < slices.
-    // The launch reduces the slices' winners by (error, reference key): bc7_candidate_merge.
+    // partition (one TRIPLE command; the anchors of a slice's partitions are searched once per slice, in front of its TRIPLE
+    // commands, so no unit reads another slice's results).  Units go longest first to the least loaded slice.  Layout: cmds[s] =
+    // offset of slice s's sub-stream (each ends with END), s < slices.  The launch reduces the slices' winners by (error,
+    // reference key): bc7_candidate_merge.
     static int compile_split(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, int slices)
     {
-        struct Unit { int cost, kind; std::vector<uint32_t> words; };      // kind: 0 mode 6, 1 modes 4 / 5, 2 three subsets, 3 two subsets
+        struct Unit { int cost, kind, partition; bool m0, m2; std::vector<uint32_t> words; };      // kind: 0 mode 6, 1 modes 4 / 5, 2 three subsets, 3 two subsets
         std::vector<Unit> units;
         const uint8_t *spRGB = plan.seedPointsForShapeRGB, *spRGBA = plan.seedPointsForShapeRGBA;
         // trial passes of one shape: (parity combinations, two per pass) x seeds
@@ -279,21 +344,14 @@ namespace cvttb200
             const bool m2 = ((plan.mode2PartitionEnabled >> p) & 1) && searched;
             if (!m0 && !m2)
                 continue;
+            // its words are made per slice (below): the anchors of a slice's partitions are searched once, their TRIPLE commands follow
             Unit u;
-            u.cost = 24;
             u.kind = 2;
-            int slots0[3], slots2[3];
-            for (int k = 0; k < 3; k++)
-            {
-                const int shape = kBC7Shapes3[p * 3 + k];
-                std::vector<Run> runs;
-                if (m0) runs.push_back(Run{ 0, spRGB[shape], slots0[k] = 6 + 2 * k });
-                if (m2) runs.push_back(Run{ 2, spRGB[shape], slots2[k] = 7 + 2 * k });
-                emit_shape(u.words, plan, shape, runs);
-                u.cost += popcount16(kBC7ShapeMask[shape]) * ((m0 ? passes(0, spRGB[shape]) : 0) + (m2 ? passes(2, spRGB[shape]) : 0));
-            }
-            if (m0) emit_eval(u.words, 0, p, 3, slots0);
-            if (m2) emit_eval(u.words, 2, p, 3, slots2);
+            u.partition = p;
+            u.m0 = m0;
+            u.m2 = m2;
+            const int shapeA = kBC7Shapes3[p * 3 + triple_anchor(p)];
+            u.cost = 24 + popcount16(kBC7ShapeMask[shapeA]) * ((m0 ? passes(0, spRGB[shapeA]) : 0) + (m2 ? passes(2, spRGB[shapeA]) : 0)) * 5 / 4;
             units.push_back(u);
         }
 
@@ -314,11 +372,36 @@ namespace cvttb200
             assigned[slice].push_back(order[k]);
         }
         std::vector<std::vector<uint32_t> > streams((size_t)slices);
+        int maxSlot = 12;
         for (size_t s = 0; s < (size_t)slices; s++)
         {
             std::stable_sort(assigned[s].begin(), assigned[s].end(), [&](size_t a, size_t b) { return units[a].kind < units[b].kind; });
+            bool enabled[2][64];
+            memset(enabled, 0, sizeof(enabled));
+            bool anyThree = false, threeDone = false;
             for (size_t k = 0; k < assigned[s].size(); k++)
-                streams[s].insert(streams[s].end(), units[assigned[s][k]].words.begin(), units[assigned[s][k]].words.end());
+                if (units[assigned[s][k]].kind == 2)
+                {
+                    enabled[0][units[assigned[s][k]].partition] = units[assigned[s][k]].m0;
+                    enabled[1][units[assigned[s][k]].partition] = units[assigned[s][k]].m2;
+                    anyThree = true;
+                }
+            for (size_t k = 0; k < assigned[s].size(); k++)
+            {
+                const Unit &u = units[assigned[s][k]];
+                if (u.kind == 2)
+                {
+                    if (anyThree && !threeDone)
+                    {
+                        int nextSlot = 6;
+                        emit_three_subset_block(streams[s], plan, enabled, nextSlot);
+                        maxSlot = std::max(maxSlot, nextSlot);
+                        threeDone = true;
+                    }
+                    continue;
+                }
+                streams[s].insert(streams[s].end(), u.words.begin(), u.words.end());
+            }
         }
         cmds.assign((size_t)slices, 0u);
         for (size_t s = 0; s < (size_t)slices; s++)
@@ -327,7 +410,7 @@ namespace cvttb200
             cmds.insert(cmds.end(), streams[s].begin(), streams[s].end());
             cmds.push_back(kCmdEnd);
         }
-        return 12;
+        return maxSlot;
     }
 
     int bc7_compile_plan(const BC7PlanPOD &plan, std::vector<uint32_t> &cmds, int form, int slices)
@@ -381,51 +464,7 @@ namespace cvttb200
             if (pairCommands && kBC7TripleCommands)
             {
                 // TRIPLE commands (bc7_core.cuh): only each partition's largest subset, the anchor, is searched for every block
-                int anchor[64];
-                for (int p = 0; p < 64; p++)
-                {
-                    anchor[p] = 0;
-                    for (int k = 1; k < 3; k++)
-                        if (popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + k]]) > popcount16(kBC7ShapeMask[kBC7Shapes3[p * 3 + anchor[p]]]))
-                            anchor[p] = k;
-                    for (int m = 0; m < 2; m++)
-                        if (enabled[m][p])
-                            slotOf[m][kBC7Shapes3[p * 3 + anchor[p]]] = 0;
-                }
-                for (int shape = 0; shape < 243; shape++)
-                {
-                    std::vector<Run> runs;
-                    if (slotOf[0][shape] == 0)
-                        runs.push_back(Run{ 0, spRGB[shape], slotOf[0][shape] = nextSlot++ });
-                    if (slotOf[1][shape] == 0)
-                        runs.push_back(Run{ 2, spRGB[shape], slotOf[1][shape] = nextSlot++ });
-                    if (!runs.empty())
-                        emit_shape(cmds, plan, shape, runs);
-                }
-                for (int p = 0; p < 64; p++)
-                {
-                    if (!enabled[0][p] && !enabled[1][p])
-                        continue;
-                    int others[2], n = 0;
-                    for (int k = 0; k < 3; k++)
-                        if (k != anchor[p])
-                            others[n++] = k;
-                    const int shapeA = kBC7Shapes3[p * 3 + anchor[p]], shapeB = kBC7Shapes3[p * 3 + others[0]], shapeC = kBC7Shapes3[p * 3 + others[1]];
-                    bool listedB = false, listedC = false;
-                    for (int i = 0; i < plan.rgbNumShapesToEvaluate; i++)
-                    {
-                        listedB |= (plan.rgbShapeList[i] == shapeB);
-                        listedC |= (plan.rgbShapeList[i] == shapeC);
-                    }
-                    const int nRuns = (enabled[0][p] ? 1 : 0) + (enabled[1][p] ? 1 : 0);
-                    cmds.push_back(kCmdTriple | ((uint32_t)nRuns << 8) | ((uint32_t)anchor[p] << 16) | ((uint32_t)listedB << 18) | ((uint32_t)listedC << 19) | ((uint32_t)p << 24));
-                    cmds.push_back(kBC7ShapeMask[shapeB] | ((uint32_t)popcount16(kBC7ShapeMask[shapeB]) << 16) | ((uint32_t)others[0] << 24));
-                    cmds.push_back(kBC7ShapeMask[shapeC] | ((uint32_t)popcount16(kBC7ShapeMask[shapeC]) << 16) | ((uint32_t)others[1] << 24));
-                    for (int m = 0; m < 2; m++)
-                        if (enabled[m][p])
-                            cmds.push_back((uint32_t)(m ? 2 : 0) | ((uint32_t)std::min<int>(spRGB[shapeB], 4) << 4) | ((uint32_t)std::min<int>(spRGB[shapeC], 4) << 8) |
-                                           ((uint32_t)slotOf[m][shapeA] << 16));
-                }
+                emit_three_subset_block(cmds, plan, enabled, nextSlot);
                 maxSlot = std::max(maxSlot, nextSlot);
             }
             else
